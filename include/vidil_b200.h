@@ -1,0 +1,133 @@
+/*
+ * vidil_b200 — C ABI of the B200-native frame-encoding path of VidIL.
+ *
+ * One shared library (vidil_b200/_C/libvidil_b200.so), plain pointers and sizes only.  It replaces the
+ * arithmetic behind these reference call sites (paths relative to the VidIL repository):
+ *
+ *   models/vit.py:180-194        VisionTransformer.forward          -> vidil_vit_forward
+ *   models/blip.py:128, blip_itm.py:43   visual_encoder(image)      -> vidil_vit_forward
+ *   run_visual_tokenization.py:141-142   CLIPModel(**inputs).image_embeds -> vidil_clip_forward
+ *   run_visual_tokenization.py:276,306   image_embeds @ text_embeds.t(); np.argsort(...)[::-1][:k]
+ *                                                                    -> vidil_sim_topk
+ *
+ * Conventions
+ *   - Every function returns 0 on success, non-zero on failure; vidil_last_error() then returns a
+ *     NUL-terminated description (thread-local, valid until the next call on that thread).
+ *   - All *device* pointers are borrowed for the duration of the call only.  The library owns nothing
+ *     but the packed 16-bit weights inside an encoder handle.  No allocation happens in a forward call.
+ *   - Work is enqueued on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream) and the
+ *     call returns without synchronising, except the *_host variants, which synchronise before returning.
+ *   - One process per GPU; a handle is bound to the device that was current at creation and is not
+ *     thread-safe.
+ *   - There is no CPU fallback: on a machine without an sm_100 GPU every compute entry point fails.
+ */
+#ifndef VIDIL_B200_H_
+#define VIDIL_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VIDIL_B200_ABI_VERSION 1
+
+/* Tensor-core operand type.  Accumulation, LayerNorm/softmax statistics and the residual stream are fp32. */
+enum { VIDIL_DTYPE_BF16 = 0, VIDIL_DTYPE_FP16 = 1 };
+/* MLP activation: exact erf GELU (nn.GELU, vit.py:26) or CLIP's quick_gelu x*sigmoid(1.702x). */
+enum { VIDIL_ACT_GELU_ERF = 0, VIDIL_ACT_QUICK_GELU = 1 };
+
+/* Architecture of one vision tower.  BLIP ViT (models/blip.py:298-326): patch 16, patch_bias 1, pre_ln 0,
+ * ln_eps 1e-6, act GELU_ERF, proj_dim 0.  CLIP ViT-L/14: patch 14, patch_bias 0, pre_ln 1, ln_eps 1e-5,
+ * act QUICK_GELU, proj_dim 768. */
+typedef struct vidil_encoder_cfg {
+    int32_t img_size;    /* square input side, e.g. 224 or 384 */
+    int32_t patch_size;  /* 16 (BLIP) or 14 (CLIP); must be even and divide img_size */
+    int32_t embed_dim;   /* D: 768 or 1024 (multiple of 128, head_dim must be 64) */
+    int32_t depth;       /* number of transformer blocks */
+    int32_t num_heads;   /* D / 64 */
+    int32_t mlp_dim;     /* 4*D */
+    float   ln_eps;
+    int32_t act;         /* VIDIL_ACT_* */
+    int32_t patch_bias;  /* 1: patch conv has a bias */
+    int32_t pre_ln;      /* 1: LayerNorm after the position add (CLIP pre_layrnorm) */
+    int32_t proj_dim;    /* >0: CLS -> post LN -> bias-free projection to proj_dim -> L2 normalise (CLIP) */
+    int32_t dtype;       /* VIDIL_DTYPE_* */
+    int32_t cta_group;   /* 1 or 2: CTAs cooperating on one tcgen05 tile; 0 = library default (2) */
+} vidil_encoder_cfg;
+
+typedef struct vidil_encoder vidil_encoder;
+
+int32_t vidil_abi_version(void);
+const char* vidil_last_error(void);
+
+/* Number of CUDA kernels this library has launched in this process (all streams).  bench.py reads it
+ * before/after the timed region to report gpu_launches. */
+int64_t vidil_kernel_launch_count(void);
+
+/* ---- encoder handle -------------------------------------------------------------------------- */
+int32_t vidil_encoder_create(const vidil_encoder_cfg* cfg, vidil_encoder** out);
+void    vidil_encoder_destroy(vidil_encoder* enc);
+
+/* Load one parameter from a device fp32 tensor (contiguous, `numel` elements).  `name` uses the
+ * reference ViT state_dict keys (models/vit.py):
+ *   cls_token [D]  pos_embed [(P+1)*D]  patch_embed.proj.weight [D*3*ps*ps]  patch_embed.proj.bias [D]
+ *   blocks.<i>.norm1.weight|bias  blocks.<i>.attn.qkv.weight [3D*D]|bias [3D]
+ *   blocks.<i>.attn.proj.weight|bias  blocks.<i>.norm2.weight|bias
+ *   blocks.<i>.mlp.fc1.weight|bias  blocks.<i>.mlp.fc2.weight|bias  norm.weight|bias
+ * plus, for CLIP-style towers: pre_norm.weight|bias (pre_ln) and head.proj.weight [proj_dim*D] (proj_dim).
+ * Matrices are converted to the 16-bit operand type into handle-owned buffers; vectors stay fp32. */
+int32_t vidil_encoder_load(vidil_encoder* enc, const char* name, const float* dev_ptr, int64_t numel, void* stream);
+/* Fails (and names the first missing parameter) unless every parameter has been loaded. */
+int32_t vidil_encoder_check_loaded(const vidil_encoder* enc);
+
+size_t  vidil_encoder_workspace_bytes(const vidil_encoder* enc, int32_t batch);
+int32_t vidil_encoder_tokens(const vidil_encoder* enc); /* P + 1 */
+
+/* VisionTransformer.forward: frames fp32 NCHW [B,3,S,S] (device) -> tokens fp32 [B, P+1, D] (device),
+ * all tokens after the final LayerNorm (vit.py:192-194). */
+int32_t vidil_vit_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_tokens,
+                          void* workspace, size_t workspace_bytes, void* stream);
+
+/* CLIP vision tower + visual_projection + L2 normalisation: frames -> image_embeds fp32 [B, proj_dim].
+ * If out_hidden != NULL it also receives last_hidden_state (before post_layernorm) fp32 [B, P+1, D]. */
+int32_t vidil_clip_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_embeds,
+                           float* out_hidden, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Host-buffer variants (the reference-facing call with CPU tensors): copy frames host->device, run the
+ * forward above, copy the result device->host, synchronise.  Host buffers should be pinned for full
+ * PCIe bandwidth.  Device staging and workspace are the caller's (dev_scratch, at least
+ * vidil_encoder_host_scratch_bytes(enc, batch) bytes). */
+size_t  vidil_encoder_host_scratch_bytes(const vidil_encoder* enc, int32_t batch);
+int32_t vidil_vit_forward_host(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_tokens_host,
+                               void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+int32_t vidil_clip_forward_host(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_embeds_host,
+                                void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
+/* ---- similarity + top-k ----------------------------------------------------------------------- */
+/* img fp32 [F,D], bank fp32 [T,D] (device, D multiple of 64) -> out_scores fp32 [F,k], out_idx int32 [F,k]:
+ * for each frame the k phrases with the largest fp32 dot product, best first (k <= 12). */
+size_t  vidil_sim_topk_workspace_bytes(int32_t F, int32_t T, int32_t D);
+int32_t vidil_sim_topk(const float* img, const float* bank, int32_t F, int32_t T, int32_t D, int32_t k,
+                       float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- single operators (parity tests call these; same kernels the forwards use) --------------- */
+/* out = epilogue(A[M,K] @ W[N,K]^T): A, W fp32 on device are cast to `dtype` first (workspace).  epi:
+ * 0 store T, 1 gelu_erf T, 2 quick_gelu T, 3 out_f32 += , 4 patch scatter (pos, patches_per_frame), 5 store f32.
+ * out_is_f32 tells how `out` is typed for epi 0..2 the result is written as fp32 after a T round trip. */
+size_t  vidil_op_linear_workspace_bytes(int32_t M, int32_t N, int32_t K);
+int32_t vidil_op_linear(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
+                        int32_t epi, int32_t dtype, int32_t cta_group, const float* pos, int32_t patches_per_frame,
+                        void* workspace, size_t workspace_bytes, void* stream);
+int32_t vidil_op_layernorm(const float* in, const float* gamma, const float* beta, float* out, int32_t rows, int32_t D,
+                           float eps, void* stream);
+/* qkv fp32 [B,N,3,H,64] -> out fp32 [B,N,H*64]; operands are rounded to `dtype` as in the forward. */
+size_t  vidil_op_attention_workspace_bytes(int32_t B, int32_t N, int32_t H);
+int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VIDIL_B200_H_ */

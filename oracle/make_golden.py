@@ -1,0 +1,152 @@
+"""Generate the committed parity fixtures under tests/golden/ by executing the reference itself.
+
+TEST INFRASTRUCTURE, build-container only (needs /root/reference and, for the CLIP fixtures, the installed
+transformers package).  Run from the repository root:
+
+    python -m oracle.make_golden
+
+What is produced (all inputs/weights are regenerated from seeds by oracle/weights.py, so only outputs are
+stored):
+
+  vit_tiny.npz            reference VisionTransformer (D=128, depth 2, 32x32 px), full output, 2 frames
+  vit_large_224.npz       reference ViT-L/16 @224 (create_vit('large', 224)), 1 frame: CLS + every 4th token,
+                          plus the residual stream after blocks 0, 11, 23 for the same tokens
+  vit_base_384.npz        reference ViT-B/16 @384 (the shipped pipeline config), 1 frame: CLS + every 8th token
+  clip_tiny.npz           transformers.CLIPModel vision path (D=128, 2 layers), full outputs, 2 frames
+  clip_large14.npz        transformers.CLIPModel ViT-L/14 @224, 1 frame: image_embeds + CLS/every 8th token of
+                          last_hidden_state
+  tokenization.json       sim top-k indices computed with the reference's own lines (:276, :306), and
+                          aggregate_frame_tokens executed from run_visual_tokenization.py:173-187
+  sharding.json           per-rank slices from the reference's partition formula for several (n, world) pairs
+"""
+from __future__ import annotations
+
+import json
+import os
+
+import numpy as np
+import torch
+
+from . import reference_shims as rs
+from . import weights as W
+
+GOLDEN_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden")
+
+
+def _save(name, **arrays):
+    path = os.path.join(GOLDEN_DIR, name)
+    np.savez_compressed(path, **{k: np.asarray(v) for k, v in arrays.items()})
+    print(f"wrote {path} ({os.path.getsize(path) / 1024:.0f} KB)")
+
+
+@torch.no_grad()
+def golden_vit(vit, image_size, batch, token_stride, tap_blocks, fname):
+    sd = W.vit_state_dict(vit, image_size, seed=0)
+    model = rs.build_reference_vit(vit, image_size, sd)
+    x = W.frames(batch, image_size, seed=0)
+    taps = {}
+    hooks = []
+    for i in tap_blocks:
+        hooks.append(model.blocks[i].register_forward_hook(lambda m, a, out, i=i: taps.__setitem__(i, out.clone())))
+    out = model(x)
+    for h in hooks:
+        h.remove()
+    n_tok = out.shape[1]
+    tok = np.arange(0, n_tok, token_stride)
+    arrays = dict(tokens=tok, out=out[:, tok].numpy(), out_mean_abs=np.float32(out.abs().mean().item()),
+                  out_std=np.float32(out.std().item()))
+    for i, t in taps.items():
+        arrays[f"block{i}"] = t[:, tok].numpy()
+    _save(fname, **arrays)
+
+
+def _clip_model(name):
+    from transformers import CLIPConfig, CLIPModel
+    c = W.CLIP_CONFIGS[name]
+    vision = dict(hidden_size=c["hidden_size"], intermediate_size=c["intermediate_size"],
+                  num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
+                  image_size=c["image_size"], patch_size=c["patch_size"], layer_norm_eps=1e-5, hidden_act="quick_gelu")
+    text = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=1,
+                max_position_embeddings=8, vocab_size=64, hidden_act="quick_gelu")  # unused by the image path
+    cfg = CLIPConfig(text_config=text, vision_config=vision, projection_dim=c["projection_dim"])
+    cfg._attn_implementation = "eager"
+    model = CLIPModel(cfg).eval()
+    sd = W.clip_vision_state_dict(name, seed=0)
+    missing, unexpected = model.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith(("text_model.", "text_projection", "logit_scale")) for k in missing), missing
+    return model
+
+
+@torch.no_grad()
+def golden_clip(name, batch, token_stride, fname):
+    model = _clip_model(name)
+    c = W.CLIP_CONFIGS[name]
+    x = W.frames(batch, c["image_size"], seed=1)
+    vout = model.vision_model(pixel_values=x)
+    # exactly CLIPModel.forward's image branch (modeling_clip.py:916-923)
+    emb = model.visual_projection(vout.pooler_output)
+    emb = emb / emb.norm(p=2, dim=-1, keepdim=True)
+    tok = np.arange(0, vout.last_hidden_state.shape[1], token_stride)
+    _save(fname, tokens=tok, image_embeds=emb.numpy(), last_hidden=vout.last_hidden_state[:, tok].numpy())
+
+
+def golden_tokenization():
+    # similarity + per-frame argsort exactly as run_visual_tokenization.py:276,298-306
+    F_, T, D, k = 64, 1000, 768, 5
+    img = W.unit_rows(F_, D, seed=0)
+    bank = W.unit_rows(T, D, seed=1)
+    sims_matrix = img @ bank.t()                                     # :276
+    score = sims_matrix.view(F_ // 8, 8, -1).cpu().numpy()           # :298-299
+    inds = [[np.argsort(score[j][f])[::-1][:k].tolist() for f in range(8)] for j in range(F_ // 8)]   # :306
+    agg = rs.extract_reference_function("run_visual_tokenization.py", 173, 187, "aggregate_frame_tokens")
+    cases = []
+    rng = np.random.Generator(np.random.PCG64(7))
+    vocab = [f"phrase {i}" for i in range(12)]
+    for _ in range(6):
+        num_frm, topk = int(rng.integers(2, 9)), int(rng.integers(1, 6))
+        frames = []
+        for _f in range(num_frm):
+            frames.append({key: [vocab[int(i)] for i in rng.integers(0, len(vocab), size=topk)]
+                           for key in ("objects", "attributes", "scenes", "verbs")})
+        frames[0]["verbs"] = [] if rng.integers(0, 2) else frames[0]["verbs"]
+        if frames[0]["verbs"] == []:
+            for fr in frames:
+                fr["verbs"] = []
+        cases.append({"frame_tokens": frames, "aggregated": agg(frames)})
+    with open(os.path.join(GOLDEN_DIR, "tokenization.json"), "w") as f:
+        json.dump({"F": F_, "T": T, "D": D, "k": k, "img_seed": 0, "bank_seed": 1, "topk_indices": inds,
+                   "aggregate_cases": cases}, f)
+    print("wrote tokenization.json")
+
+
+def golden_sharding():
+    out = []
+    for n, world in [(0, 1), (1, 1), (7, 2), (8, 2), (2990, 8), (6250, 8), (5, 8), (16, 4), (1000, 3)]:
+        data = list(range(n))
+        slices = []
+        for rank in range(world):
+            step = len(data) // world + 1      # run_visual_tokenization.py:429-431 / run_video_CapFilt.py:239-241
+            start = rank * step
+            end = min(len(data), start + step)
+            s = data[start:end]
+            slices.append([s[0], s[-1] + 1] if s else None)
+        out.append({"n": n, "world": world, "slices": slices})
+    with open(os.path.join(GOLDEN_DIR, "sharding.json"), "w") as f:
+        json.dump(out, f)
+    print("wrote sharding.json")
+
+
+def main():
+    os.makedirs(GOLDEN_DIR, exist_ok=True)
+    torch.set_num_threads(os.cpu_count() or 1)
+    golden_vit("tiny", 32, 2, 1, [0, 1], "vit_tiny.npz")
+    golden_vit("large", 224, 1, 4, [0, 11, 23], "vit_large_224.npz")
+    golden_vit("base", 384, 1, 8, [0, 11], "vit_base_384.npz")
+    golden_clip("tiny", 2, 1, "clip_tiny.npz")
+    golden_clip("large14", 1, 8, "clip_large14.npz")
+    golden_tokenization()
+    golden_sharding()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,132 @@
+"""Deterministic synthetic parameters for the towers on the hot path.
+
+TEST INFRASTRUCTURE — only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / reference arm may
+import anything under oracle/.
+
+There are no pretrained checkpoints offline, and a 303 M-parameter state_dict cannot be committed, so both
+sides of every parity test regenerate the same tensors from a seed.  numpy's PCG64 stream is
+platform-independent, unlike torch's per-ISA vectorised samplers, so the golden fixtures made in the build
+container stay valid on the GPU box.
+
+Keys and shapes are exactly the reference's `VisionTransformer.state_dict()` (models/vit.py:144-161, probed:
+294 tensors for ViT-L/16), so a dict from here also exercises `load_state_dict` on the drop-in module.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+VIT_CONFIGS = {
+    # name: (embed_dim, depth, num_heads) — models/blip.py:309-322
+    "tiny": (128, 2, 2),  # not a reference config; small enough for pure-CPU tests
+    "base": (768, 12, 12),
+    "large": (1024, 24, 16),
+}
+
+
+def _normal(rng: np.random.Generator, shape, std: float, mean: float = 0.0) -> torch.Tensor:
+    a = rng.standard_normal(size=shape, dtype=np.float32)
+    a *= np.float32(std)
+    if mean != 0.0:
+        a += np.float32(mean)
+    return torch.from_numpy(a)
+
+
+def vit_state_dict(vit: str = "large", image_size: int = 224, patch_size: int = 16, seed: int = 0,
+                   exercise_affine: bool = True) -> dict:
+    """Synthetic BLIP-ViT parameters.
+
+    Weights ~ N(0, 0.02) like the reference's trunc_normal_(std=.02) init (models/vit.py:163-174; the ±2
+    truncation at 100 sigma is immaterial).  With `exercise_affine` biases ~ N(0, 0.02) and LayerNorm
+    gamma ~ N(1, 0.02), beta ~ N(0, 0.02) instead of the init's exact 0 / 1, so the bias and affine paths of
+    the kernels are actually tested.
+    """
+    D, depth, _ = VIT_CONFIGS[vit]
+    P = (image_size // patch_size) ** 2
+    rng = np.random.Generator(np.random.PCG64(seed))
+    bstd = 0.02 if exercise_affine else 0.0
+
+    def bias(n):
+        return _normal(rng, (n,), bstd) if exercise_affine else torch.zeros(n)
+
+    def gamma(n):
+        return _normal(rng, (n,), 0.02, 1.0) if exercise_affine else torch.ones(n)
+
+    sd = {}
+    sd["cls_token"] = _normal(rng, (1, 1, D), 0.02)
+    sd["pos_embed"] = _normal(rng, (1, P + 1, D), 0.02)
+    sd["patch_embed.proj.weight"] = _normal(rng, (D, 3, patch_size, patch_size), 0.02)
+    sd["patch_embed.proj.bias"] = bias(D)
+    for i in range(depth):
+        p = f"blocks.{i}."
+        sd[p + "norm1.weight"] = gamma(D)
+        sd[p + "norm1.bias"] = bias(D)
+        sd[p + "attn.qkv.weight"] = _normal(rng, (3 * D, D), 0.02)
+        sd[p + "attn.qkv.bias"] = bias(3 * D)
+        sd[p + "attn.proj.weight"] = _normal(rng, (D, D), 0.02)
+        sd[p + "attn.proj.bias"] = bias(D)
+        sd[p + "norm2.weight"] = gamma(D)
+        sd[p + "norm2.bias"] = bias(D)
+        sd[p + "mlp.fc1.weight"] = _normal(rng, (4 * D, D), 0.02)
+        sd[p + "mlp.fc1.bias"] = bias(4 * D)
+        sd[p + "mlp.fc2.weight"] = _normal(rng, (D, 4 * D), 0.02)
+        sd[p + "mlp.fc2.bias"] = bias(D)
+    sd["norm.weight"] = gamma(D)
+    sd["norm.bias"] = bias(D)
+    return sd
+
+
+# openai/clip-vit-large-patch14 vision tower (configs/pipeline_config/pipeline_config_msrvtt_test.yaml:15);
+# "tiny" is a CPU-sized stand-in with the same structure.
+CLIP_CONFIGS = {
+    "tiny": dict(hidden_size=128, intermediate_size=512, num_hidden_layers=2, num_attention_heads=2, image_size=28,
+                 patch_size=14, projection_dim=64),
+    "large14": dict(hidden_size=1024, intermediate_size=4096, num_hidden_layers=24, num_attention_heads=16,
+                    image_size=224, patch_size=14, projection_dim=768),
+}
+
+
+def clip_vision_state_dict(name: str = "large14", seed: int = 0) -> dict:
+    """Synthetic parameters under transformers' CLIPModel key names (vision tower + visual_projection)."""
+    c = CLIP_CONFIGS[name]
+    D, I, L = c["hidden_size"], c["intermediate_size"], c["num_hidden_layers"]
+    P = (c["image_size"] // c["patch_size"]) ** 2
+    rng = np.random.Generator(np.random.PCG64(seed))
+    v = "vision_model."
+    sd = {}
+    sd[v + "embeddings.class_embedding"] = _normal(rng, (D,), 0.02)
+    sd[v + "embeddings.patch_embedding.weight"] = _normal(rng, (D, 3, c["patch_size"], c["patch_size"]), 0.02)
+    sd[v + "embeddings.position_embedding.weight"] = _normal(rng, (P + 1, D), 0.02)
+    sd[v + "pre_layrnorm.weight"] = _normal(rng, (D,), 0.02, 1.0)
+    sd[v + "pre_layrnorm.bias"] = _normal(rng, (D,), 0.02)
+    for i in range(L):
+        p = f"{v}encoder.layers.{i}."
+        sd[p + "layer_norm1.weight"] = _normal(rng, (D,), 0.02, 1.0)
+        sd[p + "layer_norm1.bias"] = _normal(rng, (D,), 0.02)
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[p + f"self_attn.{nm}.weight"] = _normal(rng, (D, D), 0.02)
+            sd[p + f"self_attn.{nm}.bias"] = _normal(rng, (D,), 0.02)
+        sd[p + "layer_norm2.weight"] = _normal(rng, (D,), 0.02, 1.0)
+        sd[p + "layer_norm2.bias"] = _normal(rng, (D,), 0.02)
+        sd[p + "mlp.fc1.weight"] = _normal(rng, (I, D), 0.02)
+        sd[p + "mlp.fc1.bias"] = _normal(rng, (I,), 0.02)
+        sd[p + "mlp.fc2.weight"] = _normal(rng, (D, I), 0.02)
+        sd[p + "mlp.fc2.bias"] = _normal(rng, (D,), 0.02)
+    sd[v + "post_layernorm.weight"] = _normal(rng, (D,), 0.02, 1.0)
+    sd[v + "post_layernorm.bias"] = _normal(rng, (D,), 0.02)
+    sd["visual_projection.weight"] = _normal(rng, (c["projection_dim"], D), 0.02)
+    return sd
+
+
+def frames(batch: int, image_size: int = 224, seed: int = 0) -> torch.Tensor:
+    """Synthetic post-Normalize frames ~ N(0,1), fp32 NCHW."""
+    rng = np.random.Generator(np.random.PCG64(1_000_003 + seed))
+    return torch.from_numpy(rng.standard_normal(size=(batch, 3, image_size, image_size), dtype=np.float32))
+
+
+def unit_rows(n: int, d: int, seed: int) -> torch.Tensor:
+    """n unit-norm fp32 rows — stand-ins for CLIP image/text embeddings."""
+    rng = np.random.Generator(np.random.PCG64(2_000_003 + seed))
+    a = rng.standard_normal(size=(n, d), dtype=np.float32)
+    a /= np.linalg.norm(a, axis=1, keepdims=True)
+    return torch.from_numpy(a)

@@ -1,0 +1,740 @@
+// C ABI (include/vidil_b200.h): encoder handle, weight packing, forward plans, similarity/top-k and the
+// operator-level entry points used by the parity tests.
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <atomic>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/vidil_b200.h"
+#include "kernels.h"
+
+namespace vidil {
+
+static thread_local std::string g_error;
+static std::atomic<int64_t> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+}
+const char* get_error() { return g_error.c_str(); }
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+namespace {
+
+constexpr size_t ALIGN = 1024;
+inline size_t align_up(size_t x) { return (x + ALIGN - 1) / ALIGN * ALIGN; }
+inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    bool loaded = false;
+    ~DevBuf() {
+        if (p) cudaFree(p);
+    }
+    int alloc(size_t n) {
+        VIDIL_CUDA_OK(cudaMalloc(&p, n));
+        bytes = n;
+        return 0;
+    }
+};
+
+struct Layer {
+    DevBuf ln1_w, ln1_b, qkv_w, qkv_b, proj_w, proj_b, ln2_w, ln2_b, fc1_w, fc1_b, fc2_w, fc2_b;
+};
+
+// All GEMMs of one forward at a given batch size and workspace address, TMA maps already encoded.
+struct Plan {
+    int batch = 0;
+    const void* ws = nullptr;
+    uint64_t stamp = 0;
+    float* resid = nullptr;
+    void* xn = nullptr;
+    void* qkv = nullptr;
+    void* attn = nullptr;
+    void* hidden = nullptr;
+    void* patches = nullptr;  // aliases hidden
+    float* pre = nullptr;     // CLIP: pre-LayerNorm fp32 embeddings, aliases qkv
+    void* cls_ln = nullptr;
+    float* head_out = nullptr;
+    GemmProblem patch;
+    std::vector<GemmProblem> qkv_g, proj_g, fc1_g, fc2_g;
+    GemmProblem head;
+};
+
+}  // namespace
+}  // namespace vidil
+
+using namespace vidil;
+
+struct vidil_encoder {
+    vidil_encoder_cfg cfg;
+    int device = 0;
+    int grid = 0, patches = 0, tokens = 0, kpatch = 0, kpatch_pad = 0;
+    DType dt = DT_BF16;
+    DevBuf cls, pos, patch_w, patch_b, pre_w, pre_b, norm_w, norm_b, head_w;
+    std::vector<std::unique_ptr<Layer>> layers;
+    std::vector<std::unique_ptr<Plan>> plans;
+    uint64_t clock = 0;
+};
+
+namespace {
+
+struct WsLayout {
+    size_t resid, xn, qkv, attn, hidden, cls_ln, head_out, total;
+};
+
+WsLayout ws_layout(const vidil_encoder* e, int B) {
+    const size_t M = static_cast<size_t>(B) * e->tokens;
+    const size_t D = e->cfg.embed_dim;
+    WsLayout w;
+    size_t off = 0;
+    w.resid = off;
+    off += align_up(M * D * 4);
+    w.xn = off;
+    off += align_up(M * D * 2);
+    w.qkv = off;
+    off += align_up(M * 3 * D * 2);
+    w.attn = off;
+    off += align_up(M * D * 2);
+    size_t hid = M * e->cfg.mlp_dim * 2;
+    const size_t pat = static_cast<size_t>(B) * e->patches * e->kpatch_pad * 2;
+    if (pat > hid) hid = pat;
+    w.hidden = off;
+    off += align_up(hid);
+    w.cls_ln = off;
+    off += align_up(static_cast<size_t>(B) * D * 2);
+    w.head_out = off;
+    off += align_up(static_cast<size_t>(B) * (e->cfg.proj_dim > 0 ? e->cfg.proj_dim : 1) * 4);
+    w.total = off;
+    return w;
+}
+
+int build_plan(vidil_encoder* e, Plan& pl, int B, void* ws) {
+    const vidil_encoder_cfg& c = e->cfg;
+    const WsLayout L = ws_layout(e, B);
+    uint8_t* base = reinterpret_cast<uint8_t*>(ws);
+    pl.batch = B;
+    pl.ws = ws;
+    pl.resid = reinterpret_cast<float*>(base + L.resid);
+    pl.xn = base + L.xn;
+    pl.qkv = base + L.qkv;
+    pl.attn = base + L.attn;
+    pl.hidden = base + L.hidden;
+    pl.patches = pl.hidden;
+    pl.pre = reinterpret_cast<float*>(pl.qkv);
+    pl.cls_ln = base + L.cls_ln;
+    pl.head_out = reinterpret_cast<float*>(base + L.head_out);
+    const int M = B * e->tokens, D = c.embed_dim;
+    const int cg = c.cta_group;
+
+    GemmProblem g;
+    g.dt = e->dt;
+    g.cta_group = cg;
+
+    // patch embedding: [B*P, Kpad] x [D, Kpad]^T -> token rows 1..P of every frame (+bias +pos)
+    pl.patch = g;
+    pl.patch.epi = EPI_PATCH;
+    pl.patch.M = B * e->patches;
+    pl.patch.N = D;
+    pl.patch.K = e->kpatch_pad;
+    pl.patch.A = pl.patches;
+    pl.patch.lda = e->kpatch_pad;
+    pl.patch.W = e->patch_w.p;
+    pl.patch.ldw = e->kpatch_pad;
+    pl.patch.bias = c.patch_bias ? reinterpret_cast<const float*>(e->patch_b.p) : nullptr;
+    pl.patch.out = c.pre_ln ? pl.pre : pl.resid;
+    pl.patch.ldo = D;
+    pl.patch.pos = reinterpret_cast<const float*>(e->pos.p);
+    pl.patch.patches_per_frame = e->patches;
+    if (gemm_prepare(pl.patch)) return 1;
+
+    pl.qkv_g.assign(c.depth, g);
+    pl.proj_g.assign(c.depth, g);
+    pl.fc1_g.assign(c.depth, g);
+    pl.fc2_g.assign(c.depth, g);
+    for (int i = 0; i < c.depth; ++i) {
+        Layer& ly = *e->layers[i];
+        GemmProblem& q = pl.qkv_g[i];
+        q.epi = EPI_STORE;
+        q.M = M; q.N = 3 * D; q.K = D;
+        q.A = pl.xn; q.lda = D;
+        q.W = ly.qkv_w.p; q.ldw = D;
+        q.bias = reinterpret_cast<const float*>(ly.qkv_b.p);
+        q.out = pl.qkv; q.ldo = 3 * D;
+        if (gemm_prepare(q)) return 1;
+
+        GemmProblem& p = pl.proj_g[i];
+        p.epi = EPI_RESID;
+        p.M = M; p.N = D; p.K = D;
+        p.A = pl.attn; p.lda = D;
+        p.W = ly.proj_w.p; p.ldw = D;
+        p.bias = reinterpret_cast<const float*>(ly.proj_b.p);
+        p.out = pl.resid; p.ldo = D;
+        if (gemm_prepare(p)) return 1;
+
+        GemmProblem& f1 = pl.fc1_g[i];
+        f1.epi = (c.act == VIDIL_ACT_QUICK_GELU) ? EPI_QUICKGELU : EPI_GELU;
+        f1.M = M; f1.N = c.mlp_dim; f1.K = D;
+        f1.A = pl.xn; f1.lda = D;
+        f1.W = ly.fc1_w.p; f1.ldw = D;
+        f1.bias = reinterpret_cast<const float*>(ly.fc1_b.p);
+        f1.out = pl.hidden; f1.ldo = c.mlp_dim;
+        if (gemm_prepare(f1)) return 1;
+
+        GemmProblem& f2 = pl.fc2_g[i];
+        f2.epi = EPI_RESID;
+        f2.M = M; f2.N = D; f2.K = c.mlp_dim;
+        f2.A = pl.hidden; f2.lda = c.mlp_dim;
+        f2.W = ly.fc2_w.p; f2.ldw = c.mlp_dim;
+        f2.bias = reinterpret_cast<const float*>(ly.fc2_b.p);
+        f2.out = pl.resid; f2.ldo = D;
+        if (gemm_prepare(f2)) return 1;
+    }
+    if (c.proj_dim > 0) {
+        pl.head = g;
+        pl.head.epi = EPI_STORE_F32;
+        pl.head.M = B; pl.head.N = c.proj_dim; pl.head.K = D;
+        pl.head.A = pl.cls_ln; pl.head.lda = D;
+        pl.head.W = e->head_w.p; pl.head.ldw = D;
+        pl.head.bias = nullptr;
+        pl.head.out = pl.head_out; pl.head.ldo = c.proj_dim;
+        if (gemm_prepare(pl.head)) return 1;
+    }
+    return 0;
+}
+
+Plan* get_plan(vidil_encoder* e, int B, void* ws) {
+    for (auto& p : e->plans)
+        if (p->batch == B && p->ws == ws) {
+            p->stamp = ++e->clock;
+            return p.get();
+        }
+    std::unique_ptr<Plan> pl(new Plan());
+    if (build_plan(e, *pl, B, ws)) return nullptr;
+    pl->stamp = ++e->clock;
+    if (e->plans.size() >= 8) {  // evict the least recently used plan
+        size_t victim = 0;
+        for (size_t i = 1; i < e->plans.size(); ++i)
+            if (e->plans[i]->stamp < e->plans[victim]->stamp) victim = i;
+        e->plans[victim] = std::move(pl);
+        return e->plans[victim].get();
+    }
+    e->plans.push_back(std::move(pl));
+    return e->plans.back().get();
+}
+
+int check_common(vidil_encoder* e, const void* frames, int B, const void* out, void* ws, size_t ws_bytes) {
+    if (e == nullptr || frames == nullptr || out == nullptr || ws == nullptr) {
+        set_error("null argument");
+        return 1;
+    }
+    if (B <= 0) {
+        set_error("batch must be positive, got %d", B);
+        return 1;
+    }
+    if (vidil_encoder_check_loaded(e)) return 1;
+    const size_t need = ws_layout(e, B).total;
+    if (ws_bytes < need) {
+        set_error("workspace too small: %zu bytes given, %zu needed for batch %d", ws_bytes, need, B);
+        return 1;
+    }
+    if ((reinterpret_cast<uintptr_t>(ws) & (ALIGN - 1)) || (reinterpret_cast<uintptr_t>(frames) & 15) ||
+        (reinterpret_cast<uintptr_t>(out) & 15)) {
+        set_error("workspace must be %zu-byte aligned and frames/out 16-byte aligned", ALIGN);
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    return 0;
+}
+
+// Everything up to (not including) the final LayerNorm: leaves the last block's output in pl.resid.
+int run_trunk(vidil_encoder* e, Plan& pl, const float* frames, cudaStream_t s) {
+    const vidil_encoder_cfg& c = e->cfg;
+    const int B = pl.batch, M = B * e->tokens, D = c.embed_dim;
+    if (e->kpatch_pad != e->kpatch)  // zero the K padding once per call (CLIP 588 -> 640)
+        VIDIL_CUDA_OK(cudaMemsetAsync(pl.patches, 0, static_cast<size_t>(B) * e->patches * e->kpatch_pad * 2, s));
+    if (im2col_run(frames, pl.patches, e->dt, B, 3, c.img_size, c.patch_size, e->kpatch_pad, s)) return 1;
+    float* emb = c.pre_ln ? pl.pre : pl.resid;
+    if (cls_pos_run(reinterpret_cast<const float*>(e->cls.p), reinterpret_cast<const float*>(e->pos.p), emb, B,
+                    e->tokens, D, s))
+        return 1;
+    if (gemm_run(pl.patch, s)) return 1;
+    if (c.pre_ln) {
+        if (layernorm_run(pl.pre, D, reinterpret_cast<const float*>(e->pre_w.p),
+                          reinterpret_cast<const float*>(e->pre_b.p), pl.resid, true, e->dt, M, D, c.ln_eps, s))
+            return 1;
+    }
+    const float scale = 0.125f;  // head_dim ** -0.5 with head_dim = 64 (vit.py:49)
+    for (int i = 0; i < c.depth; ++i) {
+        Layer& ly = *e->layers[i];
+        if (layernorm_run(pl.resid, D, reinterpret_cast<const float*>(ly.ln1_w.p),
+                          reinterpret_cast<const float*>(ly.ln1_b.p), pl.xn, false, e->dt, M, D, c.ln_eps, s))
+            return 1;
+        if (gemm_run(pl.qkv_g[i], s)) return 1;
+        if (attention_run(pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads, scale, s)) return 1;
+        if (gemm_run(pl.proj_g[i], s)) return 1;
+        if (layernorm_run(pl.resid, D, reinterpret_cast<const float*>(ly.ln2_w.p),
+                          reinterpret_cast<const float*>(ly.ln2_b.p), pl.xn, false, e->dt, M, D, c.ln_eps, s))
+            return 1;
+        if (gemm_run(pl.fc1_g[i], s)) return 1;
+        if (gemm_run(pl.fc2_g[i], s)) return 1;
+    }
+    return 0;
+}
+
+struct Slot {
+    DevBuf* buf;
+    int64_t numel;
+    bool matrix;
+    int rows, cols, ld;  // matrices: logical [rows, cols] packed into [rows, ld]
+};
+
+bool find_slot(vidil_encoder* e, const char* name, Slot& s) {
+    const vidil_encoder_cfg& c = e->cfg;
+    const int D = c.embed_dim, H = c.mlp_dim;
+    auto vec = [&](DevBuf& b, int64_t n) { s = Slot{&b, n, false, 0, 0, 0}; return true; };
+    auto mat = [&](DevBuf& b, int r, int k, int ld) { s = Slot{&b, static_cast<int64_t>(r) * k, true, r, k, ld}; return true; };
+    if (!strcmp(name, "cls_token")) return vec(e->cls, D);
+    if (!strcmp(name, "pos_embed")) return vec(e->pos, static_cast<int64_t>(e->tokens) * D);
+    if (!strcmp(name, "patch_embed.proj.weight")) return mat(e->patch_w, D, e->kpatch, e->kpatch_pad);
+    if (!strcmp(name, "patch_embed.proj.bias") && c.patch_bias) return vec(e->patch_b, D);
+    if (!strcmp(name, "pre_norm.weight") && c.pre_ln) return vec(e->pre_w, D);
+    if (!strcmp(name, "pre_norm.bias") && c.pre_ln) return vec(e->pre_b, D);
+    if (!strcmp(name, "norm.weight")) return vec(e->norm_w, D);
+    if (!strcmp(name, "norm.bias")) return vec(e->norm_b, D);
+    if (!strcmp(name, "head.proj.weight") && c.proj_dim > 0) return mat(e->head_w, c.proj_dim, D, D);
+    int idx = -1, consumed = 0;
+    if (sscanf(name, "blocks.%d.%n", &idx, &consumed) == 1 && consumed > 0 && idx >= 0 && idx < c.depth) {
+        const char* r = name + consumed;
+        Layer& ly = *e->layers[idx];
+        if (!strcmp(r, "norm1.weight")) return vec(ly.ln1_w, D);
+        if (!strcmp(r, "norm1.bias")) return vec(ly.ln1_b, D);
+        if (!strcmp(r, "attn.qkv.weight")) return mat(ly.qkv_w, 3 * D, D, D);
+        if (!strcmp(r, "attn.qkv.bias")) return vec(ly.qkv_b, 3 * D);
+        if (!strcmp(r, "attn.proj.weight")) return mat(ly.proj_w, D, D, D);
+        if (!strcmp(r, "attn.proj.bias")) return vec(ly.proj_b, D);
+        if (!strcmp(r, "norm2.weight")) return vec(ly.ln2_w, D);
+        if (!strcmp(r, "norm2.bias")) return vec(ly.ln2_b, D);
+        if (!strcmp(r, "mlp.fc1.weight")) return mat(ly.fc1_w, H, D, D);
+        if (!strcmp(r, "mlp.fc1.bias")) return vec(ly.fc1_b, H);
+        if (!strcmp(r, "mlp.fc2.weight")) return mat(ly.fc2_w, D, H, H);
+        if (!strcmp(r, "mlp.fc2.bias")) return vec(ly.fc2_b, D);
+    }
+    return false;
+}
+
+struct NamedBuf {
+    std::string name;
+    const DevBuf* buf;
+};
+
+void list_params(const vidil_encoder* e, std::vector<NamedBuf>& out) {
+    const vidil_encoder_cfg& c = e->cfg;
+    out.push_back({"cls_token", &e->cls});
+    out.push_back({"pos_embed", &e->pos});
+    out.push_back({"patch_embed.proj.weight", &e->patch_w});
+    if (c.patch_bias) out.push_back({"patch_embed.proj.bias", &e->patch_b});
+    if (c.pre_ln) {
+        out.push_back({"pre_norm.weight", &e->pre_w});
+        out.push_back({"pre_norm.bias", &e->pre_b});
+    }
+    for (int i = 0; i < c.depth; ++i) {
+        const Layer& ly = *e->layers[i];
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        out.push_back({p + "norm1.weight", &ly.ln1_w});
+        out.push_back({p + "norm1.bias", &ly.ln1_b});
+        out.push_back({p + "attn.qkv.weight", &ly.qkv_w});
+        out.push_back({p + "attn.qkv.bias", &ly.qkv_b});
+        out.push_back({p + "attn.proj.weight", &ly.proj_w});
+        out.push_back({p + "attn.proj.bias", &ly.proj_b});
+        out.push_back({p + "norm2.weight", &ly.ln2_w});
+        out.push_back({p + "norm2.bias", &ly.ln2_b});
+        out.push_back({p + "mlp.fc1.weight", &ly.fc1_w});
+        out.push_back({p + "mlp.fc1.bias", &ly.fc1_b});
+        out.push_back({p + "mlp.fc2.weight", &ly.fc2_w});
+        out.push_back({p + "mlp.fc2.bias", &ly.fc2_b});
+    }
+    out.push_back({"norm.weight", &e->norm_w});
+    out.push_back({"norm.bias", &e->norm_b});
+    if (c.proj_dim > 0) out.push_back({"head.proj.weight", &e->head_w});
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t vidil_abi_version(void) { return VIDIL_B200_ABI_VERSION; }
+const char* vidil_last_error(void) { return get_error(); }
+int64_t vidil_kernel_launch_count(void) { return launch_count(); }
+
+int32_t vidil_encoder_create(const vidil_encoder_cfg* cfg, vidil_encoder** out) {
+    if (cfg == nullptr || out == nullptr) {
+        set_error("vidil_encoder_create: null argument");
+        return 1;
+    }
+    *out = nullptr;
+    vidil_encoder_cfg c = *cfg;
+    if (c.cta_group == 0) c.cta_group = 2;
+    if (c.img_size <= 0 || c.patch_size <= 0 || c.patch_size % 2 != 0 || c.img_size % c.patch_size != 0) {
+        set_error("unsupported geometry: img_size=%d patch_size=%d (patch must be even and divide the image)", c.img_size,
+                  c.patch_size);
+        return 1;
+    }
+    if (c.embed_dim <= 0 || c.embed_dim % 128 != 0 || c.num_heads * 64 != c.embed_dim) {
+        set_error("unsupported width: embed_dim=%d num_heads=%d (need embed_dim %% 128 == 0 and head_dim 64)", c.embed_dim,
+                  c.num_heads);
+        return 1;
+    }
+    if (c.embed_dim != 128 && c.embed_dim != 256 && c.embed_dim != 512 && c.embed_dim != 768 && c.embed_dim != 1024 &&
+        c.embed_dim != 1280) {
+        set_error("unsupported embed_dim=%d (LayerNorm kernel covers 128/256/512/768/1024/1280)", c.embed_dim);
+        return 1;
+    }
+    if (c.depth <= 0 || c.mlp_dim <= 0 || c.mlp_dim % 64 != 0) {
+        set_error("unsupported depth=%d / mlp_dim=%d (mlp_dim must be a multiple of 64)", c.depth, c.mlp_dim);
+        return 1;
+    }
+    if (c.dtype != VIDIL_DTYPE_BF16 && c.dtype != VIDIL_DTYPE_FP16) {
+        set_error("unsupported dtype %d", c.dtype);
+        return 1;
+    }
+    if (c.act != VIDIL_ACT_GELU_ERF && c.act != VIDIL_ACT_QUICK_GELU) {
+        set_error("unsupported activation %d", c.act);
+        return 1;
+    }
+    if (c.cta_group != 1 && c.cta_group != 2) {
+        set_error("cta_group must be 0, 1 or 2");
+        return 1;
+    }
+    if (c.proj_dim < 0 || c.proj_dim % 4 != 0) {
+        set_error("proj_dim must be a non-negative multiple of 4");
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    std::unique_ptr<vidil_encoder> e(new vidil_encoder());
+    e->cfg = c;
+    VIDIL_CUDA_OK(cudaGetDevice(&e->device));
+    e->dt = (c.dtype == VIDIL_DTYPE_BF16) ? DT_BF16 : DT_FP16;
+    e->grid = c.img_size / c.patch_size;
+    e->patches = e->grid * e->grid;
+    e->tokens = e->patches + 1;
+    e->kpatch = 3 * c.patch_size * c.patch_size;
+    e->kpatch_pad = round_up(e->kpatch, 64);
+    for (int i = 0; i < c.depth; ++i) e->layers.emplace_back(new Layer());
+
+    // allocate every parameter buffer up front (fp32 vectors, 16-bit matrices)
+    std::vector<NamedBuf> names;
+    list_params(e.get(), names);
+    for (auto& nb : names) {
+        Slot s;
+        if (!find_slot(e.get(), nb.name.c_str(), s)) {
+            set_error("internal: no slot for %s", nb.name.c_str());
+            return 1;
+        }
+        const size_t bytes = s.matrix ? static_cast<size_t>(s.rows) * s.ld * 2 : static_cast<size_t>(s.numel) * 4;
+        if (s.buf->alloc(bytes)) return 1;
+    }
+    *out = e.release();
+    return 0;
+}
+
+void vidil_encoder_destroy(vidil_encoder* enc) { delete enc; }
+
+int32_t vidil_encoder_load(vidil_encoder* enc, const char* name, const float* dev_ptr, int64_t numel, void* stream) {
+    if (enc == nullptr || name == nullptr || dev_ptr == nullptr) {
+        set_error("vidil_encoder_load: null argument");
+        return 1;
+    }
+    Slot s;
+    if (!find_slot(enc, name, s)) {
+        set_error("vidil_encoder_load: unknown parameter '%s' for this configuration", name);
+        return 1;
+    }
+    if (numel != s.numel) {
+        set_error("vidil_encoder_load: '%s' has %lld elements, expected %lld", name, (long long)numel, (long long)s.numel);
+        return 1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (s.matrix) {
+        if (cast_run(dev_ptr, s.buf->p, enc->dt, s.rows, s.cols, s.ld, st)) return 1;
+    } else {
+        VIDIL_CUDA_OK(cudaMemcpyAsync(s.buf->p, dev_ptr, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    s.buf->loaded = true;
+    return 0;
+}
+
+int32_t vidil_encoder_check_loaded(const vidil_encoder* enc) {
+    if (enc == nullptr) {
+        set_error("null encoder");
+        return 1;
+    }
+    std::vector<NamedBuf> names;
+    list_params(enc, names);
+    for (auto& nb : names)
+        if (!nb.buf->loaded) {
+            set_error("parameter '%s' has not been loaded", nb.name.c_str());
+            return 1;
+        }
+    return 0;
+}
+
+size_t vidil_encoder_workspace_bytes(const vidil_encoder* enc, int32_t batch) {
+    if (enc == nullptr || batch <= 0) return 0;
+    return ws_layout(enc, batch).total;
+}
+
+int32_t vidil_encoder_tokens(const vidil_encoder* enc) { return enc ? enc->tokens : 0; }
+
+int32_t vidil_vit_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_tokens, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    if (check_common(enc, frames, batch, out_tokens, workspace, workspace_bytes)) return 1;
+    if (enc->cfg.proj_dim > 0 || enc->cfg.pre_ln) {
+        set_error("vidil_vit_forward: this handle is a CLIP-style tower; use vidil_clip_forward");
+        return 1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    Plan* pl = get_plan(enc, batch, workspace);
+    if (pl == nullptr) return 1;
+    if (run_trunk(enc, *pl, frames, s)) return 1;
+    const int M = batch * enc->tokens, D = enc->cfg.embed_dim;
+    return layernorm_run(pl->resid, D, reinterpret_cast<const float*>(enc->norm_w.p),
+                         reinterpret_cast<const float*>(enc->norm_b.p), out_tokens, true, enc->dt, M, D, enc->cfg.ln_eps, s);
+}
+
+int32_t vidil_clip_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_embeds, float* out_hidden,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    if (check_common(enc, frames, batch, out_embeds, workspace, workspace_bytes)) return 1;
+    if (enc->cfg.proj_dim <= 0) {
+        set_error("vidil_clip_forward: handle has no projection head (proj_dim == 0)");
+        return 1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    Plan* pl = get_plan(enc, batch, workspace);
+    if (pl == nullptr) return 1;
+    if (run_trunk(enc, *pl, frames, s)) return 1;
+    const int D = enc->cfg.embed_dim;
+    const size_t M = static_cast<size_t>(batch) * enc->tokens;
+    if (out_hidden != nullptr)
+        VIDIL_CUDA_OK(cudaMemcpyAsync(out_hidden, pl->resid, M * D * 4, cudaMemcpyDeviceToDevice, s));
+    // post_layernorm on the CLS row of every frame only, then the bias-free projection and L2 normalisation
+    if (layernorm_run(pl->resid, static_cast<int64_t>(enc->tokens) * D, reinterpret_cast<const float*>(enc->norm_w.p),
+                      reinterpret_cast<const float*>(enc->norm_b.p), pl->cls_ln, false, enc->dt, batch, D, enc->cfg.ln_eps, s))
+        return 1;
+    if (gemm_run(pl->head, s)) return 1;
+    return l2norm_run(pl->head_out, out_embeds, batch, enc->cfg.proj_dim, s);
+}
+
+size_t vidil_encoder_host_scratch_bytes(const vidil_encoder* enc, int32_t batch) {
+    if (enc == nullptr || batch <= 0) return 0;
+    const size_t in = align_up(static_cast<size_t>(batch) * 3 * enc->cfg.img_size * enc->cfg.img_size * 4);
+    const size_t out_tok = align_up(static_cast<size_t>(batch) * enc->tokens * enc->cfg.embed_dim * 4);
+    return in + out_tok + ws_layout(enc, batch).total;
+}
+
+static int host_forward(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_host, bool clip,
+                        void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+    if (enc == nullptr || frames_host == nullptr || out_host == nullptr || dev_scratch == nullptr || batch <= 0) {
+        set_error("host forward: null argument or empty batch");
+        return 1;
+    }
+    const size_t need = vidil_encoder_host_scratch_bytes(enc, batch);
+    if (dev_scratch_bytes < need) {
+        set_error("device scratch too small: %zu bytes given, %zu needed", dev_scratch_bytes, need);
+        return 1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const size_t in_bytes = static_cast<size_t>(batch) * 3 * enc->cfg.img_size * enc->cfg.img_size * 4;
+    const size_t out_tok_bytes = static_cast<size_t>(batch) * enc->tokens * enc->cfg.embed_dim * 4;
+    uint8_t* base = reinterpret_cast<uint8_t*>(dev_scratch);
+    float* d_in = reinterpret_cast<float*>(base);
+    float* d_out = reinterpret_cast<float*>(base + align_up(in_bytes));
+    void* ws = base + align_up(in_bytes) + align_up(out_tok_bytes);
+    const size_t ws_bytes = dev_scratch_bytes - align_up(in_bytes) - align_up(out_tok_bytes);
+    VIDIL_CUDA_OK(cudaMemcpyAsync(d_in, frames_host, in_bytes, cudaMemcpyHostToDevice, s));
+    size_t out_bytes;
+    if (clip) {
+        if (vidil_clip_forward(enc, d_in, batch, d_out, nullptr, ws, ws_bytes, stream)) return 1;
+        out_bytes = static_cast<size_t>(batch) * enc->cfg.proj_dim * 4;
+    } else {
+        if (vidil_vit_forward(enc, d_in, batch, d_out, ws, ws_bytes, stream)) return 1;
+        out_bytes = out_tok_bytes;
+    }
+    VIDIL_CUDA_OK(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, s));
+    VIDIL_CUDA_OK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+int32_t vidil_vit_forward_host(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_tokens_host,
+                               void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+    return host_forward(enc, frames_host, batch, out_tokens_host, false, dev_scratch, dev_scratch_bytes, stream);
+}
+int32_t vidil_clip_forward_host(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_embeds_host,
+                                void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+    return host_forward(enc, frames_host, batch, out_embeds_host, true, dev_scratch, dev_scratch_bytes, stream);
+}
+
+// ---- similarity + top-k ---------------------------------------------------------------------------
+size_t vidil_sim_topk_workspace_bytes(int32_t F, int32_t T, int32_t D) {
+    if (F <= 0 || T <= 0 || D <= 0) return 0;
+    return align_up(static_cast<size_t>(F) * D * 2) + align_up(static_cast<size_t>(T) * D * 2) +
+           align_up(static_cast<size_t>(F) * round_up(T, 4) * 4);
+}
+
+int32_t vidil_sim_topk(const float* img, const float* bank, int32_t F, int32_t T, int32_t D, int32_t k, float* out_scores,
+                       int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+    if (img == nullptr || bank == nullptr || out_scores == nullptr || out_idx == nullptr || workspace == nullptr) {
+        set_error("vidil_sim_topk: null argument");
+        return 1;
+    }
+    if (F <= 0 || T <= 0 || D <= 0 || D % 64 != 0) {
+        set_error("vidil_sim_topk: need F, T > 0 and D a positive multiple of 64 (F=%d T=%d D=%d)", F, T, D);
+        return 1;
+    }
+    if (workspace_bytes < vidil_sim_topk_workspace_bytes(F, T, D) || (reinterpret_cast<uintptr_t>(workspace) & (ALIGN - 1))) {
+        set_error("vidil_sim_topk: workspace too small or not %zu-byte aligned", ALIGN);
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+    void* img_h = base;
+    void* bank_h = base + align_up(static_cast<size_t>(F) * D * 2);
+    float* scores = reinterpret_cast<float*>(base + align_up(static_cast<size_t>(F) * D * 2) +
+                                             align_up(static_cast<size_t>(T) * D * 2));
+    const int ld = round_up(T, 4);
+    // fp16 operands: unit-norm embeddings sit well inside fp16 range and keep 3 more mantissa bits than bf16
+    if (cast_run(img, img_h, DT_FP16, F, D, D, s)) return 1;
+    if (cast_run(bank, bank_h, DT_FP16, T, D, D, s)) return 1;
+    GemmProblem g;
+    g.dt = DT_FP16;
+    g.epi = EPI_STORE_F32;
+    g.cta_group = 2;
+    g.M = F; g.N = T; g.K = D;
+    g.A = img_h; g.lda = D;
+    g.W = bank_h; g.ldw = D;
+    g.out = scores; g.ldo = ld;
+    if (gemm_prepare(g)) return 1;
+    if (gemm_run(g, s)) return 1;
+    return topk_rerank_run(scores, ld, img, bank, F, T, D, k, out_scores, out_idx, s);
+}
+
+// ---- operator-level entry points --------------------------------------------------------------------
+size_t vidil_op_linear_workspace_bytes(int32_t M, int32_t N, int32_t K) {
+    if (M <= 0 || N <= 0 || K <= 0) return 0;
+    return align_up(static_cast<size_t>(M) * K * 2) + align_up(static_cast<size_t>(N) * K * 2) +
+           align_up(static_cast<size_t>(M) * N * 2);
+}
+
+int32_t vidil_op_linear(const float* A, const float* W, const float* bias, float* out, int32_t M, int32_t N, int32_t K,
+                        int32_t epi, int32_t dtype, int32_t cta_group, const float* pos, int32_t patches_per_frame,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+    if (A == nullptr || W == nullptr || out == nullptr || workspace == nullptr) {
+        set_error("vidil_op_linear: null argument");
+        return 1;
+    }
+    if (workspace_bytes < vidil_op_linear_workspace_bytes(M, N, K) || (reinterpret_cast<uintptr_t>(workspace) & (ALIGN - 1))) {
+        set_error("vidil_op_linear: workspace too small or misaligned");
+        return 1;
+    }
+    if (epi < 0 || epi >= EPI_COUNT || (dtype != VIDIL_DTYPE_BF16 && dtype != VIDIL_DTYPE_FP16)) {
+        set_error("vidil_op_linear: bad epilogue %d or dtype %d", epi, dtype);
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const DType dt = (dtype == VIDIL_DTYPE_BF16) ? DT_BF16 : DT_FP16;
+    uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+    void* a_h = base;
+    void* w_h = base + align_up(static_cast<size_t>(M) * K * 2);
+    void* o_h = base + align_up(static_cast<size_t>(M) * K * 2) + align_up(static_cast<size_t>(N) * K * 2);
+    if (cast_run(A, a_h, dt, M, K, K, s)) return 1;
+    if (cast_run(W, w_h, dt, N, K, K, s)) return 1;
+    const bool f32_out = (epi == EPI_RESID || epi == EPI_PATCH || epi == EPI_STORE_F32);
+    GemmProblem g;
+    g.dt = dt;
+    g.epi = epi;
+    g.cta_group = cta_group == 0 ? 2 : cta_group;
+    g.M = M; g.N = N; g.K = K;
+    g.A = a_h; g.lda = K;
+    g.W = w_h; g.ldw = K;
+    g.bias = bias;
+    g.out = f32_out ? static_cast<void*>(out) : o_h;
+    g.ldo = N;
+    g.pos = pos;
+    g.patches_per_frame = patches_per_frame;
+    if (gemm_prepare(g)) return 1;
+    if (gemm_run(g, s)) return 1;
+    if (!f32_out) return uncast_run(o_h, out, dt, static_cast<int64_t>(M) * N, s);
+    return 0;
+}
+
+int32_t vidil_op_layernorm(const float* in, const float* gamma, const float* beta, float* out, int32_t rows, int32_t D,
+                           float eps, void* stream) {
+    if (in == nullptr || gamma == nullptr || beta == nullptr || out == nullptr) {
+        set_error("vidil_op_layernorm: null argument");
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    return layernorm_run(in, D, gamma, beta, out, true, DT_BF16, rows, D, eps, reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t vidil_op_attention_workspace_bytes(int32_t B, int32_t N, int32_t H) {
+    if (B <= 0 || N <= 0 || H <= 0) return 0;
+    const size_t rows = static_cast<size_t>(B) * N;
+    return align_up(rows * 3 * H * 64 * 2) + align_up(rows * H * 64 * 2);
+}
+
+int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    if (qkv == nullptr || out == nullptr || workspace == nullptr) {
+        set_error("vidil_op_attention: null argument");
+        return 1;
+    }
+    if (workspace_bytes < vidil_op_attention_workspace_bytes(B, N, H) ||
+        (reinterpret_cast<uintptr_t>(workspace) & (ALIGN - 1))) {
+        set_error("vidil_op_attention: workspace too small or misaligned");
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const DType dt = (dtype == VIDIL_DTYPE_BF16) ? DT_BF16 : DT_FP16;
+    const int64_t rows = static_cast<int64_t>(B) * N;
+    uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+    void* qkv_h = base;
+    void* out_h = base + align_up(static_cast<size_t>(rows) * 3 * H * 64 * 2);
+    if (cast_run(qkv, qkv_h, dt, rows, 3 * H * 64, 3 * H * 64, s)) return 1;
+    if (attention_run(qkv_h, out_h, dt, B, N, H, scale, s)) return 1;
+    return uncast_run(out_h, out, dt, rows * H * 64, s);
+}
+
+}  // extern "C"

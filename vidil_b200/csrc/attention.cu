@@ -1,0 +1,293 @@
+// Fused scaled-dot-product attention for short ViT sequences, head_dim 64:
+//   out[b, n, h*64 + d] = softmax_j( q[b,h,n,:] . k[b,h,j,:] * scale ) @ v[b,h,j,d]
+// Reference: models/vit.py:72-83 (Attention.forward) — the reference materialises the [B,H,N,N] score
+// tensor (636 MB fp32 at B=256, L/16); here scores never leave the SM.
+//
+// q/k/v are read in place from the fused-QKV GEMM output, layout [B, N, 3, H, 64] (the reshape at
+// vit.py:72 without the permute copy), and the result is written head-merged ([B, N, H*64], the
+// transpose(1,2).reshape at vit.py:83) ready to be the proj GEMM's A operand.
+//
+// Round-1 kernel: one CTA = 64 queries of one (frame, head); 4 warps x 16 query rows; keys/values
+// streamed in 64-row blocks through a cp.async double buffer; QK^T and PV on mma.sync m16n8k16
+// (fp16/bf16 in, fp32 accumulate) fed by ldmatrix from XOR-swizzled shared memory; online softmax in
+// fp32 with exp2 on pre-scaled logits.  Per layer the kernel is HBM-bound on reading qkv once and
+// writing out once (98 FLOP/B at N=197), so the legacy tensor path is not the limiter yet; a tcgen05
+// version (S and P resident in TMEM) is the planned replacement.
+#include <math.h>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace vidil {
+namespace {
+
+constexpr int HD = 64;       // head dim
+constexpr int BQ = 64;       // queries per CTA
+constexpr int BKV = 64;      // keys per pipeline stage
+constexpr int ATT_THREADS = 128;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, bool valid) {
+    const int sz = valid ? 16 : 0;  // src-size 0 => the 16 destination bytes are zero-filled
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+__device__ __forceinline__ void ldsm_x4(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_trans(uint32_t addr, uint32_t& r0, uint32_t& r1, uint32_t& r2, uint32_t& r3) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                 : "r"(addr));
+}
+
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], const uint32_t (&a)[4], uint32_t b0,
+                                                        uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+        : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// Byte offset of 16-byte chunk `chunk` (0..7) of row `row` in a [rows][64 x 16-bit] tile whose chunks are
+// XOR-swizzled by the low row bits so ldmatrix's 8 row addresses hit 8 different bank groups.
+__device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
+    return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
+}
+
+// Copy a [64 x 64] tile (rows row0..row0+63 of a strided matrix, zero beyond `nrows`) into shared memory.
+template <typename T>
+__device__ __forceinline__ void load_tile_async(uint32_t smem_tile, const T* g, int64_t row_stride, int row0,
+                                                int nrows) {
+#pragma unroll
+    for (int i = 0; i < (BKV * 8) / ATT_THREADS; ++i) {
+        const int idx = threadIdx.x + i * ATT_THREADS;
+        const int r = idx >> 3, c = idx & 7;
+        const int gr = row0 + r;
+        const bool ok = gr < nrows;
+        const T* src = g + static_cast<int64_t>(ok ? gr : 0) * row_stride + c * 8;
+        cp_async16(smem_tile + tile_off(r, c), src, ok);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+    attention_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, float scale_log2e) {
+    __shared__ __align__(128) uint8_t smem[BQ * HD * 2 + 2 * 2 * BKV * HD * 2];  // Q | K0 V0 | K1 V1 : 40 KB
+    const uint32_t sQ = ptx::smem_u32(smem);
+    const uint32_t sKV = sQ + BQ * HD * 2;  // stage s: K at sKV + s*16384, V at +8192
+
+    const int qblk = blockIdx.x, h = blockIdx.y, b = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t tok_stride = static_cast<int64_t>(3) * H * HD;
+    const T* q_base = qkv + static_cast<int64_t>(b) * N * tok_stride + h * HD;
+    const T* k_base = q_base + static_cast<int64_t>(H) * HD;
+    const T* v_base = k_base + static_cast<int64_t>(H) * HD;
+    const int q0 = qblk * BQ;
+    const int num_kb = (N + BKV - 1) / BKV;
+
+    load_tile_async<T>(sQ, q_base, tok_stride, q0, N);
+    load_tile_async<T>(sKV, k_base, tok_stride, 0, N);
+    load_tile_async<T>(sKV + 8192, v_base, tok_stride, 0, N);
+    cp_async_commit();
+
+    uint32_t qf[4][4];  // Q fragments for the 4 k-steps over head_dim
+    float o[8][4];      // output accumulator: 16 rows x 64 dims per warp
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY};  // running max of scaled logits (rows g and g+8)
+    float l_run[2] = {0.f, 0.f};              // running sum of exp2
+
+    for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb & 1;
+        if (kb + 1 < num_kb) {
+            const uint32_t nxt = sKV + (stage ^ 1) * 16384;
+            load_tile_async<T>(nxt, k_base, tok_stride, (kb + 1) * BKV, N);
+            load_tile_async<T>(nxt + 8192, v_base, tok_stride, (kb + 1) * BKV, N);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        if (kb == 0) {
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = kk * 2 + (lane >> 4);
+                ldsm_x4(sQ + tile_off(r, c), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+            }
+        }
+
+        const uint32_t sK = sKV + stage * 16384;
+        const uint32_t sV = sK + 8192;
+
+        // S = Q K^T : 16 x 64 per warp
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+            for (int kk2 = 0; kk2 < 2; ++kk2) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), kk2 * 4 + (lane >> 3)), b0, b1, b2, b3);
+                mma16816<T>(s[nt], qf[2 * kk2], b0, b1);
+                mma16816<T>(s[nt], qf[2 * kk2 + 1], b2, b3);
+            }
+        }
+
+        // scale into the log2 domain, mask keys beyond N in the last block
+        const int key0 = kb * BKV + (lane & 3) * 2;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int key = key0 + nt * 8;
+            s[nt][0] = (key < N) ? s[nt][0] * scale_log2e : -INFINITY;
+            s[nt][1] = (key + 1 < N) ? s[nt][1] * scale_log2e : -INFINITY;
+            s[nt][2] = (key < N) ? s[nt][2] * scale_log2e : -INFINITY;
+            s[nt][3] = (key + 1 < N) ? s[nt][3] * scale_log2e : -INFINITY;
+        }
+
+        // online softmax (rows g = lane/4 and g+8; a row lives in the 4 lanes of a quad)
+        float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+            mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+        }
+        // every key block holds at least one valid key (kb*64 < N), so mx is finite here
+        const float corr0 = exp2f(m_run[0] - mx[0]);
+        const float corr1 = exp2f(m_run[1] - mx[1]);
+        m_run[0] = mx[0];
+        m_run[1] = mx[1];
+        float rs[2] = {0.f, 0.f};
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = exp2f(s[nt][0] - mx[0]);
+            s[nt][1] = exp2f(s[nt][1] - mx[0]);
+            s[nt][2] = exp2f(s[nt][2] - mx[1]);
+            s[nt][3] = exp2f(s[nt][3] - mx[1]);
+            rs[0] += s[nt][0] + s[nt][1];
+            rs[1] += s[nt][2] + s[nt][3];
+        }
+        l_run[0] = l_run[0] * corr0 + rs[0];
+        l_run[1] = l_run[1] * corr1 + rs[1];
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+            o[nd][0] *= corr0;
+            o[nd][1] *= corr0;
+            o[nd][2] *= corr1;
+            o[nd][3] *= corr1;
+        }
+
+        // O += P V : P re-used straight from the S accumulator registers as the A operand
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t pa[4];
+            pa[0] = pack2<T>(s[2 * j][0], s[2 * j][1]);
+            pa[1] = pack2<T>(s[2 * j][2], s[2 * j][3]);
+            pa[2] = pack2<T>(s[2 * j + 1][0], s[2 * j + 1][1]);
+            pa[3] = pack2<T>(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+            for (int nd2 = 0; nd2 < 4; ++nd2) {
+                uint32_t b0, b1, b2, b3;
+                const int r = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = nd2 * 2 + (lane >> 4);
+                ldsm_x4_trans(sV + tile_off(r, c), b0, b1, b2, b3);
+                mma16816<T>(o[2 * nd2], pa, b0, b1);
+                mma16816<T>(o[2 * nd2 + 1], pa, b2, b3);
+            }
+        }
+        __syncthreads();  // all warps are done with this stage before it is refilled
+    }
+
+    // finalise: full row sums across the quad, normalise, stage through this warp's rows of the Q tile
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 1);
+        l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 2);
+    }
+    const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+    const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+        // element columns nd*8 + tq*2 + {0,1}: chunk nd, byte offset tq*4 inside the chunk
+        const int r0 = warp * 16 + g, r1 = r0 + 8;
+        const uint32_t v0 = pack2<T>(o[nd][0] * inv0, o[nd][1] * inv0);
+        const uint32_t v1 = pack2<T>(o[nd][2] * inv1, o[nd][3] * inv1);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + tile_off(r0, nd) + tq * 4), "r"(v0) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + tile_off(r1, nd) + tq * 4), "r"(v1) : "memory");
+    }
+    __syncwarp();
+    T* o_base = out + static_cast<int64_t>(b) * N * (H * HD) + h * HD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + i * 32;  // 16 rows x 8 chunks
+        const int r = warp * 16 + (idx >> 3), c = idx & 7;
+        const int n = q0 + r;
+        if (n < N) {
+            uint4 v;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                         : "r"(sQ + tile_off(r, c)));
+            *reinterpret_cast<uint4*>(o_base + static_cast<int64_t>(n) * (H * HD) + c * 8) = v;
+        }
+    }
+}
+
+}  // namespace
+
+int attention_run(const void* qkv, void* out, DType dt, int B, int N, int H, float scale, cudaStream_t stream) {
+    if (B <= 0 || N <= 0 || H <= 0) return 0;
+    if (H > 65535 || B > 65535) {
+        set_error("attention: H and B must be <= 65535 (grid y/z limits); got H=%d B=%d", H, B);
+        return 1;
+    }
+    const dim3 grid((N + BQ - 1) / BQ, H, B);
+    const float sl2 = scale * 1.4426950408889634f;
+    if (dt == DT_BF16)
+        attention_kernel<__nv_bfloat16><<<grid, ATT_THREADS, 0, stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), N, H, sl2);
+    else
+        attention_kernel<__half><<<grid, ATT_THREADS, 0, stream>>>(reinterpret_cast<const __half*>(qkv),
+                                                                   reinterpret_cast<__half*>(out), N, H, sl2);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+}  // namespace vidil

@@ -1,0 +1,503 @@
+// D[M,N] = A[M,K] * W[N,K]^T with a fused epilogue — the dense contraction behind every Linear on
+// the frame-encoding path (reference: models/vit.py:51,53,72,84 qkv/proj; :29,31,36,39 fc1/fc2;
+// the patch-embed Conv2d at :144-145 as a GEMM over im2col rows; CLIP's visual_projection and the
+// image x phrase-bank similarity at run_visual_tokenization.py:276).
+//
+// sm_100a design (one persistent kernel, warp-specialised):
+//   warp 0 / lane 0 : TMA producer   — cp.async.bulk.tensor 2-D tiles of A and W into a ring of
+//                                      SWIZZLE_128B shared-memory stages, completion on mbarriers
+//   warp 1 / lane 0 : MMA issuer     — tcgen05.mma kind::f16 (fp16 or bf16 in, fp32 accumulate in TMEM);
+//                                      tcgen05.commit releases smem stages and publishes accumulators
+//   warp 2          : TMEM allocator — 512 columns = two 128x256 fp32 accumulators (double buffered)
+//   warps 4..11     : epilogue       — tcgen05.ld TMEM->registers, bias / GELU / residual / position
+//                                      add, 16-byte global stores; overlaps the next tile's MMAs
+// With CTA_GROUP == 2 two CTAs of a cluster (one TPC) run cta_group::2 MMAs on a 256x256 tile: each
+// CTA stages its own 128 rows of A and half (128 rows) of the W tile, halving shared-memory and L2
+// operand traffic per FLOP; accumulator rows [128r, 128r+128) live in CTA r's TMEM.
+#include <stdarg.h>
+#include <stdio.h>
+
+#include <string>
+#include <type_traits>
+
+#include "kernels.h"
+#include "ptx.cuh"
+
+namespace vidil {
+
+namespace {
+
+constexpr int BLOCK_M = 128;  // rows per CTA (UMMA M = 128 * CTA_GROUP)
+constexpr int BLOCK_N = 256;  // UMMA N
+constexpr int BLOCK_K = 64;   // one 128-byte swizzle atom of 16-bit elements
+constexpr int UMMA_K = 16;
+constexpr int NUM_EPI_WARPS = 8;
+constexpr int NUM_THREADS = (4 + NUM_EPI_WARPS) * 32;
+constexpr int NUM_ACC = 2;  // TMEM accumulator buffers
+constexpr int TMEM_COLS = NUM_ACC * BLOCK_N;
+
+template <int CG>
+struct Cfg {
+    static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;         // 16 KB
+    static constexpr int W_ROWS = BLOCK_N / CG;                   // rows of W this CTA stages
+    static constexpr int W_BYTES = W_ROWS * BLOCK_K * 2;          // 32 KB or 16 KB
+    static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;         // 48 KB or 32 KB
+    static constexpr int STAGES = (CG == 1) ? 4 : 6;              // 192 KB of operand ring either way
+    static constexpr int BAR_BYTES = 256;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+};
+
+struct EpiArgs {
+    const float* bias;
+    void* out;
+    int64_t ldo;
+    const float* pos;
+    int patches_per_frame;
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+
+template <typename T>
+__device__ __forceinline__ uint32_t pack2(float a, float b);
+template <>
+__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
+    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+template <>
+__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
+    __half2 v = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// One 32-column slice of one accumulator row: v[] holds acc, (row, col0) are global coordinates.
+template <typename T, int EPI>
+__device__ __forceinline__ void epilogue_chunk(float (&v)[32], const EpiArgs& e, int row, int col0, int N) {
+    const bool full = (col0 + 32 <= N);
+    if (e.bias != nullptr) {
+        if (full) {
+            const float4* b4 = reinterpret_cast<const float4*>(e.bias + col0);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 b = __ldg(b4 + i);
+                v[4 * i + 0] += b.x;
+                v[4 * i + 1] += b.y;
+                v[4 * i + 2] += b.z;
+                v[4 * i + 3] += b.w;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (col0 + i < N) v[i] += __ldg(e.bias + col0 + i);
+        }
+    }
+    if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = gelu_erf(v[i]);
+    } else if constexpr (EPI == EPI_QUICKGELU) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
+    }
+
+    if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_QUICKGELU) {
+        T* o = reinterpret_cast<T*>(e.out) + static_cast<int64_t>(row) * e.ldo + col0;
+        if (full) {
+            uint4* o4 = reinterpret_cast<uint4*>(o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                uint4 u;
+                u.x = pack2<T>(v[8 * i + 0], v[8 * i + 1]);
+                u.y = pack2<T>(v[8 * i + 2], v[8 * i + 3]);
+                u.z = pack2<T>(v[8 * i + 4], v[8 * i + 5]);
+                u.w = pack2<T>(v[8 * i + 6], v[8 * i + 7]);
+                o4[i] = u;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (col0 + i < N) o[i] = static_cast<T>(v[i]);
+        }
+    } else {
+        int64_t orow = row;
+        if constexpr (EPI == EPI_PATCH) {
+            const int f = row / e.patches_per_frame;
+            const int p = row - f * e.patches_per_frame;
+            orow = static_cast<int64_t>(f) * (e.patches_per_frame + 1) + 1 + p;
+            const float* ps = e.pos + static_cast<int64_t>(1 + p) * N + col0;
+            if (full) {
+                const float4* p4 = reinterpret_cast<const float4*>(ps);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float4 b = __ldg(p4 + i);
+                    v[4 * i + 0] += b.x;
+                    v[4 * i + 1] += b.y;
+                    v[4 * i + 2] += b.z;
+                    v[4 * i + 3] += b.w;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (col0 + i < N) v[i] += __ldg(ps + i);
+            }
+        }
+        float* o = reinterpret_cast<float*>(e.out) + orow * e.ldo + col0;
+        if (full) {
+            float4* o4 = reinterpret_cast<float4*>(o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                float4 r = make_float4(v[4 * i + 0], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+                if constexpr (EPI == EPI_RESID) {
+                    const float4 old = o4[i];
+                    r.x += old.x;
+                    r.y += old.y;
+                    r.z += old.z;
+                    r.w += old.w;
+                }
+                o4[i] = r;
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+                if (col0 + i < N) {
+                    if constexpr (EPI == EPI_RESID)
+                        o[i] += v[i];
+                    else
+                        o[i] = v[i];
+                }
+        }
+    }
+}
+
+template <typename T, int EPI, int CG>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+    gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
+                        int M, int N, int K, EpiArgs epi) {
+    using C = Cfg<CG>;
+    extern __shared__ uint8_t smem_raw[];
+    // SWIZZLE_128B tiles must sit on 1024-byte boundaries of the shared address space.
+    const uint32_t raw_addr = ptx::smem_u32(smem_raw);
+    uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint64_t* empty_bar = full_bar + C::STAGES;
+    uint64_t* tmem_full_bar = empty_bar + C::STAGES;
+    uint64_t* tmem_empty_bar = tmem_full_bar + NUM_ACC;
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tmem_empty_bar + NUM_ACC);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t cta_rank = (CG == 2) ? ptx::cluster_ctarank() : 0u;
+    const bool is_leader = (cta_rank == 0);
+
+    if constexpr (CG == 2) ptx::cluster_sync();  // peer CTA is resident before any cross-CTA traffic
+
+    if (warp == 0 && lane == 0) {
+        ptx::prefetch_tensormap(&map_a);
+        ptx::prefetch_tensormap(&map_w);
+    }
+    if (warp == 1 && lane == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(&full_bar[s], CG);  // one arrive per producing CTA (+ the TMA bytes)
+            ptx::mbar_init(&empty_bar[s], 1);  // one tcgen05.commit
+        }
+        for (int a = 0; a < NUM_ACC; ++a) {
+            ptx::mbar_init(&tmem_full_bar[a], 1);                    // one tcgen05.commit
+            ptx::mbar_init(&tmem_empty_bar[a], CG * NUM_EPI_WARPS);  // one arrive per epilogue warp
+        }
+        ptx::fence_mbar_init();
+    }
+    if (warp == 2) ptx::tmem_alloc<CG>(tmem_ptr_smem, TMEM_COLS);
+    ptx::tcgen05_fence_before();
+    if constexpr (CG == 2)
+        ptx::cluster_sync();
+    else
+        __syncthreads();
+    ptx::tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_ptr_smem;
+
+    // Static persistent schedule, identical in every role: cluster c takes tiles c, c+G, c+2G, ...
+    // N is the fast index so concurrently running clusters share a few A row-bands and all of W in L2.
+    const int tiles_m = (M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
+    const int tiles_n = (N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = tiles_m * tiles_n;
+    const int cluster_id = blockIdx.x / CG;
+    const int num_clusters = gridDim.x / CG;
+    const int num_kb = K / BLOCK_K;
+
+    if (warp == 0) {
+        if (lane == 0) {
+            // ===================== TMA producer =====================
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters) {
+                const int m0 = ((t / tiles_n) * CG + static_cast<int>(cta_rank)) * BLOCK_M;
+                const int n0 = (t % tiles_n) * BLOCK_N + static_cast<int>(cta_rank) * C::W_ROWS;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * C::STAGE_BYTES;
+                    uint8_t* sw = sa + C::A_BYTES;
+                    if (CG == 1) {
+                        ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+                        ptx::tma_load_2d(&map_a, &full_bar[stage], sa, kb * BLOCK_K, m0);
+                        ptx::tma_load_2d(&map_w, &full_bar[stage], sw, kb * BLOCK_K, n0);
+                    } else {
+                        // Both CTAs' bytes are credited to the leader's barrier, which the MMA issuer waits on.
+                        if (is_leader)
+                            ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES * CG);
+                        else
+                            ptx::mbar_arrive_cluster(&full_bar[stage], 0);
+                        ptx::tma_load_2d_pair(&map_a, &full_bar[stage], sa, kb * BLOCK_K, m0);
+                        ptx::tma_load_2d_pair(&map_w, &full_bar[stage], sw, kb * BLOCK_K, n0);
+                    }
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0 && is_leader) {
+            // ===================== MMA issuer (leader CTA only) =====================
+            constexpr bool kIsBf16 = std::is_same<T, __nv_bfloat16>::value;
+            constexpr uint32_t idesc = ptx::make_idesc_f16(kIsBf16, BLOCK_M * CG, BLOCK_N);
+            int stage = 0;
+            uint32_t phase = 0;
+            int iter = 0;
+            for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
+                const int acc = iter & 1;
+                const uint32_t acc_phase = (iter >> 1) & 1;
+                ptx::mbar_wait(&tmem_empty_bar[acc], acc_phase ^ 1);  // epilogue drained this accumulator
+                ptx::tcgen05_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * BLOCK_N;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    ptx::mbar_wait(&full_bar[stage], phase);  // TMA bytes of this stage have landed
+                    ptx::tcgen05_fence_after();
+                    const uint32_t sa = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+                    const uint64_t da = ptx::make_kmajor_sw128_desc(sa);
+                    const uint64_t dw = ptx::make_kmajor_sw128_desc(sa + C::A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        // +32 bytes per UMMA_K step inside the swizzle atom: start-address field is >>4
+                        ptx::umma_f16<CG>(tmem_d, da + 2 * k, dw + 2 * k, idesc, (kb | k) != 0);
+                    }
+                    ptx::umma_commit<CG>(&empty_bar[stage]);  // stage reusable once these MMAs retire
+                    if (kb == num_kb - 1) ptx::umma_commit<CG>(&tmem_full_bar[acc]);
+                    if (++stage == C::STAGES) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp >= 4) {
+        // ===================== Epilogue =====================
+        const int ew = warp - 4;
+        const int lane_quarter = ew & 3;  // TMEM lanes a warp may read: 32 * (warp % 4) ...
+        const int col_half = ew >> 2;     // this warp's 128-column half of the 256-column accumulator
+        int iter = 0;
+        for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
+            const int acc = iter & 1;
+            const uint32_t acc_phase = (iter >> 1) & 1;
+            const int m0 = ((t / tiles_n) * CG + static_cast<int>(cta_rank)) * BLOCK_M;
+            const int n0 = (t % tiles_n) * BLOCK_N;
+            const int row = m0 + lane_quarter * 32 + lane;
+            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+            ptx::tcgen05_fence_after();
+            const uint32_t taddr =
+                tmem_base + (static_cast<uint32_t>(lane_quarter * 32) << 16) + acc * BLOCK_N + col_half * 128;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+                ptx::tmem_ld_wait();
+                if (c == 3) {
+                    // All of this warp's TMEM reads for the tile are complete: hand the accumulator back.
+                    ptx::tcgen05_fence_before();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CG == 1)
+                            ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                        else
+                            ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+                    }
+                }
+                const int col0 = n0 + col_half * 128 + c * 32;
+                if (row < M && col0 < N) {
+                    float v[32];
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                    epilogue_chunk<T, EPI>(v, epi, row, col0, N);
+                }
+            }
+        }
+    }
+
+    // Teardown: every role is done (the epilogue's last wait implies all MMAs and TMA loads retired).
+    ptx::tcgen05_fence_before();
+    if constexpr (CG == 2)
+        ptx::cluster_sync();
+    else
+        __syncthreads();
+    if (warp == 2) ptx::tmem_dealloc<CG>(tmem_base, TMEM_COLS);
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        // Resolved through the runtime so the library never links libcuda.so directly.
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 2-D K-major operand map: dims {K (inner), rows}, box {64, box_rows}, 128-byte swizzle, zero OOB fill.
+int encode_operand_map(CUtensorMap* out, DType dt, const void* ptr, uint64_t K, uint64_t rows,
+                       uint64_t ld_elems, uint32_t box_rows) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return 1;
+    }
+    const cuuint64_t dims[2] = {K, rows};
+    const cuuint64_t strides[1] = {ld_elems * 2};
+    const cuuint32_t box[2] = {BLOCK_K, box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUtensorMapDataType cdt = (dt == DT_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
+    CUresult r = fn(out, cdt, 2, const_cast<void*>(ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d (ptr=%p K=%llu rows=%llu ld=%llu box_rows=%u)",
+                  static_cast<int>(r), ptr, (unsigned long long)K, (unsigned long long)rows,
+                  (unsigned long long)ld_elems, box_rows);
+        return 1;
+    }
+    return 0;
+}
+
+template <typename T, int EPI, int CG>
+int launch(const GemmProblem& p, cudaStream_t stream) {
+    using C = Cfg<CG>;
+    auto kern = gemm_tcgen05_kernel<T, EPI, CG>;
+    static bool configured = false;  // per instantiation
+    if (!configured) {
+        VIDIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        configured = true;
+    }
+    const int tiles_m = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
+    const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
+    const int num_tiles = tiles_m * tiles_n;
+    int clusters = gemm_num_sms() / CG;
+    if (clusters > num_tiles) clusters = num_tiles;
+    if (clusters < 1) return 0;
+
+    EpiArgs e{p.bias, p.out, p.ldo, p.pos, p.patches_per_frame};
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * CG);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = C::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CG;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    VIDIL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p.map_a, p.map_w, p.M, p.N, p.K, e));
+    count_launches(1);
+    return 0;
+}
+
+template <typename T, int CG>
+int dispatch_epi(const GemmProblem& p, cudaStream_t s) {
+    switch (p.epi) {
+        case EPI_STORE: return launch<T, EPI_STORE, CG>(p, s);
+        case EPI_GELU: return launch<T, EPI_GELU, CG>(p, s);
+        case EPI_QUICKGELU: return launch<T, EPI_QUICKGELU, CG>(p, s);
+        case EPI_RESID: return launch<T, EPI_RESID, CG>(p, s);
+        case EPI_PATCH: return launch<T, EPI_PATCH, CG>(p, s);
+        case EPI_STORE_F32: return launch<T, EPI_STORE_F32, CG>(p, s);
+        default: set_error("gemm: unknown epilogue mode %d", p.epi); return 1;
+    }
+}
+
+}  // namespace
+
+int gemm_num_sms() {
+    static int sms = 0;
+    if (sms == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        cudaDeviceProp prop;
+        if (cudaGetDeviceProperties(&prop, dev) != cudaSuccess) return 0;
+        if (prop.major != 10) {
+            set_error("vidil_b200 kernels are built for sm_100a only; device is sm_%d%d", prop.major, prop.minor);
+            return 0;
+        }
+        sms = prop.multiProcessorCount;
+    }
+    return sms;
+}
+
+int gemm_prepare(GemmProblem& p) {
+    if (p.M <= 0 || p.N <= 0 || p.K <= 0) {
+        set_error("gemm: empty problem M=%d N=%d K=%d", p.M, p.N, p.K);
+        return 1;
+    }
+    if (p.K % BLOCK_K != 0) {
+        set_error("gemm: K=%d must be a multiple of %d", p.K, BLOCK_K);
+        return 1;
+    }
+    if (p.lda % 8 != 0 || p.ldw % 8 != 0 || (reinterpret_cast<uintptr_t>(p.A) & 15) ||
+        (reinterpret_cast<uintptr_t>(p.W) & 15)) {
+        set_error("gemm: operands must be 16-byte aligned with leading dimensions that are multiples of 8");
+        return 1;
+    }
+    const bool out_f32 = (p.epi == EPI_RESID || p.epi == EPI_PATCH || p.epi == EPI_STORE_F32);
+    if (p.ldo % (out_f32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15)) {
+        set_error("gemm: output must be 16-byte aligned with a 16-byte multiple leading dimension");
+        return 1;
+    }
+    if (p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15)) {
+        set_error("gemm: bias must be 16-byte aligned");
+        return 1;
+    }
+    if (p.epi == EPI_PATCH && (p.pos == nullptr || p.patches_per_frame <= 0)) {
+        set_error("gemm: EPI_PATCH needs a position table and patches_per_frame");
+        return 1;
+    }
+    if (p.cta_group != 1 && p.cta_group != 2) {
+        set_error("gemm: cta_group must be 1 or 2");
+        return 1;
+    }
+    if (encode_operand_map(&p.map_a, p.dt, p.A, p.K, p.M, p.lda, BLOCK_M)) return 1;
+    if (encode_operand_map(&p.map_w, p.dt, p.W, p.K, p.N, p.ldw, BLOCK_N / p.cta_group)) return 1;
+    p.prepared = true;
+    return 0;
+}
+
+int gemm_run(const GemmProblem& p, cudaStream_t stream) {
+    if (!p.prepared) {
+        set_error("gemm_run called on an unprepared problem");
+        return 1;
+    }
+    if (gemm_num_sms() == 0) return 1;
+    if (p.dt == DT_BF16)
+        return p.cta_group == 2 ? dispatch_epi<__nv_bfloat16, 2>(p, stream) : dispatch_epi<__nv_bfloat16, 1>(p, stream);
+    return p.cta_group == 2 ? dispatch_epi<__half, 2>(p, stream) : dispatch_epi<__half, 1>(p, stream);
+}
+
+}  // namespace vidil

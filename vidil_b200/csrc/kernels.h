@@ -1,0 +1,103 @@
+// Internal C++ interface between the C-ABI layer (api.cu) and the kernel translation units.
+// Nothing here is exported; the public surface is include/vidil_b200.h.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+namespace vidil {
+
+// Arithmetic type of the tensor-core operands (accumulation is always fp32).
+enum DType : int { DT_BF16 = 0, DT_FP16 = 1 };
+
+// What the GEMM epilogue does with the fp32 accumulator tile (acc = A * W^T):
+enum EpiMode : int {
+    EPI_STORE = 0,      // out[T]   = acc + bias
+    EPI_GELU = 1,       // out[T]   = gelu_erf(acc + bias)            (BLIP ViT Mlp, vit.py:35-41)
+    EPI_QUICKGELU = 2,  // out[T]   = x * sigmoid(1.702 x), x = acc+bias   (CLIP quick_gelu)
+    EPI_RESID = 3,      // out[f32] += acc + bias                     (residual stream, vit.py:108-109)
+    EPI_PATCH = 4,      // out[f32][frame*(P+1)+1+p] = acc + bias + pos[1+p]   (vit.py:182-187)
+    EPI_STORE_F32 = 5,  // out[f32] = acc + bias
+    EPI_COUNT = 6
+};
+
+void set_error(const char* fmt, ...);
+const char* get_error();
+// Every launcher adds the number of kernels it enqueued (reported by vidil_kernel_launch_count()).
+void count_launches(int n);
+int64_t launch_count();
+
+#define VIDIL_CUDA_OK(expr)                                                                  \
+    do {                                                                                     \
+        cudaError_t _e = (expr);                                                             \
+        if (_e != cudaSuccess) {                                                             \
+            ::vidil::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+            return 1;                                                                        \
+        }                                                                                    \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------
+// GEMM  D[M,N] = A[M,K] * W[N,K]^T  (both operands K-major, 16-bit), tcgen05 + TMA.
+// ---------------------------------------------------------------------------------------
+struct GemmProblem {
+    DType dt = DT_BF16;
+    int epi = EPI_STORE;
+    int cta_group = 2;  // 1: one CTA per 128x256 tile; 2: CTA pair per 256x256 tile (cta_group::2)
+    int M = 0, N = 0, K = 0;
+    const void* A = nullptr;  // [M, lda] 16-bit
+    int64_t lda = 0;
+    const void* W = nullptr;  // [N, ldw] 16-bit
+    int64_t ldw = 0;
+    const float* bias = nullptr;  // [N] or null
+    void* out = nullptr;          // [M, ldo] T or fp32 depending on epi
+    int64_t ldo = 0;
+    const float* pos = nullptr;  // EPI_PATCH: [P+1, N] fp32
+    int patches_per_frame = 0;   // EPI_PATCH
+    // filled by gemm_prepare():
+    CUtensorMap map_a;
+    CUtensorMap map_w;
+    bool prepared = false;
+};
+
+int gemm_prepare(GemmProblem& p);                          // validates + encodes the TMA maps
+int gemm_run(const GemmProblem& p, cudaStream_t stream);   // launches; asynchronous
+int gemm_num_sms();
+
+// ---------------------------------------------------------------------------------------
+// LayerNorm over the last dim of an fp32 matrix (vit.py:94,99,192; eps 1e-6 BLIP / 1e-5 CLIP).
+//   in : fp32 rows at in + r * in_row_stride      out: T or fp32 rows at out + r * D
+// ---------------------------------------------------------------------------------------
+int layernorm_run(const float* in, int64_t in_row_stride, const float* gamma, const float* beta, void* out,
+                  bool out_f32, DType dt, int rows, int D, float eps, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------
+// Fused softmax attention over packed qkv [B, N, 3, H, 64] -> out [B, N, H*64] (vit.py:72-83).
+// ---------------------------------------------------------------------------------------
+int attention_run(const void* qkv, void* out, DType dt, int B, int N, int H, float scale, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------
+// Elementwise / layout kernels.
+// ---------------------------------------------------------------------------------------
+// fp32 -> T cast of a dense [rows, cols] matrix into [rows, ld_out] (pad columns zeroed).
+int cast_run(const float* in, void* out, DType dt, int64_t rows, int64_t cols, int64_t ld_out,
+             cudaStream_t stream);
+// NCHW fp32 frames -> patch matrix [B*P, Kpad] T, column = c*ps*ps + i*ps + j (Conv2d weight order).
+int im2col_run(const float* frames, void* patches, DType dt, int B, int C, int img, int ps, int Kpad,
+               cudaStream_t stream);
+// resid[b*(P+1) + 0, :] = cls + pos[0]  (vit.py:184-187)
+int cls_pos_run(const float* cls, const float* pos, float* resid, int B, int tokens, int D, cudaStream_t stream);
+// out[r,:] = in[r,:] / ||in[r,:]||_2
+int l2norm_run(const float* in, float* out, int rows, int D, cudaStream_t stream);
+// T -> fp32 (operator-level tests read 16-bit results back through this)
+int uncast_run(const void* in, float* out, DType dt, int64_t n, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------
+// Top-k of each row of an fp32 score matrix with exact fp32 re-ranking of the candidates
+// (run_visual_tokenization.py:276,306).
+// ---------------------------------------------------------------------------------------
+int topk_rerank_run(const float* scores, int64_t ld_scores, const float* img, const float* bank, int F, int T,
+                    int D, int k, float* out_scores, int32_t* out_idx, cudaStream_t stream);
+
+}  // namespace vidil
