@@ -142,6 +142,7 @@ def main():
     golden_vit("tiny", 32, 2, 1, [0, 1], "vit_tiny.npz")
     golden_vit("large", 224, 1, 4, [0, 11, 23], "vit_large_224.npz")
     golden_vit("base", 384, 1, 8, [0, 11], "vit_base_384.npz")
+    rs.uninstall_shims()
     golden_clip("tiny", 2, 1, "clip_tiny.npz")
     golden_clip("large14", 1, 8, "clip_large14.npz")
     golden_tokenization()

@@ -80,6 +80,15 @@ def install_shims() -> None:
         _mod("fairscale.nn.checkpoint.checkpoint_activations", checkpoint_wrapper=lambda m, *a, **k: m)
 
 
+def uninstall_shims() -> None:
+    """Remove the stand-in packages again (transformers probes `timm` with find_spec and chokes on a bare
+    module object)."""
+    for name in [n for n in sys.modules if n == "timm" or n.startswith("timm.") or n == "fairscale" or
+                 n.startswith("fairscale.")]:
+        if getattr(sys.modules[name], "__file__", None) is None:
+            del sys.modules[name]
+
+
 def import_reference_vit():
     """Returns the reference's models.vit module (VisionTransformer, interpolate_pos_embed, ...)."""
     if not reference_available():
