@@ -1,0 +1,397 @@
+"""Headline benchmark: frames/s through the BLIP ViT-L/16 @224 forward (BASELINE.json configs[1]: batch 256
+synthetic 224x224 frames, bf16 operands, forward only), one process per GPU.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]            # this repo's sm_100a path
+    python bench.py --impl reference ...                           # the CPU port of the reference's vit.py (oracle/)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...          # N ranks, each its own 256-frame batches (weak scaling)
+
+One step = one 256-frame batch through vidil_vit_forward.  Prints ONE JSON line on rank 0 with
+  value     frames/s, inputs resident in HBM, CUDA events around exactly K steps, max over ranks
+  e2e       the same through the host-buffer call (VisionTransformer.encode_host -> vidil_vit_forward_host): pinned
+            host frames -> H2D -> forward -> D2H of the [B,197,1024] fp32 tokens, every step
+  roofline  the tcgen05 GEMM kernel: algorithmic FLOPs / its event-timed device time inside the timed steps
+  cpu_baseline  the oracle port of models/vit.py timed on this box's host cores (rank 0, N=1 only)
+Other workloads (not the driver's line): --workload clip | sim.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+VIT = {"large": (1024, 24, 16), "base": (768, 12, 12)}
+
+
+def flops_per_frame(D, depth, tokens, patch, proj_dim=0):
+    per_layer = 2 * tokens * D * 3 * D + 2 * tokens * D * D + 4 * tokens * D * 4 * D + 4 * tokens * tokens * D
+    return float(depth * per_layer + 2 * (tokens - 1) * 3 * patch * patch * D + 2 * D * proj_dim)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return dict(tflops=float(p.get("bf16_tflops", 1590.0)), tflops_sustained=float(p.get("bf16_tflops_sustained", 1400.0)),
+                    hbm_gbs=float(p.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json)")
+    return dict(tflops=1590.0, tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clock / throttle-reason samples of one GPU while the timed region runs."""
+
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.gpu, self.proc, self.path = gpu_index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw, reasons = [], [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        with open(self.path) as f:
+            for line in f:
+                parts = [p.strip() for p in line.split(",")]
+                if len(parts) < 7:
+                    continue
+                try:
+                    sm.append(float(parts[0]))
+                    mx.append(float(parts[1]))
+                    pw.append(float(parts[2]))
+                except ValueError:
+                    continue
+                for n, v in zip(names, parts[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+        os.unlink(self.path)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "power_w": round(statistics.median(pw), 1),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def dist_env(args):
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit(f"--gpus {args.gpus} needs torchrun --nproc-per-node {args.gpus}")
+        raise SystemExit(f"WORLD_SIZE={world} but --gpus {args.gpus}")
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference's vit.py on this box's host cores
+# ---------------------------------------------------------------------------------------------------------------------
+def cpu_vit_frames_per_s(vit, image_size, frames_per_step, steps, warmup, budget_s=None):
+    import torch
+
+    from oracle import vit_oracle, weights as W
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    D, depth, heads = VIT[vit]
+    sd = W.vit_state_dict(vit, image_size, seed=0)
+    x = W.frames(frames_per_step, image_size, seed=0)
+    for _ in range(warmup):
+        vit_oracle.vit_forward(sd, x, heads)
+    t0 = time.perf_counter()
+    done = 0
+    for _ in range(steps):
+        vit_oracle.vit_forward(sd, x, heads)
+        done += 1
+        if budget_s is not None and time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done * frames_per_step / dt, dt / done * 1e3, cores, done
+
+
+def run_reference(args):
+    rank, world, _ = dist_env(args) if "RANK" in os.environ else (0, 1, 0)
+    if rank != 0:
+        return
+    D, depth, heads = VIT[args.vit]
+    tokens = (args.image_size // 16) ** 2 + 1
+    fps, ms, cores, done = cpu_vit_frames_per_s(args.vit, args.image_size, args.ref_frames, args.steps, args.warmup)
+    sample = (f"{args.ref_frames} frames per step x {done} steps of the {args.batch}-frame workload; oracle/vit_oracle.py "
+              f"(restatement of models/vit.py:180-194, fp32, torch CPU kernels, {cores} threads)")
+    line = {
+        "impl": "reference", "metric": "frames/sec encoded", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": done, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, tokens),
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, tokens):
+    return {"workload": f"BLIP ViT-{args.vit[0].upper()}/16 @{args.image_size} forward only, batch {args.batch} synthetic "
+                        f"{args.image_size}x{args.image_size}x3 frames per GPU per step (BASELINE.json configs[1])",
+            "frames_per_step_per_gpu": args.batch, "tokens_per_frame": tokens, "image_size": args.image_size,
+            "l2_policy": "inputs larger than L2: 154 MB of fp32 frames per step from 2 rotating buffers; every layer "
+                         "streams 0.1-0.4 GB of activations",
+            "parallelism": f"dp{args.gpus} (frames sharded, weights replicated, no collective in the step)"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------------------------
+def run_vit(args):
+    import torch
+    import torch.distributed as dist
+
+    from vidil_b200 import _lib, distributed as vdist
+    from vidil_b200.blip import create_vit
+
+    rank, world, local = dist_env(args)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU path for the product (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        vdist.init_distributed_mode("nccl")
+
+    B, K, Wm = args.batch, args.steps, args.warmup
+    D, depth, heads = VIT[args.vit]
+    tokens = (args.image_size // 16) ** 2 + 1
+    gflop_frame = flops_per_frame(D, depth, tokens, 16) / 1e9
+    peaks = measured_peaks()
+
+    torch.manual_seed(1234 + rank)
+    model, width = create_vit(args.vit, args.image_size, compute_dtype=args.dtype)
+    with torch.no_grad():  # exercise bias / affine paths; values stay at init scale
+        for name, p in model.named_parameters():
+            if name.endswith(".bias"):
+                p.normal_(0.0, 0.02)
+            elif "norm" in name and name.endswith(".weight"):
+                p.normal_(1.0, 0.02)
+    model = model.to(dev).eval()
+    frames = [torch.randn(B, 3, args.image_size, args.image_size, device=dev) for _ in range(2)]
+    out = model(frames[0])  # packs weights, sizes the workspace
+    assert tuple(out.shape) == (B, tokens, D) and bool(torch.isfinite(out).all())
+    enc = model._ensure_packed()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident throughput ---------------------------------------------------------------------------------
+    for i in range(Wm):
+        model(frames[i & 1])
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    enc.set_profiling(True)
+    launches0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(K):
+        model(frames[i & 1])
+    ev1.record()
+    barrier()
+    launches = _lib.launch_count() - launches0
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    prof = enc.read_profile()
+    enc.set_profiling(False)
+    clocks = sampler.stop() if rank == 0 else None
+
+    # same K steps without the per-kernel events, to show what the instrumentation costs
+    barrier()
+    ev0.record()
+    for i in range(K):
+        model(frames[i & 1])
+    ev1.record()
+    barrier()
+    ms_total_plain = max_over_ranks(ev0.elapsed_time(ev1))
+    ms_best = min(ms_total, ms_total_plain)
+    fps = world * B * K / (ms_best / 1e3)
+
+    # ---- end to end through the host-buffer call --------------------------------------------------------------------
+    host_in = [torch.randn(B, 3, args.image_size, args.image_size).pin_memory() for _ in range(2)]
+    host_out = torch.empty(B, tokens, D, dtype=torch.float32).pin_memory()
+    for i in range(max(2, Wm // 2)):
+        model.encode_host(host_in[i & 1], out=host_out)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        model.encode_host(host_in[i & 1], out=host_out)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_fps = world * B * K / e2e_s
+    checksum = float(host_out[:, 0].double().abs().mean())
+
+    # ---- the path's one collective: all-gather of per-rank result rows (JSON), rank-0 merge --------------------------
+    t0 = time.perf_counter()
+    rows = {f"rank{rank}_frame{i}": {"cls_l1": float(host_out[i, 0].abs().sum())} for i in range(0, B, 32)}
+    merged = vdist.gather_and_write(rows, None, device=dev)
+    gather_ms = (time.perf_counter() - t0) * 1e3
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    g = prof["gemm"]
+    gemm_tflops = g["flops"] / (g["ms"] / 1e3) / 1e12 if g["ms"] > 0 else 0.0
+    step_ms = ms_best / K
+    classes = {k: {"ms_per_step": v["ms"] / K, "launches_per_step": v["launches"] / K,
+                   "tflops": (v["flops"] / (v["ms"] / 1e3) / 1e12) if v["ms"] > 0 else 0.0,
+                   "gbs": (v["bytes"] / (v["ms"] / 1e3) / 1e9) if v["ms"] > 0 else 0.0} for k, v in prof.items()}
+    line = {
+        "metric": "frames/sec encoded", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": K, "warmup": Wm,
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+        "data": "synthetic", "config": workload_config(args, tokens),
+        "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": B * 3 * args.image_size ** 2 * 4,
+                "d2h_bytes_per_step": B * tokens * D * 4, "ms_per_step": e2e_s / K * 1e3,
+                "api": "VisionTransformer.encode_host -> vidil_vit_forward_host (pinned host buffers)",
+                "cls_checksum": checksum},
+        "gpu_launches": launches,
+        "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (patch-embed, qkv, proj, fc1, fc2: "
+                                                  f"{g['launches'] // K} launches per step)",
+                     "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
+                     "frac": gemm_tflops / peaks["tflops_sustained"], "frac_of_burst_peak": gemm_tflops / peaks["tflops"],
+                     "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
+                     "traffic": None, "share_of_step": g["ms"] / ms_total},
+        "whole_step": {"gflop_per_frame": gflop_frame, "tflops": fps / world * gflop_frame / 1e3,
+                       "frac_of_sustained_peak": fps / world * gflop_frame / 1e3 / peaks["tflops_sustained"],
+                       "frac_of_burst_peak": fps / world * gflop_frame / 1e3 / peaks["tflops"],
+                       "ms_with_kernel_events": ms_total / K, "ms_without": ms_total_plain / K},
+        "kernel_classes": classes,
+        "clocks": clocks,
+        "gather": {"ms": gather_ms, "rows": len(merged), "collective": "all_gather of length-prefixed JSON rows"},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        fps_cpu, ms_cpu, cores, done = cpu_vit_frames_per_s(args.vit, args.image_size, 8, 6, 1, budget_s=20.0)
+        line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
+                                "sample": f"8-frame batches x {done} (1 warm-up) of the same workload through "
+                                          f"oracle/vit_oracle.py (fp32 restatement of models/vit.py), {cores} torch threads"}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_sim(args):
+    """BASELINE configs[3] kernel in isolation: 2048 frames x 10k phrases x 768, top-5 (not the driver's line)."""
+    import torch
+
+    from vidil_b200 import _lib, ops
+    dev = torch.device("cuda", 0)
+    Fr, T, Dm, k = 2048, 10000, 768, 5
+    img = torch.nn.functional.normalize(torch.randn(Fr, Dm, device=dev), dim=-1)
+    bank = torch.nn.functional.normalize(torch.randn(T, Dm, device=dev), dim=-1)
+    for _ in range(args.warmup):
+        ops.sim_topk(img, bank, k)
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        ops.sim_topk(img, bank, k)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    print(json.dumps({"metric": "frames/sec scored (sim + top-k)", "value": Fr / (ms / 1e3), "unit": "frames/s",
+                      "ms_per_step": ms, "tflops": 2.0 * Fr * T * Dm / (ms / 1e3) / 1e12,
+                      "gpu_launches": _lib.launch_count() - l0,
+                      "config": {"workload": f"{Fr} frames x {T} phrases x {Dm}, top-{k}"}}), flush=True)
+
+
+def run_clip(args):
+    """CLIP ViT-L/14 image tower + projection throughput (not the driver's line)."""
+    import torch
+
+    from oracle import weights as W
+    from vidil_b200.clip import CLIPVisionB200
+    dev = torch.device("cuda", 0)
+    c = W.CLIP_CONFIGS["large14"]
+    m = CLIPVisionB200(**c, compute_dtype=args.dtype)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.normal_(0.0, 0.02)
+        for n, p in m.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.add_(1.0)
+    m = m.to(dev).eval()
+    x = [torch.randn(args.batch, 3, 224, 224, device=dev) for _ in range(2)]
+    for i in range(args.warmup):
+        m(x[i & 1])
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        m(x[i & 1])
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    fps = args.batch / (ms / 1e3)
+    gf = flops_per_frame(1024, 24, 257, 14, 768) / 1e9
+    print(json.dumps({"metric": "frames/sec encoded (CLIP ViT-L/14)", "value": fps, "unit": "frames/s", "ms_per_step": ms,
+                      "tflops": fps * gf / 1e3, "frac_of_sustained_peak": fps * gf / 1e3 / measured_peaks()["tflops_sustained"],
+                      "config": {"workload": f"CLIP ViT-L/14 @224 image tower, batch {args.batch}"}}), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="vit", choices=["vit", "clip", "sim"])
+    ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--vit", default="large", choices=list(VIT))
+    ap.add_argument("--image-size", type=int, default=224)
+    ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--ref-frames", type=int, default=4, help="--impl reference: frames per CPU step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "native":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    if args.impl == "reference":
+        return run_reference(args)
+    if args.workload == "sim":
+        return run_sim(args)
+    if args.workload == "clip":
+        return run_clip(args)
+    return run_vit(args)
+
+
+if __name__ == "__main__":
+    main()

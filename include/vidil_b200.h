@@ -105,6 +105,21 @@ int32_t vidil_vit_forward_host(vidil_encoder* enc, const float* frames_host, int
 int32_t vidil_clip_forward_host(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_embeds_host,
                                 void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 
+/* ---- per-kernel-class device timing (bench.py's roofline figures) ---------------------------- */
+/* With profiling on, every kernel a forward enqueues is bracketed by CUDA events on the caller's stream.
+ * vidil_encoder_read_profile synchronises those events, adds up elapsed time / algorithmic FLOPs / algorithmic
+ * bytes / launch counts per class since the last read, writes them to *out and resets the counters. */
+enum { VIDIL_KCLASS_GEMM = 0, VIDIL_KCLASS_ATTENTION = 1, VIDIL_KCLASS_LAYERNORM = 2, VIDIL_KCLASS_OTHER = 3,
+       VIDIL_KCLASS_COUNT = 4 };
+typedef struct vidil_kernel_stats {
+    double  ms[VIDIL_KCLASS_COUNT];
+    double  flops[VIDIL_KCLASS_COUNT];
+    double  bytes[VIDIL_KCLASS_COUNT];
+    int64_t launches[VIDIL_KCLASS_COUNT];
+} vidil_kernel_stats;
+int32_t vidil_encoder_set_profiling(vidil_encoder* enc, int32_t enable);
+int32_t vidil_encoder_read_profile(vidil_encoder* enc, vidil_kernel_stats* out);
+
 /* ---- similarity + top-k ----------------------------------------------------------------------- */
 /* img fp32 [F,D], bank fp32 [T,D] (device, D multiple of 64) -> out_scores fp32 [F,k], out_idx int32 [F,k]:
  * for each frame the k phrases with the largest fp32 dot product, best first (k <= 12). */

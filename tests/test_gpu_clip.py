@@ -1,0 +1,163 @@
+"""CLIP image path on a B200: vidil_clip_forward through the drop-in module against transformers' CLIPModel outputs
+(committed fixtures) and the CPU oracle; then the whole visual-tokenization tail (predict_video) against the oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import clip_oracle, tokenization_oracle, weights as W
+from vidil_b200 import visual_tokenization as vt
+from vidil_b200.clip import CLIPVisionB200, VidilCLIPModel
+
+pytestmark = pytest.mark.gpu
+
+# image_embeds are unit vectors in R^proj (|component| ~ 0.04): absolute tolerances on components
+EMB_TOL = {"fp16": 1e-3, "bf16": 4e-3}
+
+
+def _build(name, dtype, dev):
+    c = W.CLIP_CONFIGS[name]
+    sd = W.clip_vision_state_dict(name, seed=0)
+    m = CLIPVisionB200(**c, compute_dtype=dtype)
+    m.load_state_dict(sd)
+    return m.to(dev).eval(), sd, c
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_clip_tiny_vs_fixture_and_oracle(cuda, golden_dir, dtype):
+    m, sd, c = _build("tiny", dtype, cuda)
+    x = W.frames(2, c["image_size"], seed=1)
+    emb, hid = m(x.to(cuda), return_hidden=True)
+    g = np.load(os.path.join(golden_dir, "clip_tiny.npz"))
+    assert np.abs(emb.cpu().numpy() - g["image_embeds"]).max() < EMB_TOL[dtype] * 4   # proj 64: components ~0.125
+    ref_emb, ref_hid = clip_oracle.clip_vision_forward(sd, x, c["num_attention_heads"])
+    assert (emb.cpu() - ref_emb).abs().max() < EMB_TOL[dtype] * 4
+    rel = (hid.cpu() - ref_hid).abs().max() / ref_hid.abs().max()
+    assert rel < (2e-3 if dtype == "fp16" else 1.5e-2)
+    assert torch.allclose(emb.norm(dim=-1), torch.ones(2, device=cuda), atol=1e-5)
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_clip_large14_vs_transformers_fixture(cuda, golden_dir, dtype):
+    """openai/clip-vit-large-patch14 architecture (pipeline_config_msrvtt_test.yaml:15): N=257, patch K=588 padded to 640."""
+    m, _, c = _build("large14", dtype, cuda)
+    g = np.load(os.path.join(golden_dir, "clip_large14.npz"))
+    emb, hid = m(W.frames(1, 224, seed=1).to(cuda), return_hidden=True)
+    err = np.abs(emb.cpu().numpy() - g["image_embeds"]).max()
+    cos = float((emb.cpu().numpy() * g["image_embeds"]).sum())
+    print(f"CLIP L/14 {dtype}: image_embeds max-abs {err:.3e} cosine {cos:.6f}")
+    assert err < EMB_TOL[dtype] and cos > 0.9995
+    ref = g["last_hidden"]
+    rel = np.abs(hid.cpu().numpy()[:, g["tokens"]] - ref).max() / np.abs(ref).max()
+    assert rel < (3e-3 if dtype == "fp16" else 2e-2)
+
+
+def test_clip_host_call_and_batch_invariance(cuda):
+    m, _, c = _build("tiny", "bf16", cuda)
+    x = W.frames(9, c["image_size"], seed=3)
+    dev_out = m(x.to(cuda))
+    assert torch.equal(m.encode_host(x.pin_memory()), dev_out.cpu())
+    assert torch.equal(m(x[4:6].to(cuda)), dev_out[4:6])
+
+
+# ---- predict_video: the reference's call surface end to end ----------------------------------------------------------
+class FakeProcessor:
+    """Stands in for CLIPProcessor (its vocabulary needs a download): frames are already normalised tensors; text is
+    tokenised by a deterministic hash.  Same call signature the drop-in uses."""
+
+    def __call__(self, text=None, images=None, return_tensors="pt", padding=True, truncation=True):
+        out = {}
+        if images is not None:
+            out["pixel_values"] = torch.stack(list(images))
+        if text is not None:
+            ids = torch.zeros(len(text), 8, dtype=torch.long)
+            for i, t in enumerate(text):
+                h = [1 + (hash_byte * 7 + j) % 60 for j, hash_byte in enumerate(t.encode()[:6])]
+                ids[i, :len(h)] = torch.tensor(h)
+                ids[i, len(h)] = 63   # highest id = EOS position for CLIP's argmax pooling
+            out["input_ids"] = ids
+            out["attention_mask"] = torch.ones_like(ids)
+        return out
+
+
+class FakeDataset:
+    def __init__(self, n_videos, num_frm, size, broken=()):
+        self.annotation = [{"video": f"/data/videos/video{i}.mp4"} for i in range(n_videos)]
+        self.transform = None
+        self.num_frm, self.size, self.broken = num_frm, size, set(broken)
+
+    def __len__(self):
+        return len(self.annotation)
+
+    def __getitem__(self, i):
+        vid = int(os.path.basename(self.annotation[i]["video"])[5:-4])
+        if vid in self.broken:
+            return None, None
+        return list(W.frames(self.num_frm, self.size, seed=100 + vid)), [f"caption {vid}"]
+
+
+def _hf_tiny_clip():
+    from transformers import CLIPConfig, CLIPModel
+    c = W.CLIP_CONFIGS["tiny"]
+    vision = dict(hidden_size=c["hidden_size"], intermediate_size=c["intermediate_size"],
+                  num_hidden_layers=c["num_hidden_layers"], num_attention_heads=c["num_attention_heads"],
+                  image_size=c["image_size"], patch_size=c["patch_size"], layer_norm_eps=1e-5, hidden_act="quick_gelu")
+    text = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=1,
+                max_position_embeddings=8, vocab_size=64, hidden_act="quick_gelu", eos_token_id=63, bos_token_id=0,
+                pad_token_id=0)
+    cfg = CLIPConfig(text_config=text, vision_config=vision, projection_dim=c["projection_dim"])
+    cfg._attn_implementation = "eager"
+    torch.manual_seed(0)
+    model = CLIPModel(cfg).eval()
+    model.load_state_dict(W.clip_vision_state_dict("tiny", seed=0), strict=False)
+    return model
+
+
+def test_predict_video_matches_oracle_pipeline(cuda):
+    hf = _hf_tiny_clip()
+    num_frm, k = 4, 3
+    config = {"num_frm_visual_tokenization": num_frm, "topk_visualize": k, "early_stop_step": -1, "save_frames": False}
+    phrases = {"objects": [f"object {i}" for i in range(40)], "attributes": [f"attr {i}" for i in range(25)],
+               "scenes": [f"scene {i}" for i in range(9)], "verbs": [f"verb {i}" for i in range(30)]}
+    prompts = vt.get_prefix_prompt_functions("v1")
+    proc = FakeProcessor()
+
+    # oracle side, all on the CPU in fp32: HF text tower, oracle vision tower, reference top-k + aggregation
+    ds = FakeDataset(5, num_frm, 28, broken={2})
+    vids = [0, 1, 3, 4]
+    frames = torch.cat([torch.stack(ds[i][0]) for i in vids])
+    ref_img, _ = clip_oracle.clip_vision_forward(W.clip_vision_state_dict("tiny", seed=0), frames, 2)
+    ref_idx, ref_sims = {}, {}
+    with torch.no_grad():
+        for key, lst in phrases.items():
+            t = proc(text=[prompts[key](p) for p in lst])
+            txt = hf.get_text_features(input_ids=t["input_ids"], attention_mask=t["attention_mask"])
+            txt = getattr(txt, "pooler_output", txt)
+            txt = txt / txt.norm(dim=-1, keepdim=True)
+            ref_sims[key] = ref_img.numpy() @ txt.numpy().T
+            ref_idx[key] = tokenization_oracle.sim_topk(ref_img.numpy(), txt.numpy(), k)[1]
+
+    model = VidilCLIPModel(hf.to(cuda), compute_dtype="fp16").to(cuda)
+    got = vt.predict_video(config, FakeDataset(5, num_frm, 28, broken={2}), model, cuda, phrases, prompts,
+                           encoder_version="clip", processor=proc, frame_batch=8)
+    assert list(got) == ["video0", "video1", "video3", "video4"]          # unloadable video skipped, order kept
+    flips = 0
+    for vi, vid in enumerate(got):
+        row = got[vid]
+        assert row["caption"] == [f"caption {vids[vi]}"] and len(row["frame_tokens"]) == num_frm
+        for f in range(num_frm):
+            for key, lst in phrases.items():
+                mine = [lst.index(p) for p in row["frame_tokens"][f][key]]
+                want = ref_idx[key][vi * num_frm + f].tolist()
+                if mine != want:
+                    # only phrases whose fp32 scores are closer than the tower's fp16 error may swap
+                    s = ref_sims[key][vi * num_frm + f]
+                    for a, b in zip(mine, want):
+                        assert abs(s[a] - s[b]) < 2e-3, (vid, f, key, mine, want)
+                    flips += 1
+        # aggregation is exact given the frame tokens
+        assert row["aggregated_tokens"] == tokenization_oracle.aggregate_frame_tokens(row["frame_tokens"])
+    assert flips <= 2
+    with pytest.raises(NotImplementedError):
+        vt.predict_video(config, ds, model, cuda, phrases, prompts, encoder_version="blip", processor=proc)

@@ -1,0 +1,142 @@
+"""End-to-end parity of the BLIP ViT drop-in on a B200 (vidil_vit_forward through the reference-facing module)
+against (1) the committed outputs of the reference itself and (2) the CPU oracle on the same seeded tensors.
+
+Tolerance (BASELINE.json: "within 1e-3 fp16 tolerance"): the reference's *own* code run in fp16 differs from its fp32
+run by mean-abs 1.3e-3 / max-abs 1.2e-2 on ViT-L/16.  The native path (16-bit tensor-core operands, fp32
+accumulation, fp32 residual stream, fp32 LayerNorm/softmax statistics) must stay inside that envelope:
+fp16 operands: mean-abs <= 1e-3, max-abs <= 1.2e-2;   bf16 operands (3 fewer mantissa bits): mean-abs <= 6e-3, max-abs <= 6e-2.
+Outputs are LayerNorm'd (std ~1, |max| ~5), so these are also relative figures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import vit_oracle, weights as W
+from vidil_b200 import _lib
+from vidil_b200.blip import create_vit
+from vidil_b200.vision_transformer import VisionTransformer
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp16": (1e-3, 1.2e-2), "bf16": (6e-3, 6e-2)}
+
+
+def _build(vit, size, dtype, dev, seed=0, cta_group=0):
+    D, depth, heads = W.VIT_CONFIGS[vit]
+    sd = W.vit_state_dict(vit, size, seed=seed)
+    if vit == "tiny":
+        m = VisionTransformer(img_size=size, patch_size=16, embed_dim=D, depth=depth, num_heads=heads, compute_dtype=dtype,
+                              cta_group=cta_group)
+    else:
+        m, width = create_vit(vit, size, compute_dtype=dtype)
+        assert width == D
+        m.cta_group = cta_group
+    m.load_state_dict(sd, strict=True)
+    return m.to(dev).eval(), sd
+
+
+def _check(got, ref, dtype):
+    err = (got.double() - ref.double()).abs()
+    mean_tol, max_tol = TOL[dtype]
+    assert not torch.isnan(got).any()
+    assert err.mean().item() <= mean_tol, f"mean-abs {err.mean().item():.3e} > {mean_tol}"
+    assert err.max().item() <= max_tol, f"max-abs {err.max().item():.3e} > {max_tol}"
+    return err.mean().item(), err.max().item()
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("cta_group", [1, 2])
+def test_vit_tiny_vs_oracle_and_fixture(cuda, golden_dir, dtype, cta_group):
+    m, sd = _build("tiny", 32, dtype, cuda, cta_group=cta_group)
+    x = W.frames(2, 32, seed=0)
+    got = m(x.to(cuda)).cpu()
+    assert tuple(got.shape) == (2, 5, 128) and got.dtype == torch.float32
+    _check(got, vit_oracle.vit_forward(sd, x, 2), dtype)
+    g = np.load(os.path.join(golden_dir, "vit_tiny.npz"))
+    _check(got[:, g["tokens"]], torch.from_numpy(g["out"]), dtype)
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_vit_large_224_vs_reference_fixture(cuda, golden_dir, dtype):
+    """BASELINE config 1/2 shape: create_vit('large', 224) — 1 frame through the reference (fixture) vs the native path."""
+    g = np.load(os.path.join(golden_dir, "vit_large_224.npz"))
+    m, _ = _build("large", 224, dtype, cuda)
+    got = m(W.frames(1, 224, seed=0).to(cuda)).cpu()
+    assert tuple(got.shape) == (1, 197, 1024)
+    mean_err, max_err = _check(got[:, g["tokens"]], torch.from_numpy(g["out"]), dtype)
+    print(f"ViT-L/16@224 {dtype}: mean-abs {mean_err:.3e} max-abs {max_err:.3e} (reference fp16 envelope 1.3e-3 / 1.2e-2)")
+    assert abs(got.abs().mean().item() - float(g["out_mean_abs"])) < 2e-3
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_vit_base_384_vs_reference_fixture(cuda, golden_dir, dtype):
+    """The shipped pipeline configuration (pipeline_config_msrvtt_test.yaml:39,43): ViT-B/16 @384, 577 tokens."""
+    g = np.load(os.path.join(golden_dir, "vit_base_384.npz"))
+    m, _ = _build("base", 384, dtype, cuda)
+    got = m(W.frames(1, 384, seed=0).to(cuda)).cpu()
+    assert tuple(got.shape) == (1, 577, 768)
+    _check(got[:, g["tokens"]], torch.from_numpy(g["out"]), dtype)
+
+
+def test_vit_large_batch_vs_oracle(cuda):
+    """Several frames, ragged M (5 * 197 = 985 rows: partial 128-row tiles), against the oracle run on this box's CPU."""
+    m, sd = _build("large", 224, "fp16", cuda, seed=1)
+    x = W.frames(5, 224, seed=2)
+    _check(m(x.to(cuda)).cpu(), vit_oracle.vit_forward(sd, x, 16), "fp16")
+
+
+def test_vit_full_size_batch_invariance_and_determinism(cuda):
+    """BASELINE config 2 size (256 frames, ViT-L/16): frames are independent, so frame i of a 256-batch must equal —
+    bit for bit — the same frame encoded in a batch of 3, and two runs must be identical."""
+    m, _ = _build("large", 224, "bf16", cuda)
+    x = W.frames(8, 224, seed=4).to(cuda).repeat(32, 1, 1, 1)
+    x[100:103] = W.frames(3, 224, seed=5).to(cuda)
+    big = m(x)
+    assert tuple(big.shape) == (256, 197, 1024) and torch.isfinite(big).all()
+    assert torch.equal(big, m(x))
+    small = m(x[100:103].clone())
+    assert torch.equal(big[100:103], small)
+    assert torch.equal(big[0:8], big[8:16])             # repeated frames give repeated rows
+    assert abs(big.std().item() - 1.0) < 0.1            # LayerNorm'd output
+
+
+def test_vit_host_call_equals_device_call(cuda):
+    m, _ = _build("tiny", 32, "bf16", cuda)
+    x = W.frames(6, 32, seed=7)
+    dev_out = m(x.to(cuda)).cpu()
+    host_out = m.encode_host(x.pin_memory())
+    assert not host_out.is_cuda and torch.equal(host_out, dev_out)
+
+
+def test_vit_repacks_after_weight_update(cuda):
+    m, sd = _build("tiny", 32, "fp16", cuda)
+    x = W.frames(1, 32, seed=0).to(cuda)
+    a = m(x)
+    sd2 = W.vit_state_dict("tiny", 32, seed=9)
+    m.load_state_dict(sd2)
+    b = m(x)
+    assert not torch.equal(a, b)
+    _check(b.cpu(), vit_oracle.vit_forward(sd2, x.cpu(), 2), "fp16")
+
+
+def test_vit_edge_cases(cuda):
+    m, sd = _build("tiny", 32, "fp16", cuda)
+    assert tuple(m(torch.zeros(0, 3, 32, 32, device=cuda)).shape) == (0, 5, 128)
+    with pytest.raises(RuntimeError, match="expected frames"):
+        m(torch.zeros(1, 3, 48, 48, device=cuda))
+    with pytest.raises(NotImplementedError):
+        m(torch.zeros(1, 3, 32, 32, device=cuda), register_blk=0)
+    one = m(W.frames(1, 32, seed=0).to(cuda)).cpu()
+    _check(one, vit_oracle.vit_forward(sd, W.frames(1, 32, seed=0), 2), "fp16")
+    # non-contiguous / half-precision inputs are accepted like any torch module would
+    x = W.frames(2, 32, seed=0).to(cuda)
+    assert torch.equal(m(x.half().float()), m(x.half()))
+
+
+def test_native_library_is_the_path(cuda):
+    m, _ = _build("tiny", 32, "bf16", cuda)
+    before = _lib.launch_count()
+    m(W.frames(2, 32, seed=0).to(cuda))
+    # im2col, cls/pos, patch GEMM, per block (LN, qkv, attn, proj, LN, fc1, fc2), final LN
+    assert _lib.launch_count() - before == 3 + 2 * 7 + 1

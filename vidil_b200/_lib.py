@@ -39,6 +39,16 @@ class EncoderCfg(ctypes.Structure):
     ]
 
 
+KCLASSES = ("gemm", "attention", "layernorm", "other")
+
+
+class KernelStats(ctypes.Structure):
+    """Mirror of `vidil_kernel_stats`."""
+
+    _fields_ = [("ms", ctypes.c_double * 4), ("flops", ctypes.c_double * 4), ("bytes", ctypes.c_double * 4),
+                ("launches", c_int64 * 4)]
+
+
 # name -> (restype, argtypes); the single source of truth the symbol test checks against the header
 SIGNATURES = {
     "vidil_abi_version": (c_int32, []),
@@ -52,6 +62,8 @@ SIGNATURES = {
     "vidil_encoder_tokens": (c_int32, [c_void_p]),
     "vidil_vit_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_clip_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vidil_encoder_set_profiling": (c_int32, [c_void_p, c_int32]),
+    "vidil_encoder_read_profile": (c_int32, [c_void_p, POINTER(KernelStats)]),
     "vidil_encoder_host_scratch_bytes": (c_size_t, [c_void_p, c_int32]),
     "vidil_vit_forward_host": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_clip_forward_host": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),

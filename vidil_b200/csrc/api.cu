@@ -77,6 +77,13 @@ struct Plan {
 
 using namespace vidil;
 
+// Event-pair records of the launches enqueued while profiling is on (read back by vidil_encoder_read_profile).
+struct ProfRec {
+    cudaEvent_t a, b;
+    int cls;
+    double flops, bytes;
+};
+
 struct vidil_encoder {
     vidil_encoder_cfg cfg;
     int device = 0;
@@ -86,6 +93,16 @@ struct vidil_encoder {
     std::vector<std::unique_ptr<Layer>> layers;
     std::vector<std::unique_ptr<Plan>> plans;
     uint64_t clock = 0;
+    bool profiling = false;
+    std::vector<ProfRec> prof;
+    std::vector<cudaEvent_t> free_events;
+    ~vidil_encoder() {
+        for (auto& r : prof) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        for (auto ev : free_events) cudaEventDestroy(ev);
+    }
 };
 
 namespace {
@@ -261,37 +278,82 @@ int check_common(vidil_encoder* e, const void* frames, int B, const void* out, v
     return 0;
 }
 
+int prof_event(vidil_encoder* e, cudaEvent_t* ev) {
+    if (!e->free_events.empty()) {
+        *ev = e->free_events.back();
+        e->free_events.pop_back();
+        return 0;
+    }
+    VIDIL_CUDA_OK(cudaEventCreate(ev));
+    return 0;
+}
+
+// Runs one launcher; with profiling on, brackets it with an event pair on the same stream.
+template <typename Fn>
+int timed(vidil_encoder* e, cudaStream_t s, int cls, double flops, double bytes, Fn&& fn) {
+    if (!e->profiling) return fn();
+    ProfRec r{nullptr, nullptr, cls, flops, bytes};
+    if (prof_event(e, &r.a) || prof_event(e, &r.b)) return 1;
+    VIDIL_CUDA_OK(cudaEventRecord(r.a, s));
+    const int rc = fn();
+    VIDIL_CUDA_OK(cudaEventRecord(r.b, s));
+    e->prof.push_back(r);
+    return rc;
+}
+
+inline double gemm_flops(const GemmProblem& g) { return 2.0 * g.M * g.N * g.K; }
+// operands once + output once (fp32 read-modify-write for the residual epilogue)
+inline double gemm_bytes(const GemmProblem& g) {
+    const double out = (g.epi == EPI_RESID) ? 8.0 : (g.epi == EPI_PATCH || g.epi == EPI_STORE_F32) ? 4.0 : 2.0;
+    return 2.0 * g.M * g.K + 2.0 * g.N * g.K + out * g.M * g.N;
+}
+
+int ln_timed(vidil_encoder* e, cudaStream_t s, const float* in, int64_t stride, const DevBuf& w, const DevBuf& b, void* out,
+             bool out_f32, int rows) {
+    const int D = e->cfg.embed_dim;
+    return timed(e, s, VIDIL_KCLASS_LAYERNORM, 8.0 * rows * D, static_cast<double>(rows) * D * (4 + (out_f32 ? 4 : 2)), [&] {
+        return layernorm_run(in, stride, reinterpret_cast<const float*>(w.p), reinterpret_cast<const float*>(b.p), out,
+                             out_f32, e->dt, rows, D, e->cfg.ln_eps, s);
+    });
+}
+
+int gemm_timed(vidil_encoder* e, cudaStream_t s, const GemmProblem& g) {
+    return timed(e, s, VIDIL_KCLASS_GEMM, gemm_flops(g), gemm_bytes(g), [&] { return gemm_run(g, s); });
+}
+
 // Everything up to (not including) the final LayerNorm: leaves the last block's output in pl.resid.
 int run_trunk(vidil_encoder* e, Plan& pl, const float* frames, cudaStream_t s) {
     const vidil_encoder_cfg& c = e->cfg;
     const int B = pl.batch, M = B * e->tokens, D = c.embed_dim;
-    if (e->kpatch_pad != e->kpatch)  // zero the K padding once per call (CLIP 588 -> 640)
-        VIDIL_CUDA_OK(cudaMemsetAsync(pl.patches, 0, static_cast<size_t>(B) * e->patches * e->kpatch_pad * 2, s));
-    if (im2col_run(frames, pl.patches, e->dt, B, 3, c.img_size, c.patch_size, e->kpatch_pad, s)) return 1;
-    float* emb = c.pre_ln ? pl.pre : pl.resid;
-    if (cls_pos_run(reinterpret_cast<const float*>(e->cls.p), reinterpret_cast<const float*>(e->pos.p), emb, B,
-                    e->tokens, D, s))
+    const double patch_elems = static_cast<double>(B) * e->patches * e->kpatch_pad;
+    if (timed(e, s, VIDIL_KCLASS_OTHER, 0.0, 4.0 * B * 3 * c.img_size * c.img_size + 2.0 * patch_elems, [&]() -> int {
+            if (e->kpatch_pad != e->kpatch)  // zero the K padding once per call (CLIP 588 -> 640)
+                VIDIL_CUDA_OK(cudaMemsetAsync(pl.patches, 0, static_cast<size_t>(patch_elems) * 2, s));
+            return im2col_run(frames, pl.patches, e->dt, B, 3, c.img_size, c.patch_size, e->kpatch_pad, s);
+        }))
         return 1;
-    if (gemm_run(pl.patch, s)) return 1;
-    if (c.pre_ln) {
-        if (layernorm_run(pl.pre, D, reinterpret_cast<const float*>(e->pre_w.p),
-                          reinterpret_cast<const float*>(e->pre_b.p), pl.resid, true, e->dt, M, D, c.ln_eps, s))
-            return 1;
-    }
+    float* emb = c.pre_ln ? pl.pre : pl.resid;
+    if (timed(e, s, VIDIL_KCLASS_OTHER, 0.0, 4.0 * B * D, [&] {
+            return cls_pos_run(reinterpret_cast<const float*>(e->cls.p), reinterpret_cast<const float*>(e->pos.p), emb, B,
+                               e->tokens, D, s);
+        }))
+        return 1;
+    if (gemm_timed(e, s, pl.patch)) return 1;
+    if (c.pre_ln && ln_timed(e, s, pl.pre, D, e->pre_w, e->pre_b, pl.resid, true, M)) return 1;
     const float scale = 0.125f;  // head_dim ** -0.5 with head_dim = 64 (vit.py:49)
+    const double attn_flops = 4.0 * B * c.num_heads * static_cast<double>(e->tokens) * e->tokens * 64;
+    const double attn_bytes = 2.0 * M * 4.0 * D;  // qkv read once, out written once
     for (int i = 0; i < c.depth; ++i) {
         Layer& ly = *e->layers[i];
-        if (layernorm_run(pl.resid, D, reinterpret_cast<const float*>(ly.ln1_w.p),
-                          reinterpret_cast<const float*>(ly.ln1_b.p), pl.xn, false, e->dt, M, D, c.ln_eps, s))
+        if (ln_timed(e, s, pl.resid, D, ly.ln1_w, ly.ln1_b, pl.xn, false, M)) return 1;
+        if (gemm_timed(e, s, pl.qkv_g[i])) return 1;
+        if (timed(e, s, VIDIL_KCLASS_ATTENTION, attn_flops, attn_bytes,
+                  [&] { return attention_run(pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads, scale, s); }))
             return 1;
-        if (gemm_run(pl.qkv_g[i], s)) return 1;
-        if (attention_run(pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads, scale, s)) return 1;
-        if (gemm_run(pl.proj_g[i], s)) return 1;
-        if (layernorm_run(pl.resid, D, reinterpret_cast<const float*>(ly.ln2_w.p),
-                          reinterpret_cast<const float*>(ly.ln2_b.p), pl.xn, false, e->dt, M, D, c.ln_eps, s))
-            return 1;
-        if (gemm_run(pl.fc1_g[i], s)) return 1;
-        if (gemm_run(pl.fc2_g[i], s)) return 1;
+        if (gemm_timed(e, s, pl.proj_g[i])) return 1;
+        if (ln_timed(e, s, pl.resid, D, ly.ln2_w, ly.ln2_b, pl.xn, false, M)) return 1;
+        if (gemm_timed(e, s, pl.fc1_g[i])) return 1;
+        if (gemm_timed(e, s, pl.fc2_g[i])) return 1;
     }
     return 0;
 }
@@ -514,9 +576,7 @@ int32_t vidil_vit_forward(vidil_encoder* enc, const float* frames, int32_t batch
     Plan* pl = get_plan(enc, batch, workspace);
     if (pl == nullptr) return 1;
     if (run_trunk(enc, *pl, frames, s)) return 1;
-    const int M = batch * enc->tokens, D = enc->cfg.embed_dim;
-    return layernorm_run(pl->resid, D, reinterpret_cast<const float*>(enc->norm_w.p),
-                         reinterpret_cast<const float*>(enc->norm_b.p), out_tokens, true, enc->dt, M, D, enc->cfg.ln_eps, s);
+    return ln_timed(enc, s, pl->resid, enc->cfg.embed_dim, enc->norm_w, enc->norm_b, out_tokens, true, batch * enc->tokens);
 }
 
 int32_t vidil_clip_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_embeds, float* out_hidden,
@@ -535,11 +595,41 @@ int32_t vidil_clip_forward(vidil_encoder* enc, const float* frames, int32_t batc
     if (out_hidden != nullptr)
         VIDIL_CUDA_OK(cudaMemcpyAsync(out_hidden, pl->resid, M * D * 4, cudaMemcpyDeviceToDevice, s));
     // post_layernorm on the CLS row of every frame only, then the bias-free projection and L2 normalisation
-    if (layernorm_run(pl->resid, static_cast<int64_t>(enc->tokens) * D, reinterpret_cast<const float*>(enc->norm_w.p),
-                      reinterpret_cast<const float*>(enc->norm_b.p), pl->cls_ln, false, enc->dt, batch, D, enc->cfg.ln_eps, s))
+    if (ln_timed(enc, s, pl->resid, static_cast<int64_t>(enc->tokens) * D, enc->norm_w, enc->norm_b, pl->cls_ln, false, batch))
         return 1;
-    if (gemm_run(pl->head, s)) return 1;
-    return l2norm_run(pl->head_out, out_embeds, batch, enc->cfg.proj_dim, s);
+    if (gemm_timed(enc, s, pl->head)) return 1;
+    return timed(enc, s, VIDIL_KCLASS_OTHER, 0.0, 8.0 * batch * enc->cfg.proj_dim,
+                 [&] { return l2norm_run(pl->head_out, out_embeds, batch, enc->cfg.proj_dim, s); });
+}
+
+int32_t vidil_encoder_set_profiling(vidil_encoder* enc, int32_t enable) {
+    if (enc == nullptr) {
+        set_error("null encoder");
+        return 1;
+    }
+    enc->profiling = enable != 0;
+    return 0;
+}
+
+int32_t vidil_encoder_read_profile(vidil_encoder* enc, vidil_kernel_stats* out) {
+    if (enc == nullptr || out == nullptr) {
+        set_error("vidil_encoder_read_profile: null argument");
+        return 1;
+    }
+    memset(out, 0, sizeof(*out));
+    for (auto& r : enc->prof) {
+        VIDIL_CUDA_OK(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        VIDIL_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+        out->ms[r.cls] += ms;
+        out->flops[r.cls] += r.flops;
+        out->bytes[r.cls] += r.bytes;
+        out->launches[r.cls] += 1;
+        enc->free_events.push_back(r.a);
+        enc->free_events.push_back(r.b);
+    }
+    enc->prof.clear();
+    return 0;
 }
 
 size_t vidil_encoder_host_scratch_bytes(const vidil_encoder* enc, int32_t batch) {

@@ -98,6 +98,16 @@ class NativeEncoder:
                                          torch.cuda.current_stream().cuda_stream)
         _lib.check(st, f"vidil_encoder_load({name})")
 
+    def set_profiling(self, enable: bool) -> None:
+        _lib.check(self.lib.vidil_encoder_set_profiling(self.handle, int(enable)), "vidil_encoder_set_profiling")
+
+    def read_profile(self) -> dict:
+        """{class: {ms, flops, bytes, launches}} of the kernels enqueued since the last read (synchronises)."""
+        st = _lib.KernelStats()
+        _lib.check(self.lib.vidil_encoder_read_profile(self.handle, ctypes.byref(st)), "vidil_encoder_read_profile")
+        return {name: dict(ms=st.ms[i], flops=st.flops[i], bytes=st.bytes[i], launches=int(st.launches[i]))
+                for i, name in enumerate(_lib.KCLASSES)}
+
     @staticmethod
     def _aligned(nbytes: int, device) -> torch.Tensor:
         buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
