@@ -152,17 +152,19 @@ def test_sim_topk_ties_and_duplicates(cuda):
 
 
 def test_sim_topk_near_ties_below_fp16_resolution(cuda):
-    """Phrases 1e-6 apart in score: invisible to the fp16 tensor-core pass, resolved by the fp32 re-rank."""
+    """Phrases ~1e-5 apart in score: inside the noise of the fp16 tensor-core pass (~1e-4), well above fp32 summation-order
+    noise (~1e-7, which no two fp32 matmul implementations agree on) — the fp32 re-rank must order them like the oracle."""
     D = 768
     base = W.unit_rows(1, D, seed=9)[0]
     bank = W.unit_rows(2000, D, seed=10)
     noise = W.unit_rows(8, D, seed=11)
     for j in range(8):
-        v = base + (3e-4 * (j + 1)) * noise[j]
+        v = base + (3e-3 * (j + 1)) * noise[j]
         bank[50 + 37 * j] = v / v.norm()
     img = base[None].repeat(4, 1)
     ref_scores, ref_idx = tokenization_oracle.sim_topk(img.numpy(), bank.numpy(), 8)
-    assert np.all(np.diff(ref_scores[0]) < 0) and (ref_scores[0][0] - ref_scores[0][-1]) < 1e-4
+    gaps = -np.diff(ref_scores[0])
+    assert gaps.min() > 5e-6 and (ref_scores[0][0] - ref_scores[0][-1]) < 1e-3
     _, idx = ops.sim_topk(img.to(cuda), bank.to(cuda), 8)
     assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx)
 
