@@ -9,8 +9,11 @@
 //   warp 1 / lane 0 : MMA issuer     — tcgen05.mma kind::f16 (fp16 or bf16 in, fp32 accumulate in TMEM);
 //                                      tcgen05.commit releases smem stages and publishes accumulators
 //   warp 2          : TMEM allocator — 512 columns = two 128x256 fp32 accumulators (double buffered)
-//   warps 4..11     : epilogue       — tcgen05.ld TMEM->registers, bias / GELU / residual / position
-//                                      add, 16-byte global stores; overlaps the next tile's MMAs
+//   warps 4..11     : epilogue       — tcgen05.ld TMEM->registers, bias / GELU; the 32-row x 128-byte piece is
+//                                      staged in SWIZZLE_128B shared memory and leaves through TMA: a bulk tensor
+//                                      store for 16-bit / fp32 outputs, a bulk tensor REDUCE-ADD for the fp32
+//                                      residual stream (the += happens at L2; the old value is never read by the
+//                                      SM).  Overlaps the next tile's MMAs.
 // With CTA_GROUP == 2 two CTAs of a cluster (one TPC) run cta_group::2 MMAs on a 256x256 tile: each
 // CTA stages its own 128 rows of A and half (128 rows) of the W tile, halving shared-memory and L2
 // operand traffic per FLOP; accumulator rows [128r, 128r+128) live in CTA r's TMEM.
@@ -42,9 +45,12 @@ struct Cfg {
     static constexpr int W_ROWS = BLOCK_N / CG;                   // rows of W this CTA stages
     static constexpr int W_BYTES = W_ROWS * BLOCK_K * 2;          // 32 KB or 16 KB
     static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;         // 48 KB or 32 KB
-    static constexpr int STAGES = (CG == 1) ? 4 : 6;              // 192 KB of operand ring either way
+    static constexpr int STAGES = (CG == 1) ? 3 : 5;              // 144 KB / 160 KB of operand ring
+    static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
+    static constexpr int OUT_BUF_BYTES = 32 * 128;                // one epilogue piece: 32 rows x 128 bytes
+    static constexpr int OUT_BYTES = NUM_EPI_WARPS * 2 * OUT_BUF_BYTES;  // double-buffered per warp: 64 KB
     static constexpr int BAR_BYTES = 256;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
+    static constexpr int SMEM_BYTES = RING_BYTES + OUT_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
 
 struct EpiArgs {
@@ -55,8 +61,23 @@ struct EpiArgs {
     int patches_per_frame;
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float quick_gelu(float x) { return x / (1.0f + __expf(-1.702f * x)); }
+// 0.5 x (1 + erf(x / sqrt 2)) with erf from Abramowitz & Stegun 7.1.26 (|abs err| <= 1.5e-7, the size of erff's own
+// error and 3 orders below the rounding of the 16-bit output): 10 FMA/ALU-pipe + 2 MUFU instructions per element instead
+// of erff's ~30, which made the fc1 epilogue slower than the tile's MMAs.
+__device__ __forceinline__ float gelu_erf(float x) {
+    const float t = ptx::rcp_approx(fmaf(fabsf(x), 0.3275911f * 0.70710678118654752f, 1.0f));
+    float p = fmaf(t, 1.061405429f, -1.453152027f);
+    p = fmaf(t, p, 1.421413741f);
+    p = fmaf(t, p, -0.284496736f);
+    p = fmaf(t, p, 0.254829592f);
+    p *= t;
+    const float e = ptx::ex2_approx(x * x * (-0.5f * 1.4426950408889634f));  // exp(-(x/sqrt2)^2)
+    // x >= 0: 0.5x(1 + erf) = x - 0.5x p e;  x < 0: 0.5x(1 - erf|.|) = 0.5x p e  — no 1 - erf cancellation in the tail
+    return fmaf(-fabsf(0.5f * x), p * e, fmaxf(x, 0.0f));
+}
+__device__ __forceinline__ float quick_gelu(float x) {
+    return x * ptx::rcp_approx(1.0f + ptx::ex2_approx(x * (-1.702f * 1.4426950408889634f)));
+}
 
 template <typename T>
 __device__ __forceinline__ uint32_t pack2(float a, float b);
@@ -172,14 +193,15 @@ __device__ __forceinline__ void epilogue_chunk(float (&v)[32], const EpiArgs& e,
 template <typename T, int EPI, int CG>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
     gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ CUtensorMap map_w,
-                        int M, int N, int K, EpiArgs epi) {
+                        const __grid_constant__ CUtensorMap map_out, int M, int N, int K, EpiArgs epi) {
     using C = Cfg<CG>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles must sit on 1024-byte boundaries of the shared address space.
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
 
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::STAGES * C::STAGE_BYTES);
+    uint8_t* out_stage = smem + C::RING_BYTES;  // per-epilogue-warp staging for TMA stores (1024-byte aligned)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + C::RING_BYTES + C::OUT_BYTES);
     uint64_t* empty_bar = full_bar + C::STAGES;
     uint64_t* tmem_full_bar = empty_bar + C::STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + NUM_ACC;
@@ -195,6 +217,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_w);
+        if constexpr (EPI != EPI_PATCH) ptx::prefetch_tensormap(&map_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -298,41 +321,129 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int ew = warp - 4;
         const int lane_quarter = ew & 3;  // TMEM lanes a warp may read: 32 * (warp % 4) ...
         const int col_half = ew >> 2;     // this warp's 128-column half of the 256-column accumulator
+        constexpr bool kTmaOut = (EPI != EPI_PATCH);
+        constexpr bool kOut16 = (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_QUICKGELU);
+        constexpr int PIECE_COLS = kOut16 ? 64 : 32;  // one staged piece is 32 rows x 128 bytes
+        constexpr int PIECES = 128 / PIECE_COLS;
+        const uint32_t stage_base = ptx::smem_u32(out_stage) + ew * 2 * C::OUT_BUF_BYTES;
+        const uint32_t swz = static_cast<uint32_t>(lane & 7);  // 128-byte swizzle: 16-byte chunk index ^= row & 7
+        const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
+        int piece_no = 0;
         int iter = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
             const int acc = iter & 1;
             const uint32_t acc_phase = (iter >> 1) & 1;
             const int m0 = ((t / tiles_n) * CG + static_cast<int>(cta_rank)) * BLOCK_M;
             const int n0 = (t % tiles_n) * BLOCK_N;
-            const int row = m0 + lane_quarter * 32 + lane;
+            const int row0 = m0 + lane_quarter * 32;  // first row of this warp's 32-row band
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(lane_quarter * 32) << 16) + acc * BLOCK_N + col_half * 128;
+            if constexpr (kTmaOut) {
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-                uint32_t r[32];
-                ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
-                ptx::tmem_ld_wait();
-                if (c == 3) {
-                    // All of this warp's TMEM reads for the tile are complete: hand the accumulator back.
-                    ptx::tcgen05_fence_before();
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CG == 1)
-                            ptx::mbar_arrive(&tmem_empty_bar[acc]);
-                        else
-                            ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+                for (int pc = 0; pc < PIECES; ++pc, ++piece_no) {
+                    const int col0 = n0 + col_half * 128 + pc * PIECE_COLS;
+                    uint32_t r[PIECE_COLS];
+                    ptx::tmem_ld_32x32b_x32(taddr + pc * PIECE_COLS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
+                    if constexpr (PIECE_COLS == 64)
+                        ptx::tmem_ld_32x32b_x32(taddr + pc * PIECE_COLS + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
+                    // the staging buffer about to be overwritten was handed to TMA two pieces ago by lane 0
+                    if (lane == 0) ptx::bulk_wait_group_read<1>();
+                    ptx::tmem_ld_wait();
+                    if (pc == PIECES - 1) {
+                        // All of this warp's TMEM reads for the tile are complete: hand the accumulator back.
+                        ptx::tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 1)
+                                ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                            else
+                                ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+                        }
+                    } else {
+                        __syncwarp();
+                    }
+                    if (row0 < M && col0 < N) {  // warp-uniform; TMA clips the partial tails
+                        const uint32_t buf = stage_base + (piece_no & 1) * C::OUT_BUF_BYTES + row_off;
+                        const bool full = (col0 + PIECE_COLS <= N);
+#pragma unroll
+                        for (int c = 0; c < PIECE_COLS / 4; ++c) {  // 4 columns at a time
+                            float v[4];
+#pragma unroll
+                            for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * c + i]);
+                            if (epi.bias != nullptr) {
+                                if (full) {
+                                    const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + c);
+                                    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
+                                } else {
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i)
+                                        if (col0 + 4 * c + i < N) v[i] += __ldg(epi.bias + col0 + 4 * c + i);
+                                }
+                            }
+                            if constexpr (EPI == EPI_GELU) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) v[i] = gelu_erf(v[i]);
+                            } else if constexpr (EPI == EPI_QUICKGELU) {
+#pragma unroll
+                                for (int i = 0; i < 4; ++i) v[i] = quick_gelu(v[i]);
+                            }
+                            if constexpr (kOut16) {
+                                // two consecutive 4-column groups make one 16-byte chunk: keep the first half
+                                r[4 * c + 0] = pack2<T>(v[0], v[1]);
+                                r[4 * c + 1] = pack2<T>(v[2], v[3]);
+                                if (c & 1) {
+                                    const uint32_t chunk = static_cast<uint32_t>(c >> 1);
+                                    ptx::st_shared_v4(buf + ((chunk ^ swz) << 4), r[4 * (c - 1)], r[4 * (c - 1) + 1],
+                                                      r[4 * c], r[4 * c + 1]);
+                                }
+                            } else {
+                                ptx::st_shared_v4(buf + ((static_cast<uint32_t>(c) ^ swz) << 4), __float_as_uint(v[0]),
+                                                  __float_as_uint(v[1]), __float_as_uint(v[2]), __float_as_uint(v[3]));
+                            }
+                        }
+                        ptx::fence_proxy_async_smem();
+                        __syncwarp();
+                        if (lane == 0) {
+                            const void* src = out_stage + (ew * 2 + (piece_no & 1)) * C::OUT_BUF_BYTES;
+                            if constexpr (EPI == EPI_RESID)
+                                ptx::tma_reduce_add_2d(&map_out, src, col0, row0);
+                            else
+                                ptx::tma_store_2d(&map_out, src, col0, row0);
+                        }
+                    }
+                    if (lane == 0) ptx::bulk_commit_group();  // one group per piece, empty or not, keeps the count in step
+                }
+            } else {
+                const int row = row0 + lane;
+#pragma unroll 1
+                for (int c = 0; c < 4; ++c) {
+                    uint32_t r[32];
+                    ptx::tmem_ld_32x32b_x32(taddr + c * 32, r);
+                    ptx::tmem_ld_wait();
+                    if (c == 3) {
+                        ptx::tcgen05_fence_before();
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CG == 1)
+                                ptx::mbar_arrive(&tmem_empty_bar[acc]);
+                            else
+                                ptx::mbar_arrive_cluster(&tmem_empty_bar[acc], 0);
+                        }
+                    }
+                    const int col0 = n0 + col_half * 128 + c * 32;
+                    if (row < M && col0 < N) {
+                        float v[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        epilogue_chunk<T, EPI>(v, epi, row, col0, N);
                     }
                 }
-                const int col0 = n0 + col_half * 128 + c * 32;
-                if (row < M && col0 < N) {
-                    float v[32];
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
-                    epilogue_chunk<T, EPI>(v, epi, row, col0, N);
-                }
             }
+        }
+        if constexpr (kTmaOut) {
+            if (lane == 0) ptx::bulk_wait_group<0>();  // every store / reduce of this warp has been performed
         }
     }
 
@@ -360,6 +471,28 @@ EncodeTiledFn get_encode_fn() {
             fn = reinterpret_cast<EncodeTiledFn>(p);
     }
     return fn;
+}
+
+// Output map for the epilogue's TMA stores: dims {N (inner), M}, box {128 bytes of columns, 32 rows}, 128-byte swizzle.
+int encode_output_map(CUtensorMap* out, CUtensorMapDataType cdt, int elt_bytes, void* ptr, uint64_t N, uint64_t M,
+                      uint64_t ld_elems) {
+    EncodeTiledFn fn = get_encode_fn();
+    if (fn == nullptr) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return 1;
+    }
+    const cuuint64_t dims[2] = {N, M};
+    const cuuint64_t strides[1] = {ld_elems * elt_bytes};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elt_bytes), 32};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, cdt, 2, ptr, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (output) failed with CUresult %d (ptr=%p N=%llu M=%llu ld=%llu)", static_cast<int>(r),
+                  ptr, (unsigned long long)N, (unsigned long long)M, (unsigned long long)ld_elems);
+        return 1;
+    }
+    return 0;
 }
 
 // 2-D K-major operand map: dims {K (inner), rows}, box {64, box_rows}, 128-byte swizzle, zero OOB fill.
@@ -416,7 +549,7 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    VIDIL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p.map_a, p.map_w, p.M, p.N, p.K, e));
+    VIDIL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p.map_a, p.map_w, p.map_out, p.M, p.N, p.K, e));
     count_launches(1);
     return 0;
 }
@@ -485,6 +618,13 @@ int gemm_prepare(GemmProblem& p) {
     }
     if (encode_operand_map(&p.map_a, p.dt, p.A, p.K, p.M, p.lda, BLOCK_M)) return 1;
     if (encode_operand_map(&p.map_w, p.dt, p.W, p.K, p.N, p.ldw, BLOCK_N / p.cta_group)) return 1;
+    if (p.epi != EPI_PATCH) {
+        const CUtensorMapDataType odt = out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                                                : (p.dt == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
+        if (encode_output_map(&p.map_out, odt, out_f32 ? 4 : 2, p.out, p.N, p.M, p.ldo)) return 1;
+    } else {
+        p.map_out = p.map_a;  // unused by the scatter epilogue; any valid descriptor
+    }
     p.prepared = true;
     return 0;
 }

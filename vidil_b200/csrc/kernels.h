@@ -58,6 +58,7 @@ struct GemmProblem {
     // filled by gemm_prepare():
     CUtensorMap map_a;
     CUtensorMap map_w;
+    CUtensorMap map_out;  // epilogue TMA store / reduce-add target (all modes but EPI_PATCH)
     bool prepared = false;
 };
 

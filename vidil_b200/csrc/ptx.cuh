@@ -17,6 +17,18 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// Single-instruction MUFU approximations (rel. err ~2^-22): enough ahead of a 16-bit rounding.
+__device__ __forceinline__ float rcp_approx(float x) {
+    float y;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ uint32_t lane_id() {
     uint32_t l;
     asm volatile("mov.u32 %0, %%laneid;" : "=r"(l));
@@ -125,6 +137,44 @@ __device__ __forceinline__ void tma_load_2d_pair(const CUtensorMap* m, uint64_t*
         " [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
         "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
         : "memory");
+}
+
+// 2-D tiled store shared -> global (bulk async-group completion).  Rows/columns outside the tensor are clipped.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, const void* src, int32_t c0, int32_t c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+// Same box, but global[...] += shared[...] (element type from the tensor map; performed at L2).
+__device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const void* src, int32_t c0, int32_t c1) {
+    asm volatile("cp.reduce.async.bulk.tensor.2d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+
+// Wait until at most N of this thread's bulk groups still have shared-memory reads outstanding.
+template <int N>
+__device__ __forceinline__ void bulk_wait_group_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+// Wait until at most N of this thread's bulk groups are incomplete (writes performed).
+template <int N>
+__device__ __forceinline__ void bulk_wait_group() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// Order this thread's generic-proxy shared-memory writes before subsequent async-proxy (TMA) reads.
+__device__ __forceinline__ void fence_proxy_async_smem() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // ----------------------------------------------------------------------------------------
