@@ -70,6 +70,8 @@ struct Plan {
     GemmProblem patch;
     std::vector<GemmProblem> qkv_g, proj_g, fc1_g, fc2_g;
     GemmProblem head;
+    bool attn_tc = false;  // tcgen05 attention (tokens <= 208); otherwise the streaming mma.sync kernel
+    AttentionMaps attn_maps;
 };
 
 }  // namespace
@@ -218,6 +220,8 @@ int build_plan(vidil_encoder* e, Plan& pl, int B, void* ws) {
         f2.out = pl.resid; f2.ldo = D;
         if (gemm_prepare(f2)) return 1;
     }
+    pl.attn_tc = attention_tc_supported(e->tokens);
+    if (pl.attn_tc && attention_tc_prepare(pl.attn_maps, pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads)) return 1;
     if (c.proj_dim > 0) {
         pl.head = g;
         pl.head.epi = EPI_STORE_F32;
@@ -348,7 +352,10 @@ int run_trunk(vidil_encoder* e, Plan& pl, const float* frames, cudaStream_t s) {
         if (ln_timed(e, s, pl.resid, D, ly.ln1_w, ly.ln1_b, pl.xn, false, M)) return 1;
         if (gemm_timed(e, s, pl.qkv_g[i])) return 1;
         if (timed(e, s, VIDIL_KCLASS_ATTENTION, attn_flops, attn_bytes,
-                  [&] { return attention_run(pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads, scale, s); }))
+                  [&] {
+                      return pl.attn_tc ? attention_tc_run(pl.attn_maps, scale, s)
+                                        : attention_run(pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads, scale, s);
+                  }))
             return 1;
         if (gemm_timed(e, s, pl.proj_g[i])) return 1;
         if (ln_timed(e, s, pl.resid, D, ly.ln2_w, ly.ln2_b, pl.xn, false, M)) return 1;
@@ -823,7 +830,13 @@ int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, i
     void* qkv_h = base;
     void* out_h = base + align_up(static_cast<size_t>(rows) * 3 * H * 64 * 2);
     if (cast_run(qkv, qkv_h, dt, rows, 3 * H * 64, 3 * H * 64, s)) return 1;
-    if (attention_run(qkv_h, out_h, dt, B, N, H, scale, s)) return 1;
+    if (attention_tc_supported(N)) {
+        AttentionMaps maps;
+        if (attention_tc_prepare(maps, qkv_h, out_h, dt, B, N, H)) return 1;
+        if (attention_tc_run(maps, scale, s)) return 1;
+    } else if (attention_run(qkv_h, out_h, dt, B, N, H, scale, s)) {
+        return 1;
+    }
     return uncast_run(out_h, out, dt, rows * H * 64, s);
 }
 

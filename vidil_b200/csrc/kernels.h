@@ -78,6 +78,19 @@ int layernorm_run(const float* in, int64_t in_row_stride, const float* gamma, co
 // ---------------------------------------------------------------------------------------
 int attention_run(const void* qkv, void* out, DType dt, int B, int N, int H, float scale, cudaStream_t stream);
 
+// tcgen05 version for sequences of at most 208 tokens (attention_tc.cu).  The TMA descriptors depend only on the
+// buffer addresses and the shape, so a forward plan encodes them once.
+struct AttentionMaps {
+    CUtensorMap q, kv, out;
+    const void* qkv = nullptr;
+    void* out_ptr = nullptr;
+    int B = 0, N = 0, H = 0;
+    DType dt = DT_BF16;
+};
+bool attention_tc_supported(int N);
+int attention_tc_prepare(AttentionMaps& m, const void* qkv, void* out, DType dt, int B, int N, int H);
+int attention_tc_run(const AttentionMaps& m, float scale, cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------
 // Elementwise / layout kernels.
 // ---------------------------------------------------------------------------------------

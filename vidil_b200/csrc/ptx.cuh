@@ -155,6 +155,14 @@ __device__ __forceinline__ void tma_reduce_add_2d(const CUtensorMap* m, const vo
                  : "memory");
 }
 
+// 3-D variant (attention output: {channel, token-in-frame, frame} so rows past the frame's last token are clipped).
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* m, const void* src, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(m)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+
 __device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 
 // Wait until at most N of this thread's bulk groups still have shared-memory reads outstanding.
@@ -279,6 +287,16 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)
         : "memory");
 }
 
+__device__ __forceinline__ void tmem_ld_32x32b_x16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+
 __device__ __forceinline__ void tmem_ld_wait() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
@@ -302,12 +320,32 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 
+// General shared-memory matrix descriptor: byte offsets are encoded >> 4.  layout: 0 = no swizzle, 2 = SWIZZLE_128B.
+//   K-major, no swizzle : core matrix = 8 rows x 16 B contiguous; LBO = distance between the two 16-byte K chunks of
+//                         one MMA K step, SBO = distance between 8-row groups.
+//   MN-major, SWIZZLE_128B: a K row is 64 contiguous MN elements (128 B); SBO = distance between 8-K-row groups,
+//                         LBO = distance between 64-element MN chunks.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout & 7u) << 61;
+    return d;
+}
+
 // Instruction descriptor for kind::f16, fp32 accumulate, both operands K-major.
 //   [4,6) D format (1 = f32)   [7,10) A format (0 = f16, 1 = bf16)   [10,13) B format
 //   [15] A major (0 = K)  [16] B major (0 = K)  [17,23) N >> 3   [24,29) M >> 4
 __host__ __device__ constexpr uint32_t make_idesc_f16(bool is_bf16, uint32_t umma_m, uint32_t umma_n) {
     return (1u << 4) | ((is_bf16 ? 1u : 0u) << 7) | ((is_bf16 ? 1u : 0u) << 10) | ((umma_n >> 3) << 17) |
            ((umma_m >> 4) << 24);
+}
+// Same with the B operand MN-major (bit 16): B is stored [K][N] with N contiguous.
+__host__ __device__ constexpr uint32_t make_idesc_f16_bmn(bool is_bf16, uint32_t umma_m, uint32_t umma_n) {
+    return make_idesc_f16(is_bf16, umma_m, umma_n) | (1u << 16);
 }
 
 }  // namespace ptx
