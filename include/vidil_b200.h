@@ -105,6 +105,17 @@ int32_t vidil_vit_forward_host(vidil_encoder* enc, const float* frames_host, int
 int32_t vidil_clip_forward_host(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_embeds_host,
                                 void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 
+/* Pipelined variant for a stream of batches: submit() enqueues H2D (copy stream) -> forward (`stream`) -> D2H
+ * (second copy stream) for one batch into one of two slots and returns at once; wait(slot) blocks until that
+ * slot's result is in out_host.  Submitting batch k+1 to the other slot before waiting for batch k overlaps its
+ * H2D with batch k's forward and batch k's D2H with batch k+1's forward.  The handle decides which forward runs
+ * (vit: tokens, clip: image_embeds).  dev_scratch: vidil_encoder_host_pipeline_scratch_bytes(enc, batch) bytes,
+ * the same pointer for both slots.  The caller must not touch a slot's host buffers between submit and wait. */
+size_t  vidil_encoder_host_pipeline_scratch_bytes(const vidil_encoder* enc, int32_t batch);
+int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_host,
+                                  int32_t slot, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+int32_t vidil_encoder_host_wait(vidil_encoder* enc, int32_t slot);
+
 /* ---- per-kernel-class device timing (bench.py's roofline figures) ---------------------------- */
 /* With profiling on, every kernel a forward enqueues is bracketed by CUDA events on the caller's stream.
  * vidil_encoder_read_profile synchronises those events, adds up elapsed time / algorithmic FLOPs / algorithmic

@@ -109,6 +109,22 @@ def test_vit_host_call_equals_device_call(cuda):
     assert not host_out.is_cuda and torch.equal(host_out, dev_out)
 
 
+def test_vit_host_stream_equals_device_calls(cuda):
+    """Pipelined host API (vidil_encoder_host_submit/_wait): 5 batches through 2 slots, results in order and bit-identical
+    to the device-resident call."""
+    m, _ = _build("tiny", 32, "fp16", cuda)
+    batches = [W.frames(4, 32, seed=20 + i).pin_memory() for i in range(5)]
+    want = [m(b.to(cuda)).cpu() for b in batches]
+    got = [o.clone() for o in m.encode_host_stream(iter(batches))]
+    assert len(got) == 5
+    for a, b in zip(got, want):
+        assert torch.equal(a, b)
+    outs = [torch.empty(4, 5, 128).pin_memory() for _ in range(2)]
+    for i, o in enumerate(m.encode_host_stream(iter(batches), outs=outs)):
+        assert o is outs[i & 1] and torch.equal(o, want[i])
+    assert list(m.encode_host_stream(iter([]))) == []
+
+
 def test_vit_repacks_after_weight_update(cuda):
     m, sd = _build("tiny", 32, "fp16", cuda)
     x = W.frames(1, 32, seed=0).to(cuda)

@@ -67,6 +67,9 @@ SIGNATURES = {
     "vidil_encoder_host_scratch_bytes": (c_size_t, [c_void_p, c_int32]),
     "vidil_vit_forward_host": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_clip_forward_host": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vidil_encoder_host_pipeline_scratch_bytes": (c_size_t, [c_void_p, c_int32]),
+    "vidil_encoder_host_submit": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
+    "vidil_encoder_host_wait": (c_int32, [c_void_p, c_int32]),
     "vidil_sim_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "vidil_sim_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),

@@ -98,7 +98,17 @@ struct vidil_encoder {
     bool profiling = false;
     std::vector<ProfRec> prof;
     std::vector<cudaEvent_t> free_events;
+    // host-buffer pipeline (vidil_encoder_host_submit / _wait): copy engines run on their own streams
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;
+    cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
     ~vidil_encoder() {
+        if (copy_in) cudaStreamDestroy(copy_in);
+        if (copy_out) cudaStreamDestroy(copy_out);
+        for (int i = 0; i < 2; ++i) {
+            if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+            if (ev_compute[i]) cudaEventDestroy(ev_compute[i]);
+            if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+        }
         for (auto& r : prof) {
             cudaEventDestroy(r.a);
             cudaEventDestroy(r.b);
@@ -686,6 +696,81 @@ int32_t vidil_vit_forward_host(vidil_encoder* enc, const float* frames_host, int
 int32_t vidil_clip_forward_host(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_embeds_host,
                                 void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
     return host_forward(enc, frames_host, batch, out_embeds_host, true, dev_scratch, dev_scratch_bytes, stream);
+}
+
+// ---- pipelined host-buffer encoding --------------------------------------------------------------------
+size_t vidil_encoder_host_pipeline_scratch_bytes(const vidil_encoder* enc, int32_t batch) {
+    if (enc == nullptr || batch <= 0) return 0;
+    const size_t in = align_up(static_cast<size_t>(batch) * 3 * enc->cfg.img_size * enc->cfg.img_size * 4);
+    const size_t out_tok = align_up(static_cast<size_t>(batch) * enc->tokens * enc->cfg.embed_dim * 4);
+    return 2 * (in + out_tok) + ws_layout(enc, batch).total;
+}
+
+int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_host, int32_t slot,
+                                  void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+    if (enc == nullptr || frames_host == nullptr || out_host == nullptr || dev_scratch == nullptr || batch <= 0) {
+        set_error("vidil_encoder_host_submit: null argument or empty batch");
+        return 1;
+    }
+    if (slot < 0 || slot > 1) {
+        set_error("vidil_encoder_host_submit: slot must be 0 or 1");
+        return 1;
+    }
+    if (dev_scratch_bytes < vidil_encoder_host_pipeline_scratch_bytes(enc, batch)) {
+        set_error("device scratch too small: %zu bytes given, %zu needed", dev_scratch_bytes,
+                  vidil_encoder_host_pipeline_scratch_bytes(enc, batch));
+        return 1;
+    }
+    if (enc->copy_in == nullptr) {
+        VIDIL_CUDA_OK(cudaStreamCreateWithFlags(&enc->copy_in, cudaStreamNonBlocking));
+        VIDIL_CUDA_OK(cudaStreamCreateWithFlags(&enc->copy_out, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            VIDIL_CUDA_OK(cudaEventCreateWithFlags(&enc->ev_in[i], cudaEventDisableTiming));
+            VIDIL_CUDA_OK(cudaEventCreateWithFlags(&enc->ev_compute[i], cudaEventDisableTiming));
+            VIDIL_CUDA_OK(cudaEventCreateWithFlags(&enc->ev_out[i], cudaEventDisableTiming));
+        }
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    const bool clip = enc->cfg.proj_dim > 0;
+    const size_t in_bytes = static_cast<size_t>(batch) * 3 * enc->cfg.img_size * enc->cfg.img_size * 4;
+    const size_t out_tok_bytes = static_cast<size_t>(batch) * enc->tokens * enc->cfg.embed_dim * 4;
+    const size_t per_slot = align_up(in_bytes) + align_up(out_tok_bytes);
+    uint8_t* base = reinterpret_cast<uint8_t*>(dev_scratch);
+    float* d_in = reinterpret_cast<float*>(base + slot * per_slot);
+    float* d_out = reinterpret_cast<float*>(base + slot * per_slot + align_up(in_bytes));
+    void* ws = base + 2 * per_slot;
+    const size_t ws_bytes = dev_scratch_bytes - 2 * per_slot;
+    // H2D: may start as soon as the previous forward that read this slot's frames is done
+    VIDIL_CUDA_OK(cudaStreamWaitEvent(enc->copy_in, enc->ev_compute[slot], 0));
+    VIDIL_CUDA_OK(cudaMemcpyAsync(d_in, frames_host, in_bytes, cudaMemcpyHostToDevice, enc->copy_in));
+    VIDIL_CUDA_OK(cudaEventRecord(enc->ev_in[slot], enc->copy_in));
+    // forward: needs the frames, and the previous D2H out of this slot's result buffer
+    VIDIL_CUDA_OK(cudaStreamWaitEvent(s, enc->ev_in[slot], 0));
+    VIDIL_CUDA_OK(cudaStreamWaitEvent(s, enc->ev_out[slot], 0));
+    size_t out_bytes;
+    if (clip) {
+        if (vidil_clip_forward(enc, d_in, batch, d_out, nullptr, ws, ws_bytes, stream)) return 1;
+        out_bytes = static_cast<size_t>(batch) * enc->cfg.proj_dim * 4;
+    } else {
+        if (vidil_vit_forward(enc, d_in, batch, d_out, ws, ws_bytes, stream)) return 1;
+        out_bytes = out_tok_bytes;
+    }
+    VIDIL_CUDA_OK(cudaEventRecord(enc->ev_compute[slot], s));
+    // D2H on the other copy engine
+    VIDIL_CUDA_OK(cudaStreamWaitEvent(enc->copy_out, enc->ev_compute[slot], 0));
+    VIDIL_CUDA_OK(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, enc->copy_out));
+    VIDIL_CUDA_OK(cudaEventRecord(enc->ev_out[slot], enc->copy_out));
+    return 0;
+}
+
+int32_t vidil_encoder_host_wait(vidil_encoder* enc, int32_t slot) {
+    if (enc == nullptr || slot < 0 || slot > 1) {
+        set_error("vidil_encoder_host_wait: bad argument");
+        return 1;
+    }
+    if (enc->ev_out[slot] == nullptr) return 0;  // nothing was ever submitted
+    VIDIL_CUDA_OK(cudaEventSynchronize(enc->ev_out[slot]));
+    return 0;
 }
 
 // ---- similarity + top-k ---------------------------------------------------------------------------

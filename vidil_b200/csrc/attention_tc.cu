@@ -2,16 +2,18 @@
 // ViT-L/16 @224 shape (N = 197).  Reference: models/vit.py:72-83 (Attention.forward); the reference materialises
 // [B,H,N,N] scores in HBM, here S and P never leave the SM.
 //
-// One persistent CTA per SM walks (frame, head) items.  Per item the queries form up to two 128-row tiles t:
-//   S_t = Q_t K^T        tcgen05.mma M=128, N=ceil16(keys), K=64;   fp32 S_t in TMEM columns [256t, 256t+N)
-//   P_t = exp2(c S_t - c max)   one thread per query row reads its S row from TMEM twice (max, then exp/sum),
-//                               writes bf16/fp16 P_t to shared memory in the no-swizzle K-major UMMA layout
-//   O_t = P_t V          tcgen05.mma M=128, N=64, K=keys; V is consumed straight from its TMA tile as an MN-major
-//                        B operand (no transpose anywhere); fp32 O_t in TMEM over S_t's first 64 columns
-//   out = O_t / rowsum   -> 16-bit -> swizzled staging -> 3-D TMA store (rows past the frame's last token clipped)
-// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM allocation), warps 2-5 and 6-9 two softmax/epilogue
-// groups.  Group g owns tile (g + item) & 1, so the 128-row and the 69-row tile alternate between the groups and while
-// one group runs its exponentials the tensor core works for the other.
+// One persistent CTA per SM walks (frame, head) items.  Per item the queries form up to two 128-row tiles:
+//   S = Q_t K^T          tcgen05.mma M=128, N=ceil16(keys), K=64;  fp32 S in 208 of a lane's 256 TMEM columns
+//   P = exp2(c S - c max)   two threads per query row (one per half of the keys) read S from TMEM twice (max, then
+//                           exp/sum), exchange max/sum through shared memory, and write 16-bit P to shared memory in
+//                           the no-swizzle K-major UMMA layout
+//   O = P V              tcgen05.mma M=128, N=64, K=keys; V is consumed straight from its TMA tile as an MN-major B
+//                        operand (no transpose anywhere); fp32 O over S's first 64 TMEM columns
+//   out = O / rowsum     -> 16-bit -> swizzled staging -> 3-D TMA store (rows past the frame's last token clipped)
+// The CTA runs two independent "lanes" L = 0,1, each with its own MMA-issuing thread, 256 TMEM columns, P buffer and
+// 8 softmax warps; lane L takes tile (L + item) & 1, so the 128-row and the 69-row tile alternate between the lanes and
+// each lane's S -> softmax -> PV -> output chain overlaps the other lane's.  Warp 0 is the TMA producer (Q/K are
+// reloaded as soon as both S MMAs of an item retire, V as soon as both PV MMAs do).
 // q/k/v are read in place from the fused-QKV GEMM output [B, N, 3, H, 64]; out is [B, N, H*64] (vit.py:83's
 // transpose(1,2).reshape), ready to be the proj GEMM's A operand.
 #include <math.h>
@@ -26,8 +28,8 @@ namespace {
 
 constexpr int HD = 64;
 constexpr int QT = 128;          // query rows per tile (UMMA M)
-constexpr int MAX_KEYS = 208;    // 13 x 16: S_t (fp32) fits 256 TMEM columns, K/V tiles fit one TMA box
-constexpr int ATC_THREADS = 320;
+constexpr int MAX_KEYS = 208;    // 13 x 16: S (fp32) fits 256 TMEM columns, K/V tiles fit one TMA box
+constexpr int ATC_THREADS = 640; // warp 0 producer, 1-2 MMA issuers, 3 TMEM allocator, 4-11 / 12-19 softmax groups
 
 constexpr int Q_BYTES = QT * HD * 2;               // 16 KB
 constexpr int KV_BYTES = MAX_KEYS * HD * 2;        // 26 KB
@@ -36,8 +38,9 @@ constexpr int OFF_Q = 0;
 constexpr int OFF_K = 2 * Q_BYTES;
 constexpr int OFF_V = OFF_K + KV_BYTES;
 constexpr int OFF_P = OFF_V + KV_BYTES;
-constexpr int OFF_OUT = OFF_P + 2 * P_BYTES;       // 8 warps x [32 rows][128 B]
-constexpr int OFF_BAR = OFF_OUT + 8 * 4096;
+constexpr int OFF_OUT = OFF_P + 2 * P_BYTES;       // 2 lanes x 4 quarters x [32 rows][128 B]
+constexpr int OFF_XCH = OFF_OUT + 8 * 4096;        // max / sum exchange: [2 lanes][2 halves][128 rows] x 2 floats
+constexpr int OFF_BAR = OFF_XCH + 2 * 2 * 128 * 8;
 constexpr int ATC_SMEM = OFF_BAR + 128 + 1024;     // + alignment slack
 static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_P % 1024 == 0 && OFF_OUT % 1024 == 0, "tile alignment");
 static_assert(ATC_SMEM <= 227 * 1024, "shared memory budget");
@@ -55,6 +58,46 @@ __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 
+// Row maximum over `n` (16 or 32) S values starting at column c0; columns >= N are padding.
+template <int W>
+__device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], int c0, int N, float mx) {
+    if (c0 + W <= N) {
+#pragma unroll
+        for (int i = 0; i < W; i += 2) mx = fmaxf(mx, fmaxf(__uint_as_float(r[i]), __uint_as_float(r[i + 1])));
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; ++i) mx = fmaxf(mx, (c0 + i < N) ? __uint_as_float(r[i]) : -INFINITY);
+    }
+    return mx;
+}
+
+// exp2(c s - c max) of W (16 or 32) S values -> 16-bit P chunks in shared memory; returns the partial row sums.
+template <typename T, int W>
+__device__ __forceinline__ void chunk_exp(const uint32_t (&r)[32], int c0, int N, float c, float neg_mxs, uint32_t prow,
+                                          float& sum0, float& sum1) {
+    const bool nomask = (c0 + W <= N);
+#pragma unroll
+    for (int q = 0; q < W / 8; ++q) {  // 8 keys = one 16-byte chunk of the UMMA A layout
+        float p[8];
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) {
+            float a0, a1;
+            ptx::fma2(a0, a1, __uint_as_float(r[8 * q + i]), __uint_as_float(r[8 * q + i + 1]), c, neg_mxs);
+            p[i] = ptx::ex2_approx(a0);
+            p[i + 1] = ptx::ex2_approx(a1);
+        }
+        if (!nomask) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                if (c0 + 8 * q + i >= N) p[i] = 0.f;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i += 2) ptx::add2(sum0, sum1, p[i], p[i + 1]);
+        ptx::st_shared_v4(prow + ((c0 >> 3) + q) * 2048, pack2<T>(p[0], p[1]), pack2<T>(p[2], p[3]), pack2<T>(p[4], p[5]),
+                          pack2<T>(p[6], p[7]));
+    }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
@@ -69,7 +112,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     uint64_t* v_full = bars + 1;
     uint64_t* qk_empty = bars + 2;
     uint64_t* v_empty = bars + 3;
-    uint64_t* s_full = bars + 4;   // [2]
+    uint64_t* s_full = bars + 4;   // [2] per lane
     uint64_t* p_full = bars + 6;   // [2]
     uint64_t* o_full = bars + 8;   // [2]
     uint64_t* s_free = bars + 10;  // [2]
@@ -87,17 +130,17 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         ptx::prefetch_tensormap(&map_out);
         ptx::mbar_init(qk_full, 1);
         ptx::mbar_init(v_full, 1);
-        ptx::mbar_init(qk_empty, 1);
-        ptx::mbar_init(v_empty, 1);
-        for (int t = 0; t < 2; ++t) {
-            ptx::mbar_init(&s_full[t], 1);
-            ptx::mbar_init(&p_full[t], 4);  // lane 0 of each of the owning group's 4 warps
-            ptx::mbar_init(&o_full[t], 1);
-            ptx::mbar_init(&s_free[t], 4);
+        ptx::mbar_init(qk_empty, n_tiles);  // one commit per lane that issued an S MMA for the item
+        ptx::mbar_init(v_empty, n_tiles);
+        for (int l = 0; l < 2; ++l) {
+            ptx::mbar_init(&s_full[l], 1);
+            ptx::mbar_init(&p_full[l], 8);  // lane 0 of each of the lane's 8 softmax warps
+            ptx::mbar_init(&o_full[l], 1);
+            ptx::mbar_init(&s_free[l], 4);  // one per row quarter, after the pair of warps sharing it has synchronised
         }
         ptx::fence_mbar_init();
     }
-    if (warp == 1) ptx::tmem_alloc<1>(tmem_ptr_smem, 512);
+    if (warp == 3) ptx::tmem_alloc<1>(tmem_ptr_smem, 512);
     ptx::tcgen05_fence_before();
     __syncthreads();
     ptx::tcgen05_fence_after();
@@ -122,159 +165,153 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             }
         }
         __syncwarp();
-    } else if (warp == 1) {
+    } else if (warp == 1 || warp == 2) {
         if (lane == 0) {
-            // ===================== MMA issuer =====================
+            // ===================== MMA issuer of lane L =====================
+            const int L = warp - 1;
             constexpr bool kIsBf16 = std::is_same<T, __nv_bfloat16>::value;
             const uint32_t idesc_s = ptx::make_idesc_f16(kIsBf16, QT, nk16);
             const uint32_t idesc_o = ptx::make_idesc_f16_bmn(kIsBf16, QT, HD);
             const int ksteps = nk16 / 16;
-            int it = 0;
+            const uint32_t tmem_d = tmem_base + L * 256;
+            const uint32_t sp = sbase + OFF_P + L * P_BYTES;
+            int it = 0, n = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const uint32_t ph = it & 1;
+                const int t = (n_tiles == 2) ? ((L + it) & 1) : L;  // one tile: lane 0 does every item, lane 1 idles
+                if (t >= n_tiles) continue;
+                const uint32_t ph = it & 1, par = n & 1;
+                ++n;
                 ptx::mbar_wait(qk_full, ph);
+                ptx::mbar_wait(&s_free[L], par ^ 1);  // this lane's previous O (aliasing S) has been read out
                 ptx::tcgen05_fence_after();
                 const uint64_t dk = ptx::make_kmajor_sw128_desc(sbase + OFF_K);
-                for (int t = 0; t < n_tiles; ++t) {
-                    ptx::mbar_wait(&s_free[t], ph ^ 1);  // last item's O_t (aliasing S_t) has been read out
-                    ptx::tcgen05_fence_after();
-                    const uint64_t dq = ptx::make_kmajor_sw128_desc(sbase + OFF_Q + t * Q_BYTES);
+                const uint64_t dq = ptx::make_kmajor_sw128_desc(sbase + OFF_Q + t * Q_BYTES);
 #pragma unroll
-                    for (int k = 0; k < HD / 16; ++k)
-                        ptx::umma_f16<1>(tmem_base + t * 256, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
-                    ptx::umma_commit<1>(&s_full[t]);
-                }
+                for (int k = 0; k < HD / 16; ++k) ptx::umma_f16<1>(tmem_d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
+                ptx::umma_commit<1>(&s_full[L]);
                 ptx::umma_commit<1>(qk_empty);
                 ptx::mbar_wait(v_full, ph);
-                for (int t = 0; t < n_tiles; ++t) {
-                    ptx::mbar_wait(&p_full[t], ph);  // P_t is in shared memory, S_t has been consumed
-                    ptx::tcgen05_fence_after();
-                    const uint32_t sp = sbase + OFF_P + t * P_BYTES;
-                    for (int j = 0; j < ksteps; ++j) {
-                        // A: P_t k-step j = two [128 rows][8 keys] chunks 2048 B apart, 8-row groups 128 B apart
-                        const uint64_t da = ptx::make_smem_desc(sp + j * 4096, 2048, 128, 0);
-                        // B: V rows 16j..16j+15 (two 8-row 1024-byte swizzle groups), 64 contiguous channels per row
-                        const uint64_t db = ptx::make_smem_desc(sbase + OFF_V + j * 2048, 0, 1024, 2);
-                        ptx::umma_f16<1>(tmem_base + t * 256, da, db, idesc_o, j != 0);
-                    }
-                    ptx::umma_commit<1>(&o_full[t]);
+                ptx::mbar_wait(&p_full[L], par);  // P is in shared memory, S has been consumed
+                ptx::tcgen05_fence_after();
+                for (int j = 0; j < ksteps; ++j) {
+                    // A: P k-step j = two [128 rows][8 keys] chunks 2048 B apart, 8-row groups 128 B apart
+                    const uint64_t da = ptx::make_smem_desc(sp + j * 4096, 2048, 128, 0);
+                    // B: V rows 16j..16j+15 (two 8-row 1024-byte swizzle groups), 64 contiguous channels per row
+                    const uint64_t db = ptx::make_smem_desc(sbase + OFF_V + j * 2048, 0, 1024, 2);
+                    ptx::umma_f16<1>(tmem_d, da, db, idesc_o, j != 0);
                 }
+                ptx::umma_commit<1>(&o_full[L]);
                 ptx::umma_commit<1>(v_empty);
             }
         }
         __syncwarp();
-    } else {
-        // ===================== softmax + output groups =====================
-        const int g = (warp - 2) >> 2;
-        const int quarter = warp & 3;  // TMEM lanes this warp may touch: 32 * (warp % 4) ...
-        const uint32_t stage = sbase + OFF_OUT + (warp - 2) * 4096;
-        const void* stage_ptr = smem + OFF_OUT + (warp - 2) * 4096;
-        int it = 0;
+    } else if (warp >= 4) {
+        // ===================== softmax + output group of lane L =====================
+        const int L = (warp - 4) >> 3;
+        const int half = ((warp - 4) >> 2) & 1;  // which half of the keys / of the 64 output channels
+        const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32 * (warp % 4) ...
+        const uint32_t pair_bar = 1 + L * 4 + quarter;  // named barrier shared with the warp handling the other half
+        const int row_in_tile = quarter * 32 + lane;
+        const uint32_t stage = sbase + OFF_OUT + (L * 4 + quarter) * 4096;
+        const void* stage_ptr = smem + OFF_OUT + (L * 4 + quarter) * 4096;
+        float2* xch_mine = reinterpret_cast<float2*>(smem + OFF_XCH) + (L * 2 + half) * 128 + row_in_tile;
+        float2* xch_other = reinterpret_cast<float2*>(smem + OFF_XCH) + (L * 2 + (half ^ 1)) * 128 + row_in_tile;
+        const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + L * 256;
+        const uint32_t prow = sbase + OFF_P + L * P_BYTES + row_in_tile * 16;
+        // this thread's key columns [cb, ce): the first ceil(nchunks/2) 16-column chunks go to half 0
+        const int split = ((nk16 / 16 + 1) / 2) * 16;
+        const int cb = half ? split : 0, ce = half ? nk16 : split;
+        int it = 0, n = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int t = (g + it) & 1;
+            const int t = (n_tiles == 2) ? ((L + it) & 1) : L;  // one tile: lane 0 does every item, lane 1 idles
             if (t >= n_tiles) continue;
-            const uint32_t ph = it & 1;
+            const uint32_t par = n & 1;
+            ++n;
             const int b = item / H, h = item - b * H;
-            const int row_in_tile = quarter * 32 + lane;
             const bool warp_valid = (t * QT + quarter * 32) < N;
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + t * 256;
-            float inv_sum = 0.f;
+            float sum0 = 0.f, sum1 = 0.f;
 
-            ptx::mbar_wait(&s_full[t], ph);
+            ptx::mbar_wait(&s_full[L], par);
             ptx::tcgen05_fence_after();
+            float mx = -INFINITY;
             if (warp_valid) {
-                // pass 1: row maximum over the valid keys
-                float mx = -INFINITY;
-                for (int c0 = 0; c0 < nk16; c0 += 32) {
+                for (int c0 = cb; c0 < ce; c0 += 32) {
                     uint32_t r[32];
-                    if (c0 + 32 <= nk16) {
+                    if (c0 + 32 <= ce) {
                         ptx::tmem_ld_32x32b_x32(taddr + c0, r);
+                        ptx::tmem_ld_wait();
+                        mx = chunk_max<32>(r, c0, N, mx);
                     } else {
                         ptx::tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-#pragma unroll
-                        for (int i = 16; i < 32; ++i) r[i] = 0xff800000u;  // -inf
-                    }
-                    ptx::tmem_ld_wait();
-                    if (c0 + 32 <= N) {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(r[i]));
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, (c0 + i < N) ? __uint_as_float(r[i]) : -INFINITY);
+                        ptx::tmem_ld_wait();
+                        mx = chunk_max<16>(r, c0, N, mx);
                     }
                 }
-                const float mxs = mx * scale_log2e;
-                // pass 2: p = exp2(c s - c max), row sum, 16-bit P into the UMMA A layout
-                float sum = 0.f;
-                const uint32_t prow = sbase + OFF_P + t * P_BYTES + row_in_tile * 16;
-                for (int c0 = 0; c0 < nk16; c0 += 32) {
+                xch_mine->x = mx;
+                // the staging tile is about to be reused: its previous TMA store (issued by the half-0 warp) must have read it
+                if (half == 0 && lane == 0) ptx::bulk_wait_group_read<0>();
+            }
+            ptx::named_bar_sync(pair_bar, 64);
+            if (warp_valid) {
+                mx = fmaxf(mx, xch_other->x);  // half 0 always holds key 0, so the row maximum is finite
+                const float neg_mxs = -mx * scale_log2e;
+                for (int c0 = cb; c0 < ce; c0 += 32) {
                     uint32_t r[32];
-                    const bool wide = (c0 + 32 <= nk16);
-                    if (wide)
+                    if (c0 + 32 <= ce) {
                         ptx::tmem_ld_32x32b_x32(taddr + c0, r);
-                    else
+                        ptx::tmem_ld_wait();
+                        chunk_exp<T, 32>(r, c0, N, scale_log2e, neg_mxs, prow, sum0, sum1);
+                    } else {
                         ptx::tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
-                    ptx::tmem_ld_wait();
-                    const bool nomask = (c0 + 32 <= N);
-#pragma unroll
-                    for (int q4 = 0; q4 < 4; ++q4) {  // 8 keys = one 16-byte chunk
-                        if (q4 < 2 || wide) {
-                            float p[8];
-#pragma unroll
-                            for (int i = 0; i < 8; ++i) {
-                                const float e = ptx::ex2_approx(fmaf(__uint_as_float(r[8 * q4 + i]), scale_log2e, -mxs));
-                                p[i] = (nomask || c0 + 8 * q4 + i < N) ? e : 0.f;
-                                sum += p[i];
-                            }
-                            ptx::st_shared_v4(prow + ((c0 >> 3) + q4) * 2048, pack2<T>(p[0], p[1]), pack2<T>(p[2], p[3]),
-                                              pack2<T>(p[4], p[5]), pack2<T>(p[6], p[7]));
-                        }
+                        ptx::tmem_ld_wait();
+                        chunk_exp<T, 16>(r, c0, N, scale_log2e, neg_mxs, prow, sum0, sum1);
                     }
                 }
-                inv_sum = 1.0f / sum;
+                xch_mine->y = sum0 + sum1;
             }
             ptx::fence_proxy_async_smem();  // P (generic-proxy stores) before the MMA's async-proxy reads
             ptx::tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&p_full[t]);
+            if (lane == 0) ptx::mbar_arrive(&p_full[L]);
 
-            ptx::mbar_wait(&o_full[t], ph);
+            ptx::mbar_wait(&o_full[L], par);
             ptx::tcgen05_fence_after();
             if (warp_valid) {
-                uint32_t r[64];
-                ptx::tmem_ld_32x32b_x32(taddr, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
-                ptx::tmem_ld_32x32b_x32(taddr + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-                if (lane == 0) ptx::bulk_wait_group_read<0>();  // this warp's previous output store has left the staging tile
+                uint32_t r[32];
+                ptx::tmem_ld_32x32b_x32(taddr + half * 32, r);
+                const float inv_sum = 1.0f / (sum0 + sum1 + xch_other->y);
                 ptx::tmem_ld_wait();
-                __syncwarp();
                 const uint32_t srow = stage + lane * 128;
                 const uint32_t swz = static_cast<uint32_t>(lane & 7);
 #pragma unroll
-                for (int c = 0; c < 8; ++c) {
+                for (int c = 0; c < 4; ++c) {
                     uint32_t u[4];
 #pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        u[i] = pack2<T>(__uint_as_float(r[8 * c + 2 * i]) * inv_sum, __uint_as_float(r[8 * c + 2 * i + 1]) * inv_sum);
-                    ptx::st_shared_v4(srow + ((static_cast<uint32_t>(c) ^ swz) << 4), u[0], u[1], u[2], u[3]);
+                    for (int i = 0; i < 4; ++i) {
+                        float a0, a1;
+                        ptx::mul2(a0, a1, __uint_as_float(r[8 * c + 2 * i]), __uint_as_float(r[8 * c + 2 * i + 1]), inv_sum);
+                        u[i] = pack2<T>(a0, a1);
+                    }
+                    ptx::st_shared_v4(srow + ((static_cast<uint32_t>(4 * half + c) ^ swz) << 4), u[0], u[1], u[2], u[3]);
                 }
                 ptx::fence_proxy_async_smem();
             }
             ptx::tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                ptx::mbar_arrive(&s_free[t]);  // S_t / O_t columns may be overwritten by the next item's S_t
+            ptx::named_bar_sync(pair_bar, 64);  // both halves of the staging tile written, both warps done with TMEM
+            if (half == 0 && lane == 0) {
+                ptx::mbar_arrive(&s_free[L]);  // the lane's TMEM columns may take the next S
                 if (warp_valid) {
                     ptx::tma_store_3d(&map_out, stage_ptr, h * HD, t * QT + quarter * 32, b);
                     ptx::bulk_commit_group();
                 }
             }
         }
-        if (lane == 0) ptx::bulk_wait_group<0>();
+        if (half == 0 && lane == 0) ptx::bulk_wait_group<0>();
     }
 
     ptx::tcgen05_fence_before();
     __syncthreads();
-    if (warp == 1) ptx::tmem_dealloc<1>(tmem_base, 512);
+    if (warp == 3) ptx::tmem_dealloc<1>(tmem_base, 512);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,

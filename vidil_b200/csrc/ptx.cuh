@@ -102,6 +102,35 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
                  : "memory");
 }
 
+// Named CTA barrier `id` (1..15; 0 is __syncthreads) over `nthreads` threads (a multiple of 32).
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Packed fp32x2 arithmetic (sm_100): one instruction for two lanes of a register pair.
+__device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, float b, float c) {
+    uint64_t d, a, bb, cc;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(cc) : "f"(c));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+__device__ __forceinline__ void add2(float& s0, float& s1, float a0, float a1) {
+    uint64_t s, a;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(s) : "f"(s0), "f"(s1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("add.rn.f32x2 %0, %0, %1;" : "+l"(s) : "l"(a));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(s0), "=f"(s1) : "l"(s));
+}
+__device__ __forceinline__ void mul2(float& d0, float& d1, float a0, float a1, float b) {
+    uint64_t d, a, bb;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(bb) : "f"(b));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(bb));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
+
 // ----------------------------------------------------------------------------------------
 // Cluster barrier
 // ----------------------------------------------------------------------------------------

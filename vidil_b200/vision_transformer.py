@@ -81,6 +81,7 @@ class NativeEncoder:
         self.tokens = self.lib.vidil_encoder_tokens(self.handle)
         self._ws = None
         self._scratch = None
+        self._pipe = None
 
     def __del__(self):
         try:
@@ -97,6 +98,23 @@ class NativeEncoder:
         st = self.lib.vidil_encoder_load(self.handle, name.encode(), t.data_ptr(), t.numel(),
                                          torch.cuda.current_stream().cuda_stream)
         _lib.check(st, f"vidil_encoder_load({name})")
+
+    def pipeline_scratch(self, batch: int, device) -> torch.Tensor:
+        need = self.lib.vidil_encoder_host_pipeline_scratch_bytes(self.handle, batch)
+        if self._pipe is None or self._pipe.numel() < need or self._pipe.device != device:
+            self._pipe = self._aligned(need, device)
+        return self._pipe
+
+    def host_submit(self, frames: torch.Tensor, out: torch.Tensor, slot: int, device) -> None:
+        """Enqueue H2D -> forward -> D2H of one host batch into `slot` (0/1); returns immediately."""
+        B = frames.shape[0]
+        scratch = self.pipeline_scratch(B, device)
+        st = self.lib.vidil_encoder_host_submit(self.handle, frames.data_ptr(), B, out.data_ptr(), slot, scratch.data_ptr(),
+                                                scratch.numel(), torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "vidil_encoder_host_submit")
+
+    def host_wait(self, slot: int) -> None:
+        _lib.check(self.lib.vidil_encoder_host_wait(self.handle, slot), "vidil_encoder_host_wait")
 
     def set_profiling(self, enable: bool) -> None:
         _lib.check(self.lib.vidil_encoder_set_profiling(self.handle, int(enable)), "vidil_encoder_set_profiling")
@@ -251,6 +269,40 @@ class VisionTransformer(nn.Module):
                                                 scratch.numel(), torch.cuda.current_stream().cuda_stream)
             _lib.check(st, "vidil_vit_forward_host")
         return out
+
+    @torch.no_grad()
+    def encode_host_stream(self, batches, outs=None):
+        """Encode a stream of host batches with copies overlapped with compute.
+
+        `batches`: iterable of CPU fp32 tensors [B,3,S,S] (pinned for full PCIe rate; all the same B).  Yields one CPU
+        tensor [B, N+1, D] per batch, in order.  `outs`: optional pair of pinned output tensors to cycle through (the
+        yielded tensor is then only valid until two batches later).  Batch k+1's H2D runs during batch k's forward and
+        batch k's D2H during batch k+1's (vidil_encoder_host_submit / _wait, two slots)."""
+        dev = self.cls_token.device
+        if dev.type != "cuda":
+            raise RuntimeError("vidil_b200: the module must be moved to a CUDA device first")
+        with torch.cuda.device(dev):
+            enc = self._ensure_packed()
+            pending = []  # (slot, out)
+            k = 0
+            for frames in batches:
+                if frames.is_cuda:
+                    raise RuntimeError("encode_host_stream takes host tensors")
+                _check_frames(frames, self.img_size)
+                frames = frames.contiguous().float()
+                slot = k & 1
+                if len(pending) == 2:  # the slot about to be reused must have delivered its result
+                    s0, o0, _ = pending.pop(0)
+                    enc.host_wait(s0)
+                    yield o0
+                out = outs[slot] if outs is not None else torch.empty(frames.shape[0], enc.tokens, self.embed_dim,
+                                                                      dtype=torch.float32, pin_memory=True)
+                enc.host_submit(frames, out, slot, dev)
+                pending.append((slot, out, frames))  # keep the input alive until its copy has run
+                k += 1
+            for s0, o0, _ in pending:
+                enc.host_wait(s0)
+                yield o0
 
     @torch.jit.ignore()
     def load_pretrained(self, checkpoint_path, prefix=''):
