@@ -153,6 +153,11 @@ size_t  vidil_op_attention_workspace_bytes(int32_t B, int32_t N, int32_t H);
 int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- developer hooks ---------------------------------------------------------------------------- */
+/* dev_buf: device buffer of 5*16*8 int64 (or NULL to switch off).  While set, CTA 0 of the tcgen05 attention kernel
+ * stamps clock64() at its pipeline synchronisation points for its first 16 items (tools/attn_trace.py prints them). */
+void vidil_debug_set_attention_trace(void* dev_buf);
+
 #ifdef __cplusplus
 }
 #endif

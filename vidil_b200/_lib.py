@@ -73,6 +73,7 @@ SIGNATURES = {
     "vidil_sim_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "vidil_sim_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
+    "vidil_debug_set_attention_trace": (None, [c_void_p]),
     "vidil_op_linear_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "vidil_op_linear": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
                                   c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),

@@ -821,6 +821,8 @@ int32_t vidil_sim_topk(const float* img, const float* bank, int32_t F, int32_t T
     return topk_rerank_run(scores, ld, img, bank, F, T, D, k, out_scores, out_idx, s);
 }
 
+void vidil_debug_set_attention_trace(void* dev_buf) { attention_set_trace(reinterpret_cast<long long*>(dev_buf)); }
+
 // ---- operator-level entry points --------------------------------------------------------------------
 size_t vidil_op_linear_workspace_bytes(int32_t M, int32_t N, int32_t K) {
     if (M <= 0 || N <= 0 || K <= 0) return 0;

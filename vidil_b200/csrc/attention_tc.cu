@@ -101,7 +101,13 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&r)[32], int c0, int N
 template <typename T>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
-                        const __grid_constant__ CUtensorMap map_out, int n_items, int N, int H, float scale_log2e) {
+                        const __grid_constant__ CUtensorMap map_out, int n_items, int N, int H, float scale_log2e,
+                        long long* trace) {
+    // Developer timeline (vidil_debug_set_trace): CTA 0 stamps clock64 at its synchronisation points for 16 items.
+#define ATC_TRACE(role, ev)                                                                    \
+    do {                                                                                       \
+        if (trace != nullptr && blockIdx.x == 0 && it < 16) trace[((role) * 16 + it) * 8 + (ev)] = clock64(); \
+    } while (0)
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -154,12 +160,15 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                 const uint32_t ph = it & 1;
                 const int b = item / H, h = item - b * H;
                 const int row0 = b * N;
+                ATC_TRACE(0, 0);
                 ptx::mbar_wait(qk_empty, ph ^ 1);  // previous item's S MMAs have consumed Q and K
+                ATC_TRACE(0, 1);
                 ptx::mbar_arrive_expect_tx(qk_full, n_tiles * Q_BYTES + nk16 * HD * 2);
                 ptx::tma_load_2d(&map_q, qk_full, smem + OFF_Q, h * HD, row0);
                 if (n_tiles == 2) ptx::tma_load_2d(&map_q, qk_full, smem + OFF_Q + Q_BYTES, h * HD, row0 + QT);
                 ptx::tma_load_2d(&map_kv, qk_full, smem + OFF_K, D + h * HD, row0);
                 ptx::mbar_wait(v_empty, ph ^ 1);  // previous item's PV MMAs have consumed V
+                ATC_TRACE(0, 2);
                 ptx::mbar_arrive_expect_tx(v_full, nk16 * HD * 2);
                 ptx::tma_load_2d(&map_kv, v_full, smem + OFF_V, 2 * D + h * HD, row0);
             }
@@ -181,8 +190,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                 if (t >= n_tiles) continue;
                 const uint32_t ph = it & 1, par = n & 1;
                 ++n;
+                ATC_TRACE(1 + L, 0);
                 ptx::mbar_wait(qk_full, ph);
+                ATC_TRACE(1 + L, 1);
                 ptx::mbar_wait(&s_free[L], par ^ 1);  // this lane's previous O (aliasing S) has been read out
+                ATC_TRACE(1 + L, 2);
                 ptx::tcgen05_fence_after();
                 const uint64_t dk = ptx::make_kmajor_sw128_desc(sbase + OFF_K);
                 const uint64_t dq = ptx::make_kmajor_sw128_desc(sbase + OFF_Q + t * Q_BYTES);
@@ -190,8 +202,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                 for (int k = 0; k < HD / 16; ++k) ptx::umma_f16<1>(tmem_d, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                 ptx::umma_commit<1>(&s_full[L]);
                 ptx::umma_commit<1>(qk_empty);
+                ATC_TRACE(1 + L, 3);
                 ptx::mbar_wait(v_full, ph);
+                ATC_TRACE(1 + L, 4);
                 ptx::mbar_wait(&p_full[L], par);  // P is in shared memory, S has been consumed
+                ATC_TRACE(1 + L, 5);
                 ptx::tcgen05_fence_after();
                 for (int j = 0; j < ksteps; ++j) {
                     // A: P k-step j = two [128 rows][8 keys] chunks 2048 B apart, 8-row groups 128 B apart
@@ -202,6 +217,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                 }
                 ptx::umma_commit<1>(&o_full[L]);
                 ptx::umma_commit<1>(v_empty);
+                ATC_TRACE(1 + L, 6);
             }
         }
         __syncwarp();
@@ -231,7 +247,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             const bool warp_valid = (t * QT + quarter * 32) < N;
             float sum0 = 0.f, sum1 = 0.f;
 
+#define ATC_TRACE_S(ev)                                     \
+    do {                                                    \
+        if (quarter == 0 && half == 0 && lane == 0) ATC_TRACE(3 + L, ev); \
+    } while (0)
+            ATC_TRACE_S(0);
             ptx::mbar_wait(&s_full[L], par);
+            ATC_TRACE_S(1);
             ptx::tcgen05_fence_after();
             float mx = -INFINITY;
             if (warp_valid) {
@@ -251,7 +273,13 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                 // the staging tile is about to be reused: its previous TMA store (issued by the half-0 warp) must have read it
                 if (half == 0 && lane == 0) ptx::bulk_wait_group_read<0>();
             }
+            ATC_TRACE_S(2);
             ptx::named_bar_sync(pair_bar, 64);
+            // The exponentials saturate the SM's MUFU units, everything else in a lane's chain (S / PV MMAs, barriers, output)
+            // does not use them: pass the MUFU phase back and forth between the lanes so that one lane's exponentials run
+            // under the other lane's MMAs instead of both lanes doing the same phase at the same time.
+            if (n_tiles == 2) ptx::mbar_wait(&p_full[L ^ 1], L == 0 ? (par ^ 1) : par);
+            ATC_TRACE_S(3);
             if (warp_valid) {
                 mx = fmaxf(mx, xch_other->x);  // half 0 always holds key 0, so the row maximum is finite
                 const float neg_mxs = -mx * scale_log2e;
@@ -273,8 +301,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             ptx::tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p_full[L]);
-
+            ATC_TRACE_S(4);
             ptx::mbar_wait(&o_full[L], par);
+            ATC_TRACE_S(5);
             ptx::tcgen05_fence_after();
             if (warp_valid) {
                 uint32_t r[32];
@@ -297,7 +326,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                 ptx::fence_proxy_async_smem();
             }
             ptx::tcgen05_fence_before();
+            ATC_TRACE_S(6);
             ptx::named_bar_sync(pair_bar, 64);  // both halves of the staging tile written, both warps done with TMEM
+            ATC_TRACE_S(7);
             if (half == 0 && lane == 0) {
                 ptx::mbar_arrive(&s_free[L]);  // the lane's TMEM columns may take the next S
                 if (warp_valid) {
@@ -330,6 +361,8 @@ EncodeTiledFn encode_fn() {
     return fn;
 }
 
+long long* g_trace = nullptr;  // developer hook, see attention_set_trace
+
 template <typename T>
 int launch_tc(const AttentionMaps& m, int B, int N, int H, float scale_log2e, cudaStream_t stream) {
     auto kern = attention_tc_kernel<T>;
@@ -342,13 +375,15 @@ int launch_tc(const AttentionMaps& m, int B, int N, int H, float scale_log2e, cu
     int grid = gemm_num_sms();
     if (grid > n_items) grid = n_items;
     if (grid < 1) return 1;
-    kern<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(m.q, m.kv, m.out, n_items, N, H, scale_log2e);
+    kern<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(m.q, m.kv, m.out, n_items, N, H, scale_log2e, g_trace);
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;
 }
 
 }  // namespace
+
+void attention_set_trace(long long* dev_buf) { g_trace = dev_buf; }
 
 bool attention_tc_supported(int N) { return N >= 1 && N <= MAX_KEYS; }
 

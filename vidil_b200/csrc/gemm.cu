@@ -45,10 +45,10 @@ struct Cfg {
     static constexpr int W_ROWS = BLOCK_N / CG;                   // rows of W this CTA stages
     static constexpr int W_BYTES = W_ROWS * BLOCK_K * 2;          // 32 KB or 16 KB
     static constexpr int STAGE_BYTES = A_BYTES + W_BYTES;         // 48 KB or 32 KB
-    static constexpr int STAGES = (CG == 1) ? 3 : 5;              // 144 KB / 160 KB of operand ring
+    static constexpr int STAGES = (CG == 1) ? 4 : 6;              // 192 KB of operand ring either way
     static constexpr int RING_BYTES = STAGES * STAGE_BYTES;
     static constexpr int OUT_BUF_BYTES = 32 * 128;                // one epilogue piece: 32 rows x 128 bytes
-    static constexpr int OUT_BYTES = NUM_EPI_WARPS * 2 * OUT_BUF_BYTES;  // double-buffered per warp: 64 KB
+    static constexpr int OUT_BYTES = NUM_EPI_WARPS * OUT_BUF_BYTES;      // one staging tile per epilogue warp: 32 KB
     static constexpr int BAR_BYTES = 256;
     static constexpr int SMEM_BYTES = RING_BYTES + OUT_BYTES + BAR_BYTES + 1024;  // +1024 alignment slack
 };
@@ -325,10 +325,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         constexpr bool kOut16 = (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_QUICKGELU);
         constexpr int PIECE_COLS = kOut16 ? 64 : 32;  // one staged piece is 32 rows x 128 bytes
         constexpr int PIECES = 128 / PIECE_COLS;
-        const uint32_t stage_base = ptx::smem_u32(out_stage) + ew * 2 * C::OUT_BUF_BYTES;
+        const uint32_t stage_base = ptx::smem_u32(out_stage) + ew * C::OUT_BUF_BYTES;
         const uint32_t swz = static_cast<uint32_t>(lane & 7);  // 128-byte swizzle: 16-byte chunk index ^= row & 7
         const uint32_t row_off = static_cast<uint32_t>(lane) * 128u;
-        int piece_no = 0;
         int iter = 0;
         for (int t = cluster_id; t < num_tiles; t += num_clusters, ++iter) {
             const int acc = iter & 1;
@@ -336,20 +335,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
             const int m0 = ((t / tiles_n) * CG + static_cast<int>(cta_rank)) * BLOCK_M;
             const int n0 = (t % tiles_n) * BLOCK_N;
             const int row0 = m0 + lane_quarter * 32;  // first row of this warp's 32-row band
+            // This warp's 128 bias values, lane l holding columns l, 32+l, 64+l, 96+l of the range: fetched before the
+            // accumulator is waited for (a load issued at the point of use stalls every piece on an L2 round trip) and
+            // broadcast with shuffles below.
+            float bias_r[4] = {0.f, 0.f, 0.f, 0.f};
+            if (kTmaOut && epi.bias != nullptr) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int col = n0 + col_half * 128 + 32 * j + lane;
+                    if (col < N) bias_r[j] = __ldg(epi.bias + col);
+                }
+            }
             ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
             ptx::tcgen05_fence_after();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(lane_quarter * 32) << 16) + acc * BLOCK_N + col_half * 128;
             if constexpr (kTmaOut) {
 #pragma unroll 1
-                for (int pc = 0; pc < PIECES; ++pc, ++piece_no) {
+                for (int pc = 0; pc < PIECES; ++pc) {
                     const int col0 = n0 + col_half * 128 + pc * PIECE_COLS;
                     uint32_t r[PIECE_COLS];
                     ptx::tmem_ld_32x32b_x32(taddr + pc * PIECE_COLS, *reinterpret_cast<uint32_t(*)[32]>(&r[0]));
                     if constexpr (PIECE_COLS == 64)
                         ptx::tmem_ld_32x32b_x32(taddr + pc * PIECE_COLS + 32, *reinterpret_cast<uint32_t(*)[32]>(&r[32]));
-                    // the staging buffer about to be overwritten was handed to TMA two pieces ago by lane 0
-                    if (lane == 0) ptx::bulk_wait_group_read<1>();
+                    // the staging tile about to be overwritten was handed to TMA one piece ago by lane 0; its read
+                    // has had this piece's TMEM load to complete
+                    if (lane == 0) ptx::bulk_wait_group_read<0>();
                     ptx::tmem_ld_wait();
                     if (pc == PIECES - 1) {
                         // All of this warp's TMEM reads for the tile are complete: hand the accumulator back.
@@ -365,21 +376,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                         __syncwarp();
                     }
                     if (row0 < M && col0 < N) {  // warp-uniform; TMA clips the partial tails
-                        const uint32_t buf = stage_base + (piece_no & 1) * C::OUT_BUF_BYTES + row_off;
-                        const bool full = (col0 + PIECE_COLS <= N);
+                        const uint32_t buf = stage_base + row_off;
+                        // this piece's bias registers, picked with selects so the array is never indexed dynamically
+                        float bsel[2];
+                        if constexpr (PIECE_COLS == 64) {
+                            bsel[0] = pc == 0 ? bias_r[0] : bias_r[2];
+                            bsel[1] = pc == 0 ? bias_r[1] : bias_r[3];
+                        } else {
+                            bsel[0] = pc == 0 ? bias_r[0] : (pc == 1 ? bias_r[1] : (pc == 2 ? bias_r[2] : bias_r[3]));
+                            bsel[1] = 0.f;
+                        }
 #pragma unroll
                         for (int c = 0; c < PIECE_COLS / 4; ++c) {  // 4 columns at a time
                             float v[4];
 #pragma unroll
                             for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[4 * c + i]);
-                            if (epi.bias != nullptr) {
-                                if (full) {
-                                    const float4 b = __ldg(reinterpret_cast<const float4*>(epi.bias + col0) + c);
-                                    v[0] += b.x; v[1] += b.y; v[2] += b.z; v[3] += b.w;
-                                } else {
+                            if (epi.bias != nullptr) {  // warp-uniform
 #pragma unroll
-                                    for (int i = 0; i < 4; ++i)
-                                        if (col0 + 4 * c + i < N) v[i] += __ldg(epi.bias + col0 + 4 * c + i);
+                                for (int i = 0; i < 4; ++i) {
+                                    const int cc = 4 * c + i;  // column within the piece
+                                    v[i] += __shfl_sync(0xffffffffu, bsel[cc >> 5], cc & 31);
                                 }
                             }
                             if constexpr (EPI == EPI_GELU) {
@@ -406,7 +422,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                         ptx::fence_proxy_async_smem();
                         __syncwarp();
                         if (lane == 0) {
-                            const void* src = out_stage + (ew * 2 + (piece_no & 1)) * C::OUT_BUF_BYTES;
+                            const void* src = out_stage + ew * C::OUT_BUF_BYTES;
                             if constexpr (EPI == EPI_RESID)
                                 ptx::tma_reduce_add_2d(&map_out, src, col0, row0);
                             else

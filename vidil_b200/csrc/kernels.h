@@ -87,6 +87,8 @@ struct AttentionMaps {
     int B = 0, N = 0, H = 0;
     DType dt = DT_BF16;
 };
+// Developer hook: a device buffer of 5*16*8 int64 that CTA 0 fills with clock64 stamps of its pipeline events.
+void attention_set_trace(long long* dev_buf);
 bool attention_tc_supported(int N);
 int attention_tc_prepare(AttentionMaps& m, const void* qkv, void* out, DType dt, int B, int N, int H);
 int attention_tc_run(const AttentionMaps& m, float scale, cudaStream_t stream);
