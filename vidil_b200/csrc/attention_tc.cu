@@ -71,6 +71,24 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], int c0, int 
     return mx;
 }
 
+// 2^a for a <= 0 on the FMA / ALU pipes (no MUFU): a = n + f with n = round(a), f in [-0.5, 0.5]; 2^f by a degree-4
+// near-minimax polynomial (rel. err 3.7e-6, far below the 16-bit rounding of P), 2^n by adding n to the exponent field.
+// The magic constant 1.5 * 2^23 leaves n in the low mantissa bits of t.
+__device__ __forceinline__ float exp2_poly(float a) {
+    a = fmaxf(a, -126.0f);
+    const float t = a + 12582912.0f;
+    const float f = a - (t - 12582912.0f);
+    float p = fmaf(f, 9.676037098e-03f, 5.592203565e-02f);
+    p = fmaf(f, p, 2.402210736e-01f);
+    p = fmaf(f, p, 6.931210340e-01f);
+    p = fmaf(f, p, 1.000000075e+00f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// The MUFU unit retires 4 exponentials per clock per SM sub-partition and is what bounds the softmax; POLY_PER_8 of every
+// 8 exponentials are therefore evaluated on the otherwise idle FMA pipe.
+constexpr int POLY_PER_8 = 3;
+
 // exp2(c s - c max) of W (16 or 32) S values -> 16-bit P chunks in shared memory; returns the partial row sums.
 template <typename T, int W>
 __device__ __forceinline__ void chunk_exp(const uint32_t (&r)[32], int c0, int N, float c, float neg_mxs, uint32_t prow,
@@ -83,8 +101,8 @@ __device__ __forceinline__ void chunk_exp(const uint32_t (&r)[32], int c0, int N
         for (int i = 0; i < 8; i += 2) {
             float a0, a1;
             ptx::fma2(a0, a1, __uint_as_float(r[8 * q + i]), __uint_as_float(r[8 * q + i + 1]), c, neg_mxs);
-            p[i] = ptx::ex2_approx(a0);
-            p[i + 1] = ptx::ex2_approx(a1);
+            p[i] = (i < POLY_PER_8) ? exp2_poly(a0) : ptx::ex2_approx(a0);
+            p[i + 1] = (i + 1 < POLY_PER_8) ? exp2_poly(a1) : ptx::ex2_approx(a1);
         }
         if (!nomask) {
 #pragma unroll

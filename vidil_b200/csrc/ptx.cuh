@@ -116,6 +116,15 @@ __device__ __forceinline__ void fma2(float& d0, float& d1, float a0, float a1, f
     asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(bb), "l"(cc));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
 }
+// d = a * b + c with all three operands per-lane pairs
+__device__ __forceinline__ void fma2v(float& d0, float& d1, float a0, float a1, float b0, float b1, float c0, float c1) {
+    uint64_t d, a, b, c;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(a) : "f"(a0), "f"(a1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(b) : "f"(b0), "f"(b1));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(c) : "f"(c0), "f"(c1));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d0), "=f"(d1) : "l"(d));
+}
 __device__ __forceinline__ void add2(float& s0, float& s1, float a0, float a1) {
     uint64_t s, a;
     asm("mov.b64 %0, {%1, %2};" : "=l"(s) : "f"(s0), "f"(s1));
