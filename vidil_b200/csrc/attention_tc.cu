@@ -72,8 +72,10 @@ __device__ __forceinline__ float chunk_max(const uint32_t (&r)[32], int c0, int 
 }
 
 // 2^a for a <= 0 on the FMA / ALU pipes (no MUFU): a = n + f with n = round(a), f in [-0.5, 0.5]; 2^f by a degree-4
-// near-minimax polynomial (rel. err 3.7e-6, far below the 16-bit rounding of P), 2^n by adding n to the exponent field.
-// The magic constant 1.5 * 2^23 leaves n in the low mantissa bits of t.
+// near-minimax polynomial (rel. err 3.7e-6), 2^n by adding n to the exponent field (the magic constant 1.5 * 2^23 leaves n
+// in the low mantissa bits of t).  Measured on B200 (ViT-L shape, ncu): evaluating 0 / 1 / 2 / 3 of every 8 exponentials
+// this way gives 136.3 / 136.7 / 138.4 / 143.3 us per layer — the MUFU unit (4 exponentials per clock per sub-partition)
+// is NOT what bounds the softmax phase, the extra instructions cost more than the MUFU slots they free — so POLY_PER_8 = 0.
 __device__ __forceinline__ float exp2_poly(float a) {
     a = fmaxf(a, -126.0f);
     const float t = a + 12582912.0f;
@@ -84,10 +86,7 @@ __device__ __forceinline__ float exp2_poly(float a) {
     p = fmaf(f, p, 1.000000075e+00f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-
-// The MUFU unit retires 4 exponentials per clock per SM sub-partition and is what bounds the softmax; POLY_PER_8 of every
-// 8 exponentials are therefore evaluated on the otherwise idle FMA pipe.
-constexpr int POLY_PER_8 = 3;
+constexpr int POLY_PER_8 = 0;
 
 // exp2(c s - c max) of W (16 or 32) S values -> 16-bit P chunks in shared memory; returns the partial row sums.
 template <typename T, int W>
@@ -245,6 +244,15 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         const int half = ((warp - 4) >> 2) & 1;  // which half of the keys / of the 64 output channels
         const int quarter = warp & 3;            // TMEM lanes this warp may touch: 32 * (warp % 4) ...
         const uint32_t pair_bar = 1 + L * 4 + quarter;  // named barrier shared with the warp handling the other half
+        const uint32_t group_bar = 9 + L;               // named barrier of the lane's 8 softmax warps
+        const bool poller = ((warp - 4) & 7) == 0;
+        // A warp spinning on an mbarrier issues a few instructions every ~20 clocks; with 8 warps of one lane doing that
+        // while the other lane computes, a third of the SM's issue slots went to polling.  One warp per lane polls, the
+        // other seven sleep in a hardware named barrier.
+        auto group_wait = [&](uint64_t* bar, uint32_t parity) {
+            if (poller) ptx::mbar_wait(bar, parity);
+            ptx::named_bar_sync(group_bar, 256);
+        };
         const int row_in_tile = quarter * 32 + lane;
         const uint32_t stage = sbase + OFF_OUT + (L * 4 + quarter) * 4096;
         const void* stage_ptr = smem + OFF_OUT + (L * 4 + quarter) * 4096;
@@ -270,7 +278,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         if (quarter == 0 && half == 0 && lane == 0) ATC_TRACE(3 + L, ev); \
     } while (0)
             ATC_TRACE_S(0);
-            ptx::mbar_wait(&s_full[L], par);
+            group_wait(&s_full[L], par);
             ATC_TRACE_S(1);
             ptx::tcgen05_fence_after();
             float mx = -INFINITY;
@@ -293,10 +301,10 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             }
             ATC_TRACE_S(2);
             ptx::named_bar_sync(pair_bar, 64);
-            // The exponentials saturate the SM's MUFU units, everything else in a lane's chain (S / PV MMAs, barriers, output)
-            // does not use them: pass the MUFU phase back and forth between the lanes so that one lane's exponentials run
-            // under the other lane's MMAs instead of both lanes doing the same phase at the same time.
-            if (n_tiles == 2) ptx::mbar_wait(&p_full[L ^ 1], L == 0 ? (par ^ 1) : par);
+            // Pass the exponential phase back and forth between the lanes, so that one lane's softmax runs under the other
+            // lane's MMAs / barriers / output instead of both lanes doing the same phase at the same time (they fall into
+            // lockstep otherwise, because they share the Q/K/V buffers).  Measured: 162 -> 136 us per layer.
+            if (n_tiles == 2) group_wait(&p_full[L ^ 1], L == 0 ? (par ^ 1) : par);
             ATC_TRACE_S(3);
             if (warp_valid) {
                 mx = fmaxf(mx, xch_other->x);  // half 0 always holds key 0, so the row maximum is finite
@@ -320,7 +328,7 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(&p_full[L]);
             ATC_TRACE_S(4);
-            ptx::mbar_wait(&o_full[L], par);
+            group_wait(&o_full[L], par);
             ATC_TRACE_S(5);
             ptx::tcgen05_fence_after();
             if (warp_valid) {

@@ -358,7 +358,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
                     if (col < N) bias_r[j] = __ldg(epi.bias + col);
                 }
             }
-            ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+            // One epilogue warp polls the accumulator barrier, the other seven sleep in a hardware named barrier: eight
+            // warps spinning on an mbarrier take issue slots from the warps that still have epilogue math to do.
+            if (ew == 0) ptx::mbar_wait(&tmem_full_bar[acc], acc_phase);
+            ptx::named_bar_sync(1, NUM_EPI_WARPS * 32);
             ptx::tcgen05_fence_after();
             const uint32_t taddr =
                 tmem_base + (static_cast<uint32_t>(lane_quarter * 32) << 16) + acc * BLOCK_N + col_half * 128;
