@@ -7,8 +7,9 @@ synthetic 224x224 frames, bf16 operands, forward only), one process per GPU.
 
 One step = one 256-frame batch through vidil_vit_forward.  Prints ONE JSON line on rank 0 with
   value     frames/s, inputs resident in HBM, CUDA events around exactly K steps, max over ranks
-  e2e       the same through the host-buffer call (VisionTransformer.encode_host -> vidil_vit_forward_host): pinned
-            host frames -> H2D -> forward -> D2H of the [B,197,1024] fp32 tokens, every step
+  e2e       the same through the host-buffer API (VisionTransformer.encode_host_stream -> vidil_encoder_host_submit/_wait):
+            pinned host frames -> H2D -> forward -> D2H of the [B,197,1024] fp32 tokens, every step, with step k+1's H2D
+            and step k-1's D2H overlapping step k's forward
   roofline  the tcgen05 GEMM kernel: algorithmic FLOPs / its event-timed device time inside the timed steps
   cpu_baseline  the oracle port of models/vit.py timed on this box's host cores (rank 0, N=1 only)
 Other workloads (not the driver's line): --workload clip | sim.
@@ -304,7 +305,12 @@ def run_vit(args):
                      "achieved": gemm_tflops, "peak": peaks["tflops_sustained"], "unit": "TFLOP/s",
                      "frac": gemm_tflops / peaks["tflops_sustained"], "frac_of_burst_peak": gemm_tflops / peaks["tflops"],
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
-                     "traffic": None, "share_of_step": g["ms"] / ms_total},
+                     # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the four per-layer GEMMs of one
+                     # `ncu --set full` capture of this build (profiles/r01c_summary.md: fc1 474, fc2 824, qkv 368,
+                     # proj 460 MB) — against 574 MB of algorithmic operand + output bytes per launch
+                     "traffic": 531.4e6 if (args.vit == "large" and B == 256 and args.image_size == 224) else None,
+                     "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1),
+                     "share_of_step": g["ms"] / ms_total},
         "whole_step": {"gflop_per_frame": gflop_frame, "tflops": fps / world * gflop_frame / 1e3,
                        "frac_of_sustained_peak": fps / world * gflop_frame / 1e3 / peaks["tflops_sustained"],
                        "frac_of_burst_peak": fps / world * gflop_frame / 1e3 / peaks["tflops"],

@@ -23,7 +23,7 @@ if [[ $what == all || $what == ncu ]]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:gemm_tcgen05 -s 120 -c 4 -f -o gpurun_out/prof_gemm \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_gemm.log 2>&1
   tail -2 gpurun_out/ncu_gemm.log
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_kernel -s 10 -c 1 -f -o gpurun_out/prof_attn \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:attention_tc -s 10 -c 1 -f -o gpurun_out/prof_attn \
       python bench.py --steps 1 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_attn.log 2>&1
   tail -2 gpurun_out/ncu_attn.log
 fi
