@@ -12,7 +12,7 @@ One step = one 256-frame batch through vidil_vit_forward.  Prints ONE JSON line 
             and step k-1's D2H overlapping step k's forward
   roofline  the tcgen05 GEMM kernel: algorithmic FLOPs / its event-timed device time inside the timed steps
   cpu_baseline  the oracle port of models/vit.py timed on this box's host cores (rank 0, N=1 only)
-Other workloads (not the driver's line): --workload clip | sim.
+Other workloads (not the driver's line): --workload clip | sim | text.
 """
 from __future__ import annotations
 
@@ -389,13 +389,47 @@ def run_clip(args):
                       "config": {"workload": f"CLIP ViT-L/14 @224 image tower, batch {args.batch}"}}), flush=True)
 
 
+def run_text(args):
+    """CLIP text tower (phrase bank) throughput: 512-phrase batches of 77 tokens (not the driver's line)."""
+    import torch
+
+    from oracle import weights as W
+    from vidil_b200.clip import CLIPTextB200
+    dev = torch.device("cuda", 0)
+    c = W.CLIP_TEXT_CONFIGS["large14"]
+    m = CLIPTextB200(**c, compute_dtype=args.dtype)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.normal_(0.0, 0.02)
+        for n, p in m.named_parameters():
+            if "norm" in n and n.endswith("weight"):
+                p.add_(1.0)
+    m = m.to(dev).eval()
+    ids = W.token_ids("large14", 512, 77, seed=0).to(dev)
+    for _ in range(args.warmup):
+        m(ids)
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        m(ids)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / args.steps
+    L, D, I = 77, 768, 3072
+    gf = 12 * (2 * L * D * 3 * D + 2 * L * D * D + 4 * L * D * I + 4 * L * L * D) / 1e9
+    print(json.dumps({"metric": "phrases/sec embedded (CLIP text tower)", "value": 512 / (ms / 1e3), "unit": "phrases/s",
+                      "ms_per_step": ms, "tflops": 512 / (ms / 1e3) * gf / 1e3,
+                      "config": {"workload": "CLIP ViT-L/14 text tower, 512 phrases x 77 tokens per step"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="vit", choices=["vit", "clip", "sim"])
+    ap.add_argument("--workload", default="vit", choices=["vit", "clip", "sim", "text"])
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--vit", default="large", choices=list(VIT))
     ap.add_argument("--image-size", type=int, default=224)
@@ -411,6 +445,8 @@ def main():
         return run_sim(args)
     if args.workload == "clip":
         return run_clip(args)
+    if args.workload == "text":
+        return run_text(args)
     return run_vit(args)
 
 

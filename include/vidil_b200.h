@@ -9,6 +9,7 @@
  *   run_visual_tokenization.py:141-142   CLIPModel(**inputs).image_embeds -> vidil_clip_forward
  *   run_visual_tokenization.py:276,306   image_embeds @ text_embeds.t(); np.argsort(...)[::-1][:k]
  *                                                                    -> vidil_sim_topk
+ *   run_visual_tokenization.py:84-96     CLIPModel(**inputs).text_embeds  -> vidil_clip_text_forward
  *
  * Conventions
  *   - Every function returns 0 on success, non-zero on failure; vidil_last_error() then returns a
@@ -115,6 +116,35 @@ size_t  vidil_encoder_host_pipeline_scratch_bytes(const vidil_encoder* enc, int3
 int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_host,
                                   int32_t slot, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 int32_t vidil_encoder_host_wait(vidil_encoder* enc, int32_t slot);
+
+/* ---- CLIP text tower (the phrase bank of run_visual_tokenization.py:84-96) ----------------------- */
+/* transformers' CLIPTextModel + text_projection + L2 normalisation.  Parameter names for vidil_text_encoder_load:
+ *   token_embedding [V*D]  position_embedding [P*D]  blocks.<i>.* as for the image towers (q,k,v fused into attn.qkv)
+ *   norm.weight|bias (final_layer_norm)  head.proj.weight [proj_dim*D] (text_projection).
+ * input_ids int32 [B, L] and eos_pos int32 [B] (the pooled position of each sequence: argmax of the ids for the
+ * legacy eos_token_id == 2 configs, else the first eos_token_id) are device pointers; out_embeds fp32 [B, proj_dim].
+ * Attention is causal; padding after the EOS token cannot influence the pooled row and needs no mask. */
+typedef struct vidil_text_cfg {
+    int32_t vocab_size;
+    int32_t max_positions; /* <= 208 */
+    int32_t embed_dim;     /* 64 * num_heads */
+    int32_t depth;
+    int32_t num_heads;
+    int32_t mlp_dim;
+    float   ln_eps;
+    int32_t act;           /* VIDIL_ACT_* */
+    int32_t proj_dim;
+    int32_t dtype;         /* VIDIL_DTYPE_* */
+    int32_t cta_group;     /* 0 = default (2) */
+} vidil_text_cfg;
+typedef struct vidil_text_encoder vidil_text_encoder;
+int32_t vidil_text_encoder_create(const vidil_text_cfg* cfg, vidil_text_encoder** out);
+void    vidil_text_encoder_destroy(vidil_text_encoder* enc);
+int32_t vidil_text_encoder_load(vidil_text_encoder* enc, const char* name, const float* dev_ptr, int64_t numel, void* stream);
+int32_t vidil_text_encoder_check_loaded(const vidil_text_encoder* enc);
+size_t  vidil_text_encoder_workspace_bytes(const vidil_text_encoder* enc, int32_t batch, int32_t seq_len);
+int32_t vidil_clip_text_forward(vidil_text_encoder* enc, const int32_t* input_ids, const int32_t* eos_pos, int32_t batch,
+                                int32_t seq_len, float* out_embeds, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- per-kernel-class device timing (bench.py's roofline figures) ---------------------------- */
 /* With profiling on, every kernel a forward enqueues is bracketed by CUDA events on the caller's stream.

@@ -15,6 +15,8 @@ stored):
   clip_tiny.npz           transformers.CLIPModel vision path (D=128, 2 layers), full outputs, 2 frames
   clip_large14.npz        transformers.CLIPModel ViT-L/14 @224, 1 frame: image_embeds + CLS/every 8th token of
                           last_hidden_state
+  clip_text_tiny.npz      transformers.CLIPModel text path (D=128, 2 layers, 12 tokens), 5 phrases: text_embeds + pooled
+  clip_text_large14.npz   transformers.CLIPModel text tower of clip-vit-large-patch14's shape, 3 phrases of 20 tokens
   tokenization.json       sim top-k indices computed with the reference's own lines (:276, :306), and
                           aggregate_frame_tokens executed from run_visual_tokenization.py:173-187
   sharding.json           per-rank slices from the reference's partition formula for several (n, world) pairs
@@ -90,6 +92,32 @@ def golden_clip(name, batch, token_stride, fname):
     _save(fname, tokens=tok, image_embeds=emb.numpy(), last_hidden=vout.last_hidden_state[:, tok].numpy())
 
 
+@torch.no_grad()
+def golden_clip_text(name, batch, seq_len, fname):
+    """transformers' CLIPModel text branch (get_text_features + normalisation, as CLIPModel.forward does)."""
+    from transformers import CLIPConfig, CLIPModel
+    c = W.CLIP_TEXT_CONFIGS[name]
+    text = dict(vocab_size=c["vocab_size"], max_position_embeddings=c["max_position_embeddings"], hidden_size=c["hidden_size"],
+                intermediate_size=c["intermediate_size"], num_hidden_layers=c["num_hidden_layers"],
+                num_attention_heads=c["num_attention_heads"], layer_norm_eps=1e-5, hidden_act="quick_gelu",
+                eos_token_id=c["eos_token_id"], bos_token_id=c["eos_token_id"] - 1, pad_token_id=c["eos_token_id"])
+    vision = dict(hidden_size=64, intermediate_size=128, num_hidden_layers=1, num_attention_heads=1, image_size=28, patch_size=14)
+    cfg = CLIPConfig(text_config=text, vision_config=vision, projection_dim=c["projection_dim"])
+    cfg._attn_implementation = "eager"
+    model = CLIPModel(cfg).eval()
+    missing, unexpected = model.load_state_dict(W.clip_text_state_dict(name, seed=0), strict=False)
+    assert not unexpected and all(k.startswith(("vision_model.", "visual_projection", "logit_scale")) for k in missing), missing
+    ids = W.token_ids(name, batch, seq_len, seed=0)
+    mask = torch.ones_like(ids)
+    for b in range(batch):                       # what the tokenizer would report: 1 up to and including the first EOS
+        e = int((ids[b] == c["eos_token_id"]).int().argmax())
+        mask[b, e + 1:] = 0
+    out = model.text_model(input_ids=ids, attention_mask=mask)
+    emb = model.text_projection(out.pooler_output)
+    emb = emb / emb.norm(p=2, dim=-1, keepdim=True)
+    _save(fname, text_embeds=emb.numpy(), pooled=out.pooler_output.numpy())
+
+
 def golden_tokenization():
     # similarity + per-frame argsort exactly as run_visual_tokenization.py:276,298-306
     F_, T, D, k = 64, 1000, 768, 5
@@ -145,6 +173,8 @@ def main():
     rs.uninstall_shims()
     golden_clip("tiny", 2, 1, "clip_tiny.npz")
     golden_clip("large14", 1, 8, "clip_large14.npz")
+    golden_clip_text("tiny", 5, 12, "clip_text_tiny.npz")
+    golden_clip_text("large14", 3, 20, "clip_text_large14.npz")
     golden_tokenization()
     golden_sharding()
 

@@ -118,6 +118,56 @@ def clip_vision_state_dict(name: str = "large14", seed: int = 0) -> dict:
     return sd
 
 
+# openai/clip-vit-large-patch14 text tower; "tiny" is a CPU-sized stand-in with the same structure.
+CLIP_TEXT_CONFIGS = {
+    "tiny": dict(vocab_size=96, max_position_embeddings=16, hidden_size=128, intermediate_size=512, num_hidden_layers=2,
+                 num_attention_heads=2, projection_dim=64, eos_token_id=95),
+    "large14": dict(vocab_size=49408, max_position_embeddings=77, hidden_size=768, intermediate_size=3072,
+                    num_hidden_layers=12, num_attention_heads=12, projection_dim=768, eos_token_id=49407),
+}
+
+
+def clip_text_state_dict(name: str = "large14", seed: int = 0) -> dict:
+    """Synthetic parameters under transformers' CLIPModel key names (text tower + text_projection)."""
+    c = CLIP_TEXT_CONFIGS[name]
+    D, I, L = c["hidden_size"], c["intermediate_size"], c["num_hidden_layers"]
+    rng = np.random.Generator(np.random.PCG64(3_000_017 + seed))
+    t = "text_model."
+    sd = {}
+    sd[t + "embeddings.token_embedding.weight"] = _normal(rng, (c["vocab_size"], D), 0.02)
+    sd[t + "embeddings.position_embedding.weight"] = _normal(rng, (c["max_position_embeddings"], D), 0.01)
+    for i in range(L):
+        p = f"{t}encoder.layers.{i}."
+        sd[p + "layer_norm1.weight"] = _normal(rng, (D,), 0.02, 1.0)
+        sd[p + "layer_norm1.bias"] = _normal(rng, (D,), 0.02)
+        for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+            sd[p + f"self_attn.{nm}.weight"] = _normal(rng, (D, D), 0.03)
+            sd[p + f"self_attn.{nm}.bias"] = _normal(rng, (D,), 0.02)
+        sd[p + "layer_norm2.weight"] = _normal(rng, (D,), 0.02, 1.0)
+        sd[p + "layer_norm2.bias"] = _normal(rng, (D,), 0.02)
+        sd[p + "mlp.fc1.weight"] = _normal(rng, (I, D), 0.03)
+        sd[p + "mlp.fc1.bias"] = _normal(rng, (I,), 0.02)
+        sd[p + "mlp.fc2.weight"] = _normal(rng, (D, I), 0.03)
+        sd[p + "mlp.fc2.bias"] = _normal(rng, (D,), 0.02)
+    sd[t + "final_layer_norm.weight"] = _normal(rng, (D,), 0.02, 1.0)
+    sd[t + "final_layer_norm.bias"] = _normal(rng, (D,), 0.02)
+    sd["text_projection.weight"] = _normal(rng, (c["projection_dim"], D), 0.03)
+    return sd
+
+
+def token_ids(name: str, batch: int, seq_len: int, seed: int = 0) -> torch.Tensor:
+    """Synthetic tokenised phrases: BOS, 1..seq_len-2 word ids, EOS, then padding (= EOS id, as CLIP's tokenizer pads)."""
+    c = CLIP_TEXT_CONFIGS[name]
+    rng = np.random.Generator(np.random.PCG64(4_000_037 + seed))
+    eos = c["eos_token_id"]
+    ids = np.full((batch, seq_len), eos, dtype=np.int64)
+    for b in range(batch):
+        n_words = int(rng.integers(1, seq_len - 1))
+        ids[b, 0] = eos - 1                                            # BOS is eos - 1 in CLIP's vocabulary
+        ids[b, 1:1 + n_words] = rng.integers(1, eos - 1, size=n_words)
+    return torch.from_numpy(ids)
+
+
 def frames(batch: int, image_size: int = 224, seed: int = 0) -> torch.Tensor:
     """Synthetic post-Normalize frames ~ N(0,1), fp32 NCHW."""
     rng = np.random.Generator(np.random.PCG64(1_000_003 + seed))

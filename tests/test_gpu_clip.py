@@ -6,9 +6,9 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import clip_oracle, tokenization_oracle, weights as W
+from oracle import clip_oracle, clip_text_oracle, tokenization_oracle, weights as W
 from vidil_b200 import visual_tokenization as vt
-from vidil_b200.clip import CLIPVisionB200, VidilCLIPModel
+from vidil_b200.clip import CLIPTextB200, CLIPVisionB200, VidilCLIPModel
 
 pytestmark = pytest.mark.gpu
 
@@ -59,6 +59,57 @@ def test_clip_host_call_and_batch_invariance(cuda):
     dev_out = m(x.to(cuda))
     assert torch.equal(m.encode_host(x.pin_memory()), dev_out.cpu())
     assert torch.equal(m(x[4:6].to(cuda)), dev_out[4:6])
+
+
+# ---- text tower (phrase bank) ------------------------------------------------------------------------------------------
+def _build_text(name, dtype, dev):
+    c = W.CLIP_TEXT_CONFIGS[name]
+    sd = W.clip_text_state_dict(name, seed=0)
+    m = CLIPTextB200(**c, compute_dtype=dtype)
+    m.load_state_dict(sd)
+    return m.to(dev).eval(), sd, c
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+@pytest.mark.parametrize("name,batch,seq,fname", [("tiny", 5, 12, "clip_text_tiny.npz"), ("large14", 3, 20, "clip_text_large14.npz")])
+def test_clip_text_vs_transformers_fixture(cuda, golden_dir, name, batch, seq, fname, dtype):
+    m, _, c = _build_text(name, dtype, cuda)
+    g = np.load(os.path.join(golden_dir, fname))
+    emb = m(W.token_ids(name, batch, seq, seed=0).to(cuda))
+    err = np.abs(emb.cpu().numpy() - g["text_embeds"]).max()
+    cos = (emb.cpu().numpy() * g["text_embeds"]).sum(axis=1).min()
+    print(f"CLIP text {name} {dtype}: text_embeds max-abs {err:.3e} min cosine {cos:.6f}")
+    scale = 4 if name == "tiny" else 1          # proj 64: components ~0.125 instead of ~0.036
+    assert err < EMB_TOL[dtype] * scale * 1.5 and cos > 0.9995
+    assert torch.allclose(emb.norm(dim=-1), torch.ones(batch, device=cuda), atol=1e-5)
+
+
+def test_clip_text_bank_batch_vs_oracle(cuda):
+    """A 512-phrase batch at the real tower's width (the reference's EMBBDING_BATCH_LIMIT_TEXT), full 77-token padding,
+    against the oracle on a sample of rows; rows are independent, so a row must not depend on its batch."""
+    m, sd, c = _build_text("large14", "fp16", cuda)
+    ids = W.token_ids("large14", 512, 77, seed=5)
+    emb = m(ids.to(cuda))
+    rows = [0, 17, 255, 511]
+    ref, _ = clip_text_oracle.clip_text_forward(sd, ids[rows], c["num_attention_heads"], c["eos_token_id"])
+    assert (emb[rows].cpu() - ref).abs().max() < 2e-3
+    assert torch.equal(m(ids[rows].to(cuda)), emb[rows])
+    with pytest.raises(ValueError):
+        m(torch.zeros(1, 78, dtype=torch.long, device=cuda))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(ids[:1])
+
+
+def test_clip_text_legacy_eos_pooling(cuda):
+    """eos_token_id == 2 configs pool at argmax(input_ids) (modeling_clip.py:564-574)."""
+    c = dict(W.CLIP_TEXT_CONFIGS["tiny"], eos_token_id=2)
+    sd = W.clip_text_state_dict("tiny", seed=0)
+    m = CLIPTextB200(**c, compute_dtype="fp16")
+    m.load_state_dict(sd)
+    m = m.to(cuda).eval()
+    ids = W.token_ids("tiny", 4, 10, seed=2)     # EOS id 95 is the largest id -> argmax = first EOS, same pooled row
+    ref, _ = clip_text_oracle.clip_text_forward(sd, ids, 2, eos_token_id=2)
+    assert (m(ids.to(cuda)).cpu() - ref).abs().max() < 6e-3
 
 
 # ---- predict_video: the reference's call surface end to end ----------------------------------------------------------

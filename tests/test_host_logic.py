@@ -74,6 +74,22 @@ def test_clip_state_dict_uses_transformers_names():
     assert torch.equal(names["blocks.1.attn.qkv.bias"][128:256], sd["vision_model.encoder.layers.1.self_attn.k_proj.bias"])
 
 
+def test_clip_text_state_dict_uses_transformers_names():
+    from vidil_b200.clip import CLIPTextB200
+    c = W.CLIP_TEXT_CONFIGS["tiny"]
+    m = CLIPTextB200(**c)
+    sd = W.clip_text_state_dict("tiny")
+    assert set(m.state_dict()) == set(sd)
+    m.load_state_dict(sd)
+    names = dict(m._packed_tensors())
+    assert tuple(names["token_embedding"].shape) == (c["vocab_size"], 128)
+    assert tuple(names["blocks.1.attn.qkv.weight"].shape) == (384, 128)
+    ids = torch.tensor([[94, 5, 7, 95, 95], [94, 9, 95, 95, 95]])
+    assert m.eos_positions(ids).tolist() == [3, 2]
+    with pytest.raises(RuntimeError, match="CUDA"):
+        m(ids)
+
+
 def test_aggregate_matches_fixture(golden_dir):
     g = json.load(open(os.path.join(golden_dir, "tokenization.json")))
     for case in g["aggregate_cases"]:

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import clip_oracle, tokenization_oracle, vit_oracle, weights as W
+from oracle import clip_oracle, clip_text_oracle, tokenization_oracle, vit_oracle, weights as W
 
 # Same ATen ops in the same order as the reference => equal up to thread-count-dependent reduction order.
 TOL = 2e-4
@@ -53,6 +53,18 @@ def test_clip_oracle_matches_transformers_fixture(golden_dir, name, batch, fname
     assert np.abs(emb.numpy() - g["image_embeds"]).max() < 1e-5
     ref = g["last_hidden"]
     assert np.abs(hidden[:, g["tokens"]].numpy() - ref).max() < TOL * max(1.0, np.abs(ref).max())
+    assert np.allclose(np.linalg.norm(emb.numpy(), axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.parametrize("name,batch,seq,fname", [("tiny", 5, 12, "clip_text_tiny.npz"), ("large14", 3, 20, "clip_text_large14.npz")])
+def test_clip_text_oracle_matches_transformers_fixture(golden_dir, name, batch, seq, fname):
+    """The fixture was produced WITH the tokenizer-style attention_mask; the oracle applies the causal mask only —
+    padding after the EOS token cannot reach the pooled EOS row."""
+    g = _load(golden_dir, fname)
+    c = W.CLIP_TEXT_CONFIGS[name]
+    emb, _ = clip_text_oracle.clip_text_forward(W.clip_text_state_dict(name, seed=0), W.token_ids(name, batch, seq, seed=0),
+                                                c["num_attention_heads"], c["eos_token_id"])
+    assert np.abs(emb.numpy() - g["text_embeds"]).max() < 1e-5
     assert np.allclose(np.linalg.norm(emb.numpy(), axis=1), 1.0, atol=1e-5)
 
 

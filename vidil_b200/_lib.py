@@ -49,6 +49,14 @@ class KernelStats(ctypes.Structure):
                 ("launches", c_int64 * 4)]
 
 
+class TextCfg(ctypes.Structure):
+    """Mirror of `vidil_text_cfg`."""
+
+    _fields_ = [("vocab_size", c_int32), ("max_positions", c_int32), ("embed_dim", c_int32), ("depth", c_int32),
+                ("num_heads", c_int32), ("mlp_dim", c_int32), ("ln_eps", c_float), ("act", c_int32), ("proj_dim", c_int32),
+                ("dtype", c_int32), ("cta_group", c_int32)]
+
+
 # name -> (restype, argtypes); the single source of truth the symbol test checks against the header
 SIGNATURES = {
     "vidil_abi_version": (c_int32, []),
@@ -62,6 +70,13 @@ SIGNATURES = {
     "vidil_encoder_tokens": (c_int32, [c_void_p]),
     "vidil_vit_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_clip_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vidil_text_encoder_create": (c_int32, [POINTER(TextCfg), POINTER(c_void_p)]),
+    "vidil_text_encoder_destroy": (None, [c_void_p]),
+    "vidil_text_encoder_load": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+    "vidil_text_encoder_check_loaded": (c_int32, [c_void_p]),
+    "vidil_text_encoder_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
+    "vidil_clip_text_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
+                                          c_void_p]),
     "vidil_encoder_set_profiling": (c_int32, [c_void_p, c_int32]),
     "vidil_encoder_read_profile": (c_int32, [c_void_p, POINTER(KernelStats)]),
     "vidil_encoder_host_scratch_bytes": (c_size_t, [c_void_p, c_int32]),

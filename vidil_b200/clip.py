@@ -3,9 +3,9 @@
 The reference builds `transformers.CLIPModel` (:347-350) and calls `model(**processor_out)`, reading
 `.image_embeds` for frames (:138-142) and `.text_embeds` for the ontology phrases (:88-92).
 `CLIPVisionB200` runs the vision tower, visual_projection and L2 normalisation natively
-(vidil_clip_forward); `VidilCLIPModel` wraps an existing CLIPModel so that the same `model(**inputs)` call
-returns native `image_embeds` while the text tower (SURVEY.md §8f "next" #3, once per run, not the per-frame
-hot path) is still evaluated by the wrapped model.
+(vidil_clip_forward), `CLIPTextB200` the text tower, text_projection and normalisation (vidil_clip_text_forward,
+SURVEY.md §8f "next" #3); `VidilCLIPModel` wraps an existing CLIPModel so that the same `model(**inputs)` call
+returns native `image_embeds` / `text_embeds`.
 """
 from __future__ import annotations
 
@@ -192,21 +192,195 @@ class CLIPVisionB200(nn.Module):
         return out
 
 
+class CLIPTextB200(nn.Module):
+    """CLIP text tower + text_projection on the native path (vidil_clip_text_forward).  Parameters use transformers'
+    CLIPModel key names (`text_model.*`, `text_projection.weight`)."""
+
+    def __init__(self, vocab_size=49408, max_position_embeddings=77, hidden_size=768, intermediate_size=3072,
+                 num_hidden_layers=12, num_attention_heads=12, projection_dim=768, layer_norm_eps=1e-5,
+                 hidden_act="quick_gelu", eos_token_id=49407, compute_dtype="bf16", cta_group=0):
+        super().__init__()
+        if hidden_size != 64 * num_attention_heads:
+            raise ValueError("head_dim must be 64")
+        if hidden_act not in ("quick_gelu", "gelu"):
+            raise ValueError(f"unsupported hidden_act {hidden_act!r}")
+        self.cfg = dict(vocab_size=vocab_size, max_position_embeddings=max_position_embeddings, hidden_size=hidden_size,
+                        intermediate_size=intermediate_size, num_hidden_layers=num_hidden_layers,
+                        num_attention_heads=num_attention_heads, projection_dim=projection_dim,
+                        layer_norm_eps=layer_norm_eps, hidden_act=hidden_act, eos_token_id=eos_token_id)
+        self.compute_dtype, self.cta_group = compute_dtype, cta_group
+        D, I = hidden_size, intermediate_size
+
+        def p(*shape):
+            return nn.Parameter(torch.zeros(*shape))
+
+        t = "text_model."
+        params = {
+            t + "embeddings.token_embedding.weight": p(vocab_size, D),
+            t + "embeddings.position_embedding.weight": p(max_position_embeddings, D),
+            t + "final_layer_norm.weight": p(D), t + "final_layer_norm.bias": p(D),
+            "text_projection.weight": p(projection_dim, D),
+        }
+        for i in range(num_hidden_layers):
+            pre = f"{t}encoder.layers.{i}."
+            for ln in ("layer_norm1", "layer_norm2"):
+                params[pre + ln + ".weight"], params[pre + ln + ".bias"] = p(D), p(D)
+            for nm in ("q_proj", "k_proj", "v_proj", "out_proj"):
+                params[pre + f"self_attn.{nm}.weight"], params[pre + f"self_attn.{nm}.bias"] = p(D, D), p(D)
+            params[pre + "mlp.fc1.weight"], params[pre + "mlp.fc1.bias"] = p(I, D), p(I)
+            params[pre + "mlp.fc2.weight"], params[pre + "mlp.fc2.bias"] = p(D, I), p(D)
+        self._names = list(params)
+        for name, prm in params.items():
+            self.register_parameter(name.replace(".", "__"), prm)
+        self._handle = None
+        self._packed_sig = None
+        self._ws = None
+
+    def __del__(self):
+        try:
+            if self._handle:
+                _lib.load().vidil_text_encoder_destroy(self._handle)
+                self._handle = None
+        except Exception:  # noqa: BLE001 - interpreter teardown
+            pass
+
+    def state_dict(self, *args, **kwargs):
+        sd = super().state_dict(*args, **kwargs)
+        return {k.replace("__", "."): v for k, v in sd.items()}
+
+    def load_state_dict(self, state_dict, strict=True, assign=False):
+        own = {n: getattr(self, n.replace(".", "__")) for n in self._names}
+        missing = [n for n in own if n not in state_dict]
+        unexpected = [k for k in state_dict if k not in own]
+        if strict and (missing or unexpected):
+            raise RuntimeError(f"missing keys {missing[:4]}..., unexpected keys {unexpected[:4]}...")
+        with torch.no_grad():
+            for n, prm in own.items():
+                if n in state_dict:
+                    prm.copy_(state_dict[n])
+        return SimpleNamespace(missing_keys=missing, unexpected_keys=unexpected)
+
+    @classmethod
+    def from_hf(cls, hf_model, compute_dtype="bf16", cta_group=0):
+        tc = hf_model.config.text_config if hasattr(hf_model.config, "text_config") else hf_model.config
+        m = cls(vocab_size=tc.vocab_size, max_position_embeddings=tc.max_position_embeddings, hidden_size=tc.hidden_size,
+                intermediate_size=tc.intermediate_size, num_hidden_layers=tc.num_hidden_layers,
+                num_attention_heads=tc.num_attention_heads,
+                projection_dim=getattr(hf_model.config, "projection_dim", tc.projection_dim),
+                layer_norm_eps=tc.layer_norm_eps, hidden_act=tc.hidden_act, eos_token_id=tc.eos_token_id,
+                compute_dtype=compute_dtype, cta_group=cta_group)
+        m.load_state_dict(hf_model.state_dict(), strict=False)
+        dev = next(hf_model.parameters()).device
+        return m.to(dev).eval()
+
+    def _packed_tensors(self):
+        g = lambda n: getattr(self, n.replace(".", "__"))  # noqa: E731
+        t = "text_model."
+        yield "token_embedding", g(t + "embeddings.token_embedding.weight")
+        yield "position_embedding", g(t + "embeddings.position_embedding.weight")
+        for i in range(self.cfg["num_hidden_layers"]):
+            s, d = f"{t}encoder.layers.{i}.", f"blocks.{i}."
+            yield d + "norm1.weight", g(s + "layer_norm1.weight")
+            yield d + "norm1.bias", g(s + "layer_norm1.bias")
+            yield d + "attn.qkv.weight", torch.cat([g(s + f"self_attn.{n}.weight") for n in ("q_proj", "k_proj", "v_proj")])
+            yield d + "attn.qkv.bias", torch.cat([g(s + f"self_attn.{n}.bias") for n in ("q_proj", "k_proj", "v_proj")])
+            yield d + "attn.proj.weight", g(s + "self_attn.out_proj.weight")
+            yield d + "attn.proj.bias", g(s + "self_attn.out_proj.bias")
+            yield d + "norm2.weight", g(s + "layer_norm2.weight")
+            yield d + "norm2.bias", g(s + "layer_norm2.bias")
+            for fc in ("fc1", "fc2"):
+                yield d + f"mlp.{fc}.weight", g(s + f"mlp.{fc}.weight")
+                yield d + f"mlp.{fc}.bias", g(s + f"mlp.{fc}.bias")
+        yield "norm.weight", g(t + "final_layer_norm.weight")
+        yield "norm.bias", g(t + "final_layer_norm.bias")
+        yield "head.proj.weight", g("text_projection.weight")
+
+    def _ensure_packed(self):
+        import ctypes
+        lib = _lib.load()
+        c = self.cfg
+        sig = tuple((p.data_ptr(), p._version) for p in self.parameters())
+        if self._handle is None:
+            cfg = _lib.TextCfg(vocab_size=c["vocab_size"], max_positions=c["max_position_embeddings"], embed_dim=c["hidden_size"],
+                               depth=c["num_hidden_layers"], num_heads=c["num_attention_heads"], mlp_dim=c["intermediate_size"],
+                               ln_eps=c["layer_norm_eps"],
+                               act=_lib.ACT_QUICK_GELU if c["hidden_act"] == "quick_gelu" else _lib.ACT_GELU_ERF,
+                               proj_dim=c["projection_dim"], dtype=_lib.DTYPES[self.compute_dtype], cta_group=self.cta_group)
+            h = ctypes.c_void_p()
+            _lib.check(lib.vidil_text_encoder_create(ctypes.byref(cfg), ctypes.byref(h)), "vidil_text_encoder_create")
+            self._handle = h
+            self._packed_sig = None
+        if sig != self._packed_sig:
+            st = torch.cuda.current_stream().cuda_stream
+            with torch.no_grad():
+                for name, t in self._packed_tensors():
+                    t = t.detach().float().contiguous()
+                    if not t.is_cuda:
+                        raise RuntimeError("vidil_b200: parameters must live on a CUDA device (no CPU path exists)")
+                    _lib.check(lib.vidil_text_encoder_load(self._handle, name.encode(), t.data_ptr(), t.numel(), st),
+                               f"vidil_text_encoder_load({name})")
+            _lib.check(lib.vidil_text_encoder_check_loaded(self._handle), "vidil_text_encoder_check_loaded")
+            self._packed_sig = sig
+        return lib
+
+    def eos_positions(self, input_ids: torch.Tensor) -> torch.Tensor:
+        """The pooled position of each sequence, as CLIPTextTransformer.forward picks it (modeling_clip.py:564-585):
+        argmax of the ids for legacy configs with eos_token_id == 2, otherwise the first eos_token_id."""
+        if self.cfg["eos_token_id"] == 2:
+            return input_ids.to(torch.int).argmax(dim=-1).to(torch.int32)
+        return (input_ids.to(torch.int) == self.cfg["eos_token_id"]).int().argmax(dim=-1).to(torch.int32)
+
+    @torch.no_grad()
+    def forward(self, input_ids: torch.Tensor, attention_mask: torch.Tensor | None = None) -> torch.Tensor:
+        """input_ids [B, L] (CUDA, integer) -> text_embeds [B, projection_dim] fp32, unit L2 norm.  attention_mask is
+        accepted and ignored: under the causal mask, padding after the EOS token cannot reach the pooled EOS row."""
+        if not input_ids.is_cuda:
+            raise RuntimeError("vidil_b200: input_ids must be on a CUDA device (no CPU path exists)")
+        if input_ids.dim() != 2:
+            raise RuntimeError(f"expected input_ids of shape [B, L], got {tuple(input_ids.shape)}")
+        B, L = input_ids.shape
+        c = self.cfg
+        if L > c["max_position_embeddings"]:
+            raise ValueError(f"Sequence length must be less than max_position_embeddings (got {L} and {c['max_position_embeddings']})")
+        out = torch.empty(B, c["projection_dim"], dtype=torch.float32, device=input_ids.device)
+        if B == 0:
+            return out
+        with torch.cuda.device(input_ids.device):
+            lib = self._ensure_packed()
+            ids = input_ids.to(torch.int32).contiguous()
+            eos = self.eos_positions(input_ids).contiguous()
+            need = lib.vidil_text_encoder_workspace_bytes(self._handle, B, L)
+            if self._ws is None or self._ws.numel() < need or self._ws.device != ids.device:
+                self._ws = NativeEncoder._aligned(need, ids.device)
+            st = lib.vidil_clip_text_forward(self._handle, ids.data_ptr(), eos.data_ptr(), B, L, out.data_ptr(),
+                                             self._ws.data_ptr(), self._ws.numel(), torch.cuda.current_stream().cuda_stream)
+            _lib.check(st, "vidil_clip_text_forward")
+        return out
+
+
 class VidilCLIPModel(nn.Module):
     """`model(**inputs)` replacement for the CLIPModel the reference builds (run_visual_tokenization.py:347):
     same keyword inputs, returns an object with `.image_embeds` / `.text_embeds` (the two fields the script reads)."""
 
-    def __init__(self, hf_model, compute_dtype="bf16"):
+    def __init__(self, hf_model, compute_dtype="bf16", native_text=True):
         super().__init__()
         self.hf = hf_model
         self.vision = CLIPVisionB200.from_hf(hf_model, compute_dtype=compute_dtype)
+        tc = hf_model.config.text_config
+        # the native text tower covers CLIP's shapes (head_dim 64, <= 208 positions); anything else stays on transformers
+        self.text = (CLIPTextB200.from_hf(hf_model, compute_dtype=compute_dtype)
+                     if native_text and tc.hidden_size == 64 * tc.num_attention_heads and tc.hidden_size % 128 == 0
+                     and tc.max_position_embeddings <= 208 else None)
 
     @torch.no_grad()
     def forward(self, input_ids=None, pixel_values=None, attention_mask=None, **_unused):
         image_embeds = self.vision(pixel_values) if pixel_values is not None else None
         text_embeds = None
         if input_ids is not None:
-            t = self.hf.text_model(input_ids=input_ids, attention_mask=attention_mask).pooler_output
-            t = self.hf.text_projection(t)
-            text_embeds = t / t.norm(p=2, dim=-1, keepdim=True)
+            if self.text is not None:
+                text_embeds = self.text(input_ids, attention_mask)
+            else:
+                t = self.hf.text_model(input_ids=input_ids, attention_mask=attention_mask).pooler_output
+                t = self.hf.text_projection(t)
+                text_embeds = t / t.norm(p=2, dim=-1, keepdim=True)
         return SimpleNamespace(image_embeds=image_embeds, text_embeds=text_embeds)

@@ -928,3 +928,273 @@ int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, i
 }
 
 }  // extern "C"
+
+// =====================================================================================================================
+// CLIP text tower (run_visual_tokenization.py:84-96 get_text_embeddings_clip; arithmetic in transformers'
+// CLIPTextTransformer): token + position embedding -> depth x [LN -> q,k,v -> causal attention -> out -> +res -> LN ->
+// fc1 -> quick_gelu -> fc2 -> +res] -> final LN on the EOS row -> bias-free projection -> L2 normalise.
+// Same kernels as the image towers; the attention runs with a causal mask and one 128-row tile per (sequence, head).
+// =====================================================================================================================
+struct vidil_text_encoder {
+    vidil_text_cfg cfg;
+    DType dt = DT_BF16;
+    DevBuf tok, pos, norm_w, norm_b, head_w;
+    std::vector<std::unique_ptr<Layer>> layers;
+};
+
+namespace {
+
+struct TextWs {
+    size_t resid, xn, qkv, attn, hidden, pooled, pooled_ln, head_out, total;
+};
+
+TextWs text_ws(const vidil_text_encoder* e, int B, int L) {
+    const size_t M = static_cast<size_t>(B) * L, D = e->cfg.embed_dim;
+    TextWs w;
+    size_t off = 0;
+    w.resid = off;     off += align_up(M * D * 4);
+    w.xn = off;        off += align_up(M * D * 2);
+    w.qkv = off;       off += align_up(M * 3 * D * 2);
+    w.attn = off;      off += align_up(M * D * 2);
+    w.hidden = off;    off += align_up(M * e->cfg.mlp_dim * 2);
+    w.pooled = off;    off += align_up(static_cast<size_t>(B) * D * 4);
+    w.pooled_ln = off; off += align_up(static_cast<size_t>(B) * D * 2);
+    w.head_out = off;  off += align_up(static_cast<size_t>(B) * e->cfg.proj_dim * 4);
+    w.total = off;
+    return w;
+}
+
+bool text_slot(vidil_text_encoder* e, const char* name, Slot& s) {
+    const vidil_text_cfg& c = e->cfg;
+    const int D = c.embed_dim, H = c.mlp_dim;
+    auto vec = [&](DevBuf& b, int64_t n) { s = Slot{&b, n, false, 0, 0, 0}; return true; };
+    auto mat = [&](DevBuf& b, int r, int k, int ld) { s = Slot{&b, static_cast<int64_t>(r) * k, true, r, k, ld}; return true; };
+    if (!strcmp(name, "token_embedding")) return vec(e->tok, static_cast<int64_t>(c.vocab_size) * D);
+    if (!strcmp(name, "position_embedding")) return vec(e->pos, static_cast<int64_t>(c.max_positions) * D);
+    if (!strcmp(name, "norm.weight")) return vec(e->norm_w, D);
+    if (!strcmp(name, "norm.bias")) return vec(e->norm_b, D);
+    if (!strcmp(name, "head.proj.weight")) return mat(e->head_w, c.proj_dim, D, D);
+    int idx = -1, consumed = 0;
+    if (sscanf(name, "blocks.%d.%n", &idx, &consumed) == 1 && consumed > 0 && idx >= 0 && idx < c.depth) {
+        const char* r = name + consumed;
+        Layer& ly = *e->layers[idx];
+        if (!strcmp(r, "norm1.weight")) return vec(ly.ln1_w, D);
+        if (!strcmp(r, "norm1.bias")) return vec(ly.ln1_b, D);
+        if (!strcmp(r, "attn.qkv.weight")) return mat(ly.qkv_w, 3 * D, D, D);
+        if (!strcmp(r, "attn.qkv.bias")) return vec(ly.qkv_b, 3 * D);
+        if (!strcmp(r, "attn.proj.weight")) return mat(ly.proj_w, D, D, D);
+        if (!strcmp(r, "attn.proj.bias")) return vec(ly.proj_b, D);
+        if (!strcmp(r, "norm2.weight")) return vec(ly.ln2_w, D);
+        if (!strcmp(r, "norm2.bias")) return vec(ly.ln2_b, D);
+        if (!strcmp(r, "mlp.fc1.weight")) return mat(ly.fc1_w, H, D, D);
+        if (!strcmp(r, "mlp.fc1.bias")) return vec(ly.fc1_b, H);
+        if (!strcmp(r, "mlp.fc2.weight")) return mat(ly.fc2_w, D, H, H);
+        if (!strcmp(r, "mlp.fc2.bias")) return vec(ly.fc2_b, D);
+    }
+    return false;
+}
+
+void text_params(const vidil_text_encoder* e, std::vector<NamedBuf>& out) {
+    out.push_back({"token_embedding", &e->tok});
+    out.push_back({"position_embedding", &e->pos});
+    for (int i = 0; i < e->cfg.depth; ++i) {
+        const Layer& ly = *e->layers[i];
+        const std::string p = "blocks." + std::to_string(i) + ".";
+        out.push_back({p + "norm1.weight", &ly.ln1_w});
+        out.push_back({p + "norm1.bias", &ly.ln1_b});
+        out.push_back({p + "attn.qkv.weight", &ly.qkv_w});
+        out.push_back({p + "attn.qkv.bias", &ly.qkv_b});
+        out.push_back({p + "attn.proj.weight", &ly.proj_w});
+        out.push_back({p + "attn.proj.bias", &ly.proj_b});
+        out.push_back({p + "norm2.weight", &ly.ln2_w});
+        out.push_back({p + "norm2.bias", &ly.ln2_b});
+        out.push_back({p + "mlp.fc1.weight", &ly.fc1_w});
+        out.push_back({p + "mlp.fc1.bias", &ly.fc1_b});
+        out.push_back({p + "mlp.fc2.weight", &ly.fc2_w});
+        out.push_back({p + "mlp.fc2.bias", &ly.fc2_b});
+    }
+    out.push_back({"norm.weight", &e->norm_w});
+    out.push_back({"norm.bias", &e->norm_b});
+    out.push_back({"head.proj.weight", &e->head_w});
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t vidil_text_encoder_create(const vidil_text_cfg* cfg, vidil_text_encoder** out) {
+    if (cfg == nullptr || out == nullptr) {
+        set_error("vidil_text_encoder_create: null argument");
+        return 1;
+    }
+    *out = nullptr;
+    vidil_text_cfg c = *cfg;
+    if (c.cta_group == 0) c.cta_group = 2;
+    if (c.vocab_size <= 0 || c.max_positions <= 0 || c.max_positions > 208) {
+        set_error("unsupported text geometry: vocab_size=%d max_positions=%d (sequences of at most 208 tokens)", c.vocab_size,
+                  c.max_positions);
+        return 1;
+    }
+    if (c.embed_dim <= 0 || c.embed_dim % 128 != 0 || c.num_heads * 64 != c.embed_dim ||
+        (c.embed_dim != 128 && c.embed_dim != 256 && c.embed_dim != 512 && c.embed_dim != 768 && c.embed_dim != 1024 &&
+         c.embed_dim != 1280)) {
+        set_error("unsupported width: embed_dim=%d num_heads=%d (head_dim must be 64; LayerNorm covers 128/256/512/768/1024/1280)",
+                  c.embed_dim, c.num_heads);
+        return 1;
+    }
+    if (c.depth <= 0 || c.mlp_dim <= 0 || c.mlp_dim % 64 != 0 || c.proj_dim <= 0 || c.proj_dim % 4 != 0) {
+        set_error("unsupported depth=%d / mlp_dim=%d / proj_dim=%d", c.depth, c.mlp_dim, c.proj_dim);
+        return 1;
+    }
+    if ((c.dtype != VIDIL_DTYPE_BF16 && c.dtype != VIDIL_DTYPE_FP16) || (c.act != VIDIL_ACT_GELU_ERF && c.act != VIDIL_ACT_QUICK_GELU) ||
+        (c.cta_group != 1 && c.cta_group != 2)) {
+        set_error("unsupported dtype %d / activation %d / cta_group %d", c.dtype, c.act, c.cta_group);
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    std::unique_ptr<vidil_text_encoder> e(new vidil_text_encoder());
+    e->cfg = c;
+    e->dt = (c.dtype == VIDIL_DTYPE_BF16) ? DT_BF16 : DT_FP16;
+    for (int i = 0; i < c.depth; ++i) e->layers.emplace_back(new Layer());
+    std::vector<NamedBuf> names;
+    text_params(e.get(), names);
+    for (auto& nb : names) {
+        Slot s;
+        if (!text_slot(e.get(), nb.name.c_str(), s)) {
+            set_error("internal: no slot for %s", nb.name.c_str());
+            return 1;
+        }
+        const size_t bytes = s.matrix ? static_cast<size_t>(s.rows) * s.ld * 2 : static_cast<size_t>(s.numel) * 4;
+        if (s.buf->alloc(bytes)) return 1;
+    }
+    *out = e.release();
+    return 0;
+}
+
+void vidil_text_encoder_destroy(vidil_text_encoder* enc) { delete enc; }
+
+int32_t vidil_text_encoder_load(vidil_text_encoder* enc, const char* name, const float* dev_ptr, int64_t numel, void* stream) {
+    if (enc == nullptr || name == nullptr || dev_ptr == nullptr) {
+        set_error("vidil_text_encoder_load: null argument");
+        return 1;
+    }
+    Slot s;
+    if (!text_slot(enc, name, s)) {
+        set_error("vidil_text_encoder_load: unknown parameter '%s'", name);
+        return 1;
+    }
+    if (numel != s.numel) {
+        set_error("vidil_text_encoder_load: '%s' has %lld elements, expected %lld", name, (long long)numel, (long long)s.numel);
+        return 1;
+    }
+    cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+    if (s.matrix) {
+        if (cast_run(dev_ptr, s.buf->p, enc->dt, s.rows, s.cols, s.ld, st)) return 1;
+    } else {
+        VIDIL_CUDA_OK(cudaMemcpyAsync(s.buf->p, dev_ptr, static_cast<size_t>(numel) * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    s.buf->loaded = true;
+    return 0;
+}
+
+int32_t vidil_text_encoder_check_loaded(const vidil_text_encoder* enc) {
+    if (enc == nullptr) {
+        set_error("null encoder");
+        return 1;
+    }
+    std::vector<NamedBuf> names;
+    text_params(enc, names);
+    for (auto& nb : names)
+        if (!nb.buf->loaded) {
+            set_error("parameter '%s' has not been loaded", nb.name.c_str());
+            return 1;
+        }
+    return 0;
+}
+
+size_t vidil_text_encoder_workspace_bytes(const vidil_text_encoder* enc, int32_t batch, int32_t seq_len) {
+    if (enc == nullptr || batch <= 0 || seq_len <= 0) return 0;
+    return text_ws(enc, batch, seq_len).total;
+}
+
+int32_t vidil_clip_text_forward(vidil_text_encoder* enc, const int32_t* input_ids, const int32_t* eos_pos, int32_t batch,
+                                int32_t seq_len, float* out_embeds, void* workspace, size_t workspace_bytes, void* stream) {
+    if (enc == nullptr || input_ids == nullptr || eos_pos == nullptr || out_embeds == nullptr || workspace == nullptr) {
+        set_error("vidil_clip_text_forward: null argument");
+        return 1;
+    }
+    const vidil_text_cfg& c = enc->cfg;
+    if (batch <= 0 || seq_len <= 0 || seq_len > c.max_positions) {
+        set_error("vidil_clip_text_forward: batch=%d seq_len=%d (max_positions %d)", batch, seq_len, c.max_positions);
+        return 1;
+    }
+    if (vidil_text_encoder_check_loaded(enc)) return 1;
+    const TextWs L = text_ws(enc, batch, seq_len);
+    if (workspace_bytes < L.total || (reinterpret_cast<uintptr_t>(workspace) & (ALIGN - 1))) {
+        set_error("vidil_clip_text_forward: workspace too small (%zu < %zu) or not %zu-byte aligned", workspace_bytes, L.total, ALIGN);
+        return 1;
+    }
+    if (gemm_num_sms() == 0) return 1;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
+    float* resid = reinterpret_cast<float*>(base + L.resid);
+    void* xn = base + L.xn;
+    void* qkv = base + L.qkv;
+    void* attn = base + L.attn;
+    void* hidden = base + L.hidden;
+    float* pooled = reinterpret_cast<float*>(base + L.pooled);
+    void* pooled_ln = base + L.pooled_ln;
+    float* head_out = reinterpret_cast<float*>(base + L.head_out);
+    const int M = batch * seq_len, D = c.embed_dim;
+
+    if (embed_tokens_run(input_ids, reinterpret_cast<const float*>(enc->tok.p), reinterpret_cast<const float*>(enc->pos.p), resid, M,
+                         seq_len, D, c.vocab_size, s))
+        return 1;
+    AttentionMaps maps;
+    if (attention_tc_prepare(maps, qkv, attn, enc->dt, batch, seq_len, c.num_heads)) return 1;
+    maps.causal = true;
+    GemmProblem g;
+    g.dt = enc->dt;
+    g.cta_group = c.cta_group;
+    for (int i = 0; i < c.depth; ++i) {
+        Layer& ly = *enc->layers[i];
+        if (layernorm_run(resid, D, reinterpret_cast<const float*>(ly.ln1_w.p), reinterpret_cast<const float*>(ly.ln1_b.p), xn, false,
+                          enc->dt, M, D, c.ln_eps, s))
+            return 1;
+        GemmProblem q = g;
+        q.epi = EPI_STORE; q.M = M; q.N = 3 * D; q.K = D; q.A = xn; q.lda = D; q.W = ly.qkv_w.p; q.ldw = D;
+        q.bias = reinterpret_cast<const float*>(ly.qkv_b.p); q.out = qkv; q.ldo = 3 * D;
+        if (gemm_prepare(q) || gemm_run(q, s)) return 1;
+        if (attention_tc_run(maps, 0.125f, s)) return 1;
+        GemmProblem p = g;
+        p.epi = EPI_RESID; p.M = M; p.N = D; p.K = D; p.A = attn; p.lda = D; p.W = ly.proj_w.p; p.ldw = D;
+        p.bias = reinterpret_cast<const float*>(ly.proj_b.p); p.out = resid; p.ldo = D;
+        if (gemm_prepare(p) || gemm_run(p, s)) return 1;
+        if (layernorm_run(resid, D, reinterpret_cast<const float*>(ly.ln2_w.p), reinterpret_cast<const float*>(ly.ln2_b.p), xn, false,
+                          enc->dt, M, D, c.ln_eps, s))
+            return 1;
+        GemmProblem f1 = g;
+        f1.epi = (c.act == VIDIL_ACT_QUICK_GELU) ? EPI_QUICKGELU : EPI_GELU; f1.M = M; f1.N = c.mlp_dim; f1.K = D; f1.A = xn; f1.lda = D;
+        f1.W = ly.fc1_w.p; f1.ldw = D; f1.bias = reinterpret_cast<const float*>(ly.fc1_b.p); f1.out = hidden; f1.ldo = c.mlp_dim;
+        if (gemm_prepare(f1) || gemm_run(f1, s)) return 1;
+        GemmProblem f2 = g;
+        f2.epi = EPI_RESID; f2.M = M; f2.N = D; f2.K = c.mlp_dim; f2.A = hidden; f2.lda = c.mlp_dim; f2.W = ly.fc2_w.p; f2.ldw = c.mlp_dim;
+        f2.bias = reinterpret_cast<const float*>(ly.fc2_b.p); f2.out = resid; f2.ldo = D;
+        if (gemm_prepare(f2) || gemm_run(f2, s)) return 1;
+    }
+    // pooled_output = final_layer_norm(hidden)[b, eos_pos[b]]: LayerNorm is per row, so gather first
+    if (gather_rows_run(resid, eos_pos, pooled, batch, seq_len, D, s)) return 1;
+    if (layernorm_run(pooled, D, reinterpret_cast<const float*>(enc->norm_w.p), reinterpret_cast<const float*>(enc->norm_b.p), pooled_ln,
+                      false, enc->dt, batch, D, c.ln_eps, s))
+        return 1;
+    GemmProblem h = g;
+    h.epi = EPI_STORE_F32; h.M = batch; h.N = c.proj_dim; h.K = D; h.A = pooled_ln; h.lda = D; h.W = enc->head_w.p; h.ldw = D;
+    h.bias = nullptr; h.out = head_out; h.ldo = c.proj_dim;
+    if (gemm_prepare(h) || gemm_run(h, s)) return 1;
+    return l2norm_run(head_out, out_embeds, batch, c.proj_dim, s);
+}
+
+}  // extern "C"

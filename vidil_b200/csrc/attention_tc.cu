@@ -119,7 +119,7 @@ template <typename T>
 __global__ void __launch_bounds__(ATC_THREADS, 1)
     attention_tc_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                         const __grid_constant__ CUtensorMap map_out, int n_items, int N, int H, float scale_log2e,
-                        long long* trace) {
+                        long long* trace, int causal) {
     // Developer timeline (vidil_debug_set_trace): CTA 0 stamps clock64 at its synchronisation points for 16 items.
 #define ATC_TRACE(role, ev)                                                                    \
     do {                                                                                       \
@@ -271,6 +271,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             ++n;
             const int b = item / H, h = item - b * H;
             const bool warp_valid = (t * QT + quarter * 32) < N;
+            // keys this query row may see: all N, or 0..row under a causal mask (padding rows see nothing that is kept)
+            const int NV = causal ? min(N, t * QT + row_in_tile + 1) : N;
             float sum0 = 0.f, sum1 = 0.f;
 
 #define ATC_TRACE_S(ev)                                     \
@@ -288,11 +290,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                     if (c0 + 32 <= ce) {
                         ptx::tmem_ld_32x32b_x32(taddr + c0, r);
                         ptx::tmem_ld_wait();
-                        mx = chunk_max<32>(r, c0, N, mx);
+                        mx = chunk_max<32>(r, c0, NV, mx);
                     } else {
                         ptx::tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
                         ptx::tmem_ld_wait();
-                        mx = chunk_max<16>(r, c0, N, mx);
+                        mx = chunk_max<16>(r, c0, NV, mx);
                     }
                 }
                 xch_mine->x = mx;
@@ -314,11 +316,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                     if (c0 + 32 <= ce) {
                         ptx::tmem_ld_32x32b_x32(taddr + c0, r);
                         ptx::tmem_ld_wait();
-                        chunk_exp<T, 32>(r, c0, N, scale_log2e, neg_mxs, prow, sum0, sum1);
+                        chunk_exp<T, 32>(r, c0, NV, scale_log2e, neg_mxs, prow, sum0, sum1);
                     } else {
                         ptx::tmem_ld_32x32b_x16(taddr + c0, *reinterpret_cast<uint32_t(*)[16]>(&r[0]));
                         ptx::tmem_ld_wait();
-                        chunk_exp<T, 16>(r, c0, N, scale_log2e, neg_mxs, prow, sum0, sum1);
+                        chunk_exp<T, 16>(r, c0, NV, scale_log2e, neg_mxs, prow, sum0, sum1);
                     }
                 }
                 xch_mine->y = sum0 + sum1;
@@ -401,7 +403,7 @@ int launch_tc(const AttentionMaps& m, int B, int N, int H, float scale_log2e, cu
     int grid = gemm_num_sms();
     if (grid > n_items) grid = n_items;
     if (grid < 1) return 1;
-    kern<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(m.q, m.kv, m.out, n_items, N, H, scale_log2e, g_trace);
+    kern<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(m.q, m.kv, m.out, n_items, N, H, scale_log2e, g_trace, m.causal ? 1 : 0);
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;

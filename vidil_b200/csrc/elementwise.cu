@@ -112,6 +112,40 @@ __global__ void uncast_kernel(const T* __restrict__ in, float* __restrict__ out,
         out[i] = static_cast<float>(in[i]);
 }
 
+// resid[b*L + t, :] = tok[ids[b*L + t], :] + pos[t, :]   (CLIPTextEmbeddings.forward: token + position embedding)
+__global__ void embed_tokens_kernel(const int32_t* __restrict__ ids, const float* __restrict__ tok,
+                                    const float* __restrict__ pos, float* __restrict__ resid, int64_t rows, int L, int D,
+                                    int vocab) {
+    const int d4 = D / 4;
+    const int64_t total = rows * d4;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / d4;
+        const int c = static_cast<int>(i - r * d4);
+        int id = ids[r];
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);  // out-of-range ids are clamped, never read out of bounds
+        const int t = static_cast<int>(r % L);
+        const float4 a = reinterpret_cast<const float4*>(tok + static_cast<int64_t>(id) * D)[c];
+        const float4 b = reinterpret_cast<const float4*>(pos + static_cast<int64_t>(t) * D)[c];
+        reinterpret_cast<float4*>(resid + r * D)[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+}
+
+// out[b, :] = in[b*L + idx[b], :]   (the EOS row of every sequence, CLIPTextTransformer pooled_output)
+__global__ void gather_rows_kernel(const float* __restrict__ in, const int32_t* __restrict__ idx, float* __restrict__ out,
+                                   int B, int L, int D) {
+    const int d4 = D / 4;
+    const int64_t total = static_cast<int64_t>(B) * d4;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int b = static_cast<int>(i / d4), c = static_cast<int>(i - static_cast<int64_t>(b) * d4);
+        int t = idx[b];
+        t = t < 0 ? 0 : (t >= L ? L - 1 : t);
+        reinterpret_cast<float4*>(out + static_cast<int64_t>(b) * D)[c] =
+            reinterpret_cast<const float4*>(in + (static_cast<int64_t>(b) * L + t) * D)[c];
+    }
+}
+
 int grid_for(int64_t total, int block) {
     int64_t g = (total + block - 1) / block;
     const int64_t cap = 148 * 16;
@@ -168,6 +202,23 @@ int im2col_run(const float* frames, void* patches, DType dt, int B, int C, int i
 int cls_pos_run(const float* cls, const float* pos, float* resid, int B, int tokens, int D, cudaStream_t stream) {
     if (B <= 0) return 0;
     cls_pos_kernel<<<grid_for(static_cast<int64_t>(B) * D, 256), 256, 0, stream>>>(cls, pos, resid, B, tokens, D);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int embed_tokens_run(const int32_t* ids, const float* tok, const float* pos, float* resid, int64_t rows, int L, int D,
+                     int vocab, cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    embed_tokens_kernel<<<grid_for(rows * (D / 4), 256), 256, 0, stream>>>(ids, tok, pos, resid, rows, L, D, vocab);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int gather_rows_run(const float* in, const int32_t* idx, float* out, int B, int L, int D, cudaStream_t stream) {
+    if (B <= 0) return 0;
+    gather_rows_kernel<<<grid_for(static_cast<int64_t>(B) * (D / 4), 256), 256, 0, stream>>>(in, idx, out, B, L, D);
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;

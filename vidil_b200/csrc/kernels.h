@@ -86,6 +86,7 @@ struct AttentionMaps {
     void* out_ptr = nullptr;
     int B = 0, N = 0, H = 0;
     DType dt = DT_BF16;
+    bool causal = false;  // query i attends to keys 0..i only (CLIP text tower)
 };
 // Developer hook: a device buffer of 5*16*8 int64 that CTA 0 fills with clock64 stamps of its pipeline events.
 void attention_set_trace(long long* dev_buf);
@@ -106,6 +107,10 @@ int im2col_run(const float* frames, void* patches, DType dt, int B, int C, int i
 int cls_pos_run(const float* cls, const float* pos, float* resid, int B, int tokens, int D, cudaStream_t stream);
 // out[r,:] = in[r,:] / ||in[r,:]||_2
 int l2norm_run(const float* in, float* out, int rows, int D, cudaStream_t stream);
+// resid[r, :] = tok[ids[r], :] + pos[r % L, :]  and  out[b, :] = in[b*L + idx[b], :]  (CLIP text tower)
+int embed_tokens_run(const int32_t* ids, const float* tok, const float* pos, float* resid, int64_t rows, int L, int D,
+                     int vocab, cudaStream_t stream);
+int gather_rows_run(const float* in, const int32_t* idx, float* out, int B, int L, int D, cudaStream_t stream);
 // T -> fp32 (operator-level tests read 16-bit results back through this)
 int uncast_run(const void* in, float* out, DType dt, int64_t n, cudaStream_t stream);
 
