@@ -150,6 +150,28 @@ def test_vit_edge_cases(cuda):
     assert torch.equal(m(x.half().float()), m(x.half()))
 
 
+def test_vit_identity_cache_for_the_caption_filter_loop(cuda):
+    """run_video_CapFilt.py:110-112 re-encodes the same frames once per caption; with the opt-in cache only the first call
+    launches kernels, and any change to the frames or the weights invalidates it."""
+    m, sd = _build("tiny", 32, "fp16", cuda)
+    m.cache_identical_inputs = True
+    x = W.frames(4, 32, seed=0).to(cuda)
+    a = m(x)
+    before = _lib.launch_count()
+    for _ in range(4):                      # 4 more captions on the same frames
+        assert m(x) is a
+    assert _lib.launch_count() == before
+    x.mul_(0.5)                             # in-place edit bumps the tensor version
+    b = m(x)
+    assert b is not a and not torch.equal(a, b)
+    y = x.clone()                           # same values at another address: recomputed, then cached under the new key
+    out_y = m(y)
+    assert out_y is not b and torch.equal(out_y, b) and m(y) is out_y
+    m.load_state_dict(W.vit_state_dict("tiny", 32, seed=3))
+    c = m(y)
+    _check(c.cpu(), vit_oracle.vit_forward(W.vit_state_dict("tiny", 32, seed=3), y.cpu(), 2), "fp16")
+
+
 def test_native_library_is_the_path(cuda):
     m, _ = _build("tiny", 32, "bf16", cuda)
     x = W.frames(2, 32, seed=0).to(cuda)

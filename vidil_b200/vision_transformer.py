@@ -157,7 +157,8 @@ class VisionTransformer(nn.Module):
     def __init__(self, img_size=224, patch_size=16, in_chans=3, num_classes=1000, embed_dim=768, depth=12,
                  num_heads=12, mlp_ratio=4., qkv_bias=True, qk_scale=None, representation_size=None,
                  drop_rate=0., attn_drop_rate=0., drop_path_rate=0., norm_layer=None,
-                 use_grad_checkpointing=False, ckpt_layer=0, compute_dtype="bf16", cta_group=0):
+                 use_grad_checkpointing=False, ckpt_layer=0, compute_dtype="bf16", cta_group=0,
+                 cache_identical_inputs=False):
         super().__init__()
         if in_chans != 3 or not qkv_bias or qk_scale is not None or mlp_ratio != 4.:
             raise ValueError("vidil_b200.VisionTransformer supports the configurations models/blip.py:create_vit "
@@ -188,6 +189,13 @@ class VisionTransformer(nn.Module):
 
         self._native = None
         self._packed_sig = None
+        # run_video_CapFilt.py:110-112 calls the filterer once per caption with the SAME frame tensor, re-running this
+        # tower every time.  With cache_identical_inputs the output of the previous call is returned
+        # when the input is the same tensor object, unmodified, and the weights have not changed.  Opt-in: the returned
+        # tensor is then shared between calls, so callers must not write into it.
+        self.cache_identical_inputs = cache_identical_inputs
+        self._cache_key = None
+        self._cache_out = None
 
     @staticmethod
     def _init_weights(m):
@@ -237,6 +245,11 @@ class VisionTransformer(nn.Module):
         _check_frames(x, self.img_size)
         with torch.cuda.device(x.device):
             enc = self._ensure_packed()
+            key = None
+            if self.cache_identical_inputs:
+                key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, x._version, self._packed_sig)
+                if key == self._cache_key and self._cache_out is not None:
+                    return self._cache_out
             x = x.contiguous().float()
             B = x.shape[0]
             out = torch.empty(B, enc.tokens, self.embed_dim, dtype=torch.float32, device=x.device)
@@ -246,6 +259,8 @@ class VisionTransformer(nn.Module):
             st = enc.lib.vidil_vit_forward(enc.handle, x.data_ptr(), B, out.data_ptr(), ws.data_ptr(), ws.numel(),
                                            torch.cuda.current_stream().cuda_stream)
             _lib.check(st, "vidil_vit_forward")
+            if key is not None:
+                self._cache_key, self._cache_out, self._cache_in = key, out, x  # keep x alive: its address is the key
         return out
 
     @torch.no_grad()
