@@ -230,8 +230,13 @@ int build_plan(vidil_encoder* e, Plan& pl, int B, void* ws) {
         f2.out = pl.resid; f2.ldo = D;
         if (gemm_prepare(f2)) return 1;
     }
-    pl.attn_tc = attention_tc_supported(e->tokens);
-    if (pl.attn_tc && attention_tc_prepare(pl.attn_maps, pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads)) return 1;
+    if (attention_tc_supported(e->tokens)) {
+        pl.attn_tc = true;
+        if (attention_tc_prepare(pl.attn_maps, pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads)) return 1;
+    } else if (attention_tcl_supported(e->tokens)) {
+        pl.attn_tc = true;
+        if (attention_tcl_prepare(pl.attn_maps, pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads)) return 1;
+    }
     if (c.proj_dim > 0) {
         pl.head = g;
         pl.head.epi = EPI_STORE_F32;
@@ -363,8 +368,9 @@ int run_trunk(vidil_encoder* e, Plan& pl, const float* frames, cudaStream_t s) {
         if (gemm_timed(e, s, pl.qkv_g[i])) return 1;
         if (timed(e, s, VIDIL_KCLASS_ATTENTION, attn_flops, attn_bytes,
                   [&] {
-                      return pl.attn_tc ? attention_tc_run(pl.attn_maps, scale, s)
-                                        : attention_run(pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads, scale, s);
+                      if (!pl.attn_tc) return attention_run(pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads, scale, s);
+                      return pl.attn_maps.is_long ? attention_tcl_run(pl.attn_maps, scale, s)
+                                                  : attention_tc_run(pl.attn_maps, scale, s);
                   }))
             return 1;
         if (gemm_timed(e, s, pl.proj_g[i])) return 1;
@@ -921,6 +927,10 @@ int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, i
         AttentionMaps maps;
         if (attention_tc_prepare(maps, qkv_h, out_h, dt, B, N, H)) return 1;
         if (attention_tc_run(maps, scale, s)) return 1;
+    } else if (attention_tcl_supported(N)) {
+        AttentionMaps maps;
+        if (attention_tcl_prepare(maps, qkv_h, out_h, dt, B, N, H)) return 1;
+        if (attention_tcl_run(maps, scale, s)) return 1;
     } else if (attention_run(qkv_h, out_h, dt, B, N, H, scale, s)) {
         return 1;
     }

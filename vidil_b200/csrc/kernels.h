@@ -87,12 +87,19 @@ struct AttentionMaps {
     int B = 0, N = 0, H = 0;
     DType dt = DT_BF16;
     bool causal = false;  // query i attends to keys 0..i only (CLIP text tower)
+    // long-sequence kernel (attention_tcl.cu): key-block size, number of key blocks, query tiles done on tcgen05
+    bool is_long = false;
+    int KB = 0, nkb = 0, n_qt = 0;
 };
 // Developer hook: a device buffer of 5*16*8 int64 that CTA 0 fills with clock64 stamps of its pipeline events.
 void attention_set_trace(long long* dev_buf);
 bool attention_tc_supported(int N);
 int attention_tc_prepare(AttentionMaps& m, const void* qkv, void* out, DType dt, int B, int N, int H);
 int attention_tc_run(const AttentionMaps& m, float scale, cudaStream_t stream);
+// tcgen05 version with a key-block loop for 128 < N <= 768 (attention_tcl.cu); non-causal
+bool attention_tcl_supported(int N);
+int attention_tcl_prepare(AttentionMaps& m, const void* qkv, void* out, DType dt, int B, int N, int H);
+int attention_tcl_run(const AttentionMaps& m, float scale, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------
 // Elementwise / layout kernels.
