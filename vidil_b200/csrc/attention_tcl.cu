@@ -362,69 +362,102 @@ __global__ void __launch_bounds__(ATL_THREADS, 1)
     if (warp == 3) ptx::tmem_dealloc<1>(tmem_base, 512);
 }
 
-// Query rows [row_first, N) of every (frame, head), one warp per row: plain fp32 SIMT softmax attention over all N keys.
+// Query rows [row_first, N) of every (frame, head): plain fp32 SIMT softmax attention over all N keys, one 4-warp CTA per
+// row (each warp a contiguous quarter of the keys, each lane every 32nd key of it, 16-byte loads of the K / V rows).
 // Only used for the few rows past the last full 128-row tile (CLIP: the 257th token).
 template <typename T>
+__device__ __forceinline__ void load_row64(const T* p, float (&x)[HD]) {
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const uint4 u = __ldg(reinterpret_cast<const uint4*>(p) + c);
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                x[8 * c + 2 * i] = __uint_as_float(w[i] << 16);
+                x[8 * c + 2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+            } else {
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                x[8 * c + 2 * i] = f.x;
+                x[8 * c + 2 * i + 1] = f.y;
+            }
+        }
+    }
+}
+
+template <typename T>
 __global__ void __launch_bounds__(128)
-    attention_rows_kernel(const T* __restrict__ qkv, T* __restrict__ out, int B, int N, int H, int row_first, float scale) {
+    attention_rows_kernel(const T* __restrict__ qkv, T* __restrict__ out, int N, int H, int row_first, float scale) {
+    __shared__ float s_red[4];
+    __shared__ float s_acc[4][HD];
     const int nrows = N - row_first;
-    const int w = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (w >= B * H * nrows) return;
-    const int row = row_first + w % nrows;
-    const int bh = w / nrows;
+    const int row = row_first + blockIdx.x % nrows;
+    const int bh = blockIdx.x / nrows;
     const int b = bh / H, h = bh - b * H;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int64_t tok_stride = static_cast<int64_t>(3) * H * HD;
     const T* base = qkv + static_cast<int64_t>(b) * N * tok_stride + h * HD;
-    const T* qp = base + static_cast<int64_t>(row) * tok_stride;
     float q[HD];
+    load_row64<T>(base + static_cast<int64_t>(row) * tok_stride, q);
 #pragma unroll
-    for (int d = 0; d < HD; ++d) q[d] = static_cast<float>(qp[d]) * scale;
-    // pass 1: this lane's keys (lane, lane + 32, ...): scores and the running maximum
-    constexpr int MAXK = 24;  // up to 768 keys
+    for (int d = 0; d < HD; ++d) q[d] *= scale;
+    const int per_warp = (N + 3) / 4;
+    const int k_begin = warp * per_warp, k_end = min(N, k_begin + per_warp);
+    constexpr int MAXK = 6;  // keys per lane: N <= 768 -> 192 per warp -> 6 per lane
     float sc[MAXK];
     float mx = -INFINITY;
 #pragma unroll
     for (int i = 0; i < MAXK; ++i) {
-        const int j = lane + 32 * i;
+        const int j = k_begin + lane + 32 * i;
         float s = -INFINITY;
-        if (j < N) {
-            const T* kp = base + static_cast<int64_t>(H) * HD + static_cast<int64_t>(j) * tok_stride;
+        if (j < k_end) {
+            float kk[HD];
+            load_row64<T>(base + static_cast<int64_t>(H) * HD + static_cast<int64_t>(j) * tok_stride, kk);
             s = 0.f;
 #pragma unroll
-            for (int d = 0; d < HD; ++d) s = fmaf(q[d], static_cast<float>(kp[d]), s);
+            for (int d = 0; d < HD; ++d) s = fmaf(q[d], kk[d], s);
         }
         sc[i] = s;
         mx = fmaxf(mx, s);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-    // pass 2: weights, weighted sum of this lane's value rows
+    if (lane == 0) s_red[warp] = mx;
+    __syncthreads();
+    mx = fmaxf(fmaxf(s_red[0], s_red[1]), fmaxf(s_red[2], s_red[3]));
+    __syncthreads();
     float acc[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) acc[d] = 0.f;
     float sum = 0.f;
 #pragma unroll
     for (int i = 0; i < MAXK; ++i) {
-        const int j = lane + 32 * i;
-        if (j < N) {
+        const int j = k_begin + lane + 32 * i;
+        if (j < k_end) {
             const float p = __expf(sc[i] - mx);
             sum += p;
-            const T* vp = base + static_cast<int64_t>(2) * H * HD + static_cast<int64_t>(j) * tok_stride;
+            float vv[HD];
+            load_row64<T>(base + static_cast<int64_t>(2) * H * HD + static_cast<int64_t>(j) * tok_stride, vv);
 #pragma unroll
-            for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, static_cast<float>(vp[d]), acc[d]);
+            for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, vv[d], acc[d]);
         }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float inv = 1.0f / sum;
-    T* op = out + (static_cast<int64_t>(b) * N + row) * (H * HD) + h * HD;
+    if (lane == 0) s_red[warp] = sum;
 #pragma unroll
     for (int d = 0; d < HD; ++d) {
         float v = acc[d];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == (d & 31)) op[d] = static_cast<T>(v * inv);
+        if (lane == (d & 31)) s_acc[warp][d] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < HD) {
+        const int d = threadIdx.x;
+        const float tot = s_red[0] + s_red[1] + s_red[2] + s_red[3];
+        const float v = s_acc[0][d] + s_acc[1][d] + s_acc[2][d] + s_acc[3][d];
+        out[(static_cast<int64_t>(b) * N + row) * (H * HD) + h * HD + d] = static_cast<T>(v / tot);
     }
 }
 
@@ -464,9 +497,9 @@ int launch_long(const AttentionMaps& m, float scale, cudaStream_t stream) {
     count_launches(1);
     const int row_first = m.n_qt * QT;
     if (row_first < m.N) {
-        const int warps = m.B * m.H * (m.N - row_first);
-        attention_rows_kernel<T><<<(warps + 3) / 4, 128, 0, stream>>>(reinterpret_cast<const T*>(m.qkv),
-                                                                      reinterpret_cast<T*>(m.out_ptr), m.B, m.N, m.H, row_first, scale);
+        const int rows = m.B * m.H * (m.N - row_first);
+        attention_rows_kernel<T><<<rows, 128, 0, stream>>>(reinterpret_cast<const T*>(m.qkv), reinterpret_cast<T*>(m.out_ptr),
+                                                           m.N, m.H, row_first, scale);
         VIDIL_CUDA_OK(cudaGetLastError());
         count_launches(1);
     }
