@@ -96,6 +96,7 @@ def test_layernorm_rejects_unsupported_width(cuda):
 
 @pytest.mark.parametrize("B,N,H,dtype", [(1, 1, 1, "fp16"), (1, 64, 1, "bf16"), (2, 197, 16, "bf16"), (2, 197, 16, "fp16"),
                                          (1, 257, 16, "fp16"), (1, 577, 12, "bf16"), (3, 5, 2, "fp16"), (64, 197, 16, "bf16"),
+                                         (2, 130, 2, "bf16"), (2, 144, 1, "fp16"), (3, 161, 2, "bf16"),
                                          (2, 209, 2, "bf16"), (3, 256, 4, "fp16"), (2, 272, 3, "bf16"), (2, 300, 2, "fp16"),
                                          (40, 257, 16, "bf16"), (1, 768, 2, "fp16"), (1, 900, 2, "bf16")])
 def test_attention(cuda, B, N, H, dtype):
