@@ -98,6 +98,7 @@ def test_layernorm_rejects_unsupported_width(cuda):
                                          (1, 257, 16, "fp16"), (1, 577, 12, "bf16"), (3, 5, 2, "fp16"), (64, 197, 16, "bf16"),
                                          (2, 130, 2, "bf16"), (2, 144, 1, "fp16"), (3, 161, 2, "bf16"),
                                          (2, 209, 2, "bf16"), (3, 256, 4, "fp16"), (2, 272, 3, "bf16"), (2, 300, 2, "fp16"),
+                                         (2, 258, 2, "fp16"), (3, 260, 3, "bf16"), (2, 261, 2, "fp16"), (2, 385, 2, "bf16"),
                                          (40, 257, 16, "bf16"), (1, 768, 2, "fp16"), (1, 900, 2, "bf16")])
 def test_attention(cuda, B, N, H, dtype):
     g = torch.Generator().manual_seed(B * 100 + N + H)

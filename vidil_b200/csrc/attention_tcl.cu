@@ -11,8 +11,10 @@
 // Recomputing S costs tensor time that is idle anyway (the kernel is bound by the softmax warps) and removes the
 // accumulator rescaling of an online softmax: O lives in its own 64 TMEM columns and is only ever accumulated into.
 // A lane whose tile index runs past the last tile recomputes the last tile and does not store it, so both lanes always
-// take part in every barrier.  Query rows beyond the last full tile, when there are at most 16 of them (the 257th token of
-// CLIP), are left to attention_rows_kernel below, one warp per row, instead of a whole extra round.
+// take part in every barrier.  Query rows beyond the last full tile are not worth a whole extra round when there are only
+// a few of them (the 257th token of CLIP): up to 4 such rows are computed by four extra "tail" warps of the same CTA with
+// plain fp32 SIMT arithmetic straight from the K / V tiles that are in shared memory anyway (no extra HBM traffic);
+// 5..16 rows go to attention_rows_kernel below.
 #include <math.h>
 
 #include <type_traits>
@@ -27,11 +29,12 @@ constexpr int HD = 64;
 constexpr int QT = 128;
 constexpr int MAX_KB = 144;        // keys per block: S (fp32) in TMEM columns [0, 144), O in [192, 256) of the lane's 256
 constexpr int O_COL = 192;
-constexpr int ATL_THREADS = 640;   // warp 0 producer, 1-2 MMA issuers, 3 TMEM allocator, 4-11 / 12-19 softmax groups
+constexpr int ATL_THREADS = 768;   // warp 0 producer, 1-2 MMA issuers, 3 TMEM allocator, 4-11 / 12-19 softmax groups, 20-23 tail rows
+constexpr int MAX_TAIL = 4;
 constexpr int Q_BYTES = QT * HD * 2;
 
 struct Layout {  // shared-memory byte offsets for a given key-block size
-    int k, v, p, out, xch, bar, total, kbytes, pbytes;
+    int k, v, p, out, xch, tail, bar, total, kbytes, pbytes;
 };
 __host__ __device__ inline Layout make_layout(int KB) {
     Layout l;
@@ -42,7 +45,8 @@ __host__ __device__ inline Layout make_layout(int KB) {
     l.p = l.v + 2 * l.kbytes;
     l.out = l.p + 2 * l.pbytes;
     l.xch = l.out + 8 * 4096;
-    l.bar = l.xch + 2 * 2 * 128 * 8;
+    l.tail = l.xch + 2 * 2 * 128 * 8;                      // tail rows: q [4][64] fp32 + per-warp partials [4][4][66] fp32
+    l.bar = l.tail + MAX_TAIL * HD * 4 + 4 * MAX_TAIL * 66 * 4;
     l.total = l.bar + 256 + 1024;
     return l;
 }
@@ -103,7 +107,7 @@ template <typename T>
 __global__ void __launch_bounds__(ATL_THREADS, 1)
     attention_tcl_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_kv,
                          const __grid_constant__ CUtensorMap map_out, int n_items, int N, int H, int KB, int nkb, int n_qt,
-                         float scale_log2e) {
+                         int n_tail, float scale_log2e, const T* __restrict__ qkv, T* __restrict__ out) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw_addr = ptx::smem_u32(smem_raw);
     uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
@@ -138,9 +142,9 @@ __global__ void __launch_bounds__(ATL_THREADS, 1)
         ptx::mbar_init(q_empty, 2);  // one commit per lane
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&k_full[i], 1);
-            ptx::mbar_init(&k_empty[i], 2);
+            ptx::mbar_init(&k_empty[i], 3);  // both lanes' MMA commits + the tail group
             ptx::mbar_init(&v_full[i], 1);
-            ptx::mbar_init(&v_empty[i], 2);
+            ptx::mbar_init(&v_empty[i], 3);
             ptx::mbar_init(&s_full[i], 1);
             ptx::mbar_init(&s_free[i], 1);   // elected thread, after the lane's 8 softmax warps have synchronised
             ptx::mbar_init(&p_full[i], 1);
@@ -236,7 +240,7 @@ __global__ void __launch_bounds__(ATL_THREADS, 1)
             }
         }
         __syncwarp();
-    } else if (warp >= 4) {
+    } else if (warp >= 4 && warp < 20) {
         // ===================== softmax + output group of lane L =====================
         const int L = (warp - 4) >> 3;
         const int half = ((warp - 4) >> 2) & 1;
@@ -355,6 +359,174 @@ __global__ void __launch_bounds__(ATL_THREADS, 1)
             }
         }
         if (half == 0 && lane == 0) ptx::bulk_wait_group<0>();
+    }
+
+    if (warp >= 20) {
+        // ===================== tail rows: queries n_qt*128 .. N-1 of each (frame, head), SIMT =====================
+        // The four warps take a quarter of each key block each.  Per warp and row: running max m, sum l and the output
+        // accumulator (two channels per lane), merged across the warps at the end of the item.  Keys and values are read
+        // from the SWIZZLE_128B tiles the TMA producer filled for the tensor-core lanes, during sweep 1 (when both the K
+        // and the V block of a step are resident); every step's buffers are released through the same k_empty / v_empty
+        // barriers the MMA issuers commit to.
+        const int tw = warp - 20;
+        float* tq = reinterpret_cast<float*>(smem + lay.tail);                 // [MAX_TAIL][64], pre-scaled by c
+        float* tpart = tq + MAX_TAIL * HD;                                      // [4 warps][MAX_TAIL][66]
+        const int row_first = n_qt * QT;
+        int it = 0, kc = 0, vc = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const int r = item % rounds, bh = item / rounds;
+            const int b = bh / H, h = bh - b * H;
+            const bool work = (n_tail > 0) && (r == 0);
+            float m_run[MAX_TAIL], l_run[MAX_TAIL], acc0[MAX_TAIL], acc1[MAX_TAIL];
+#pragma unroll
+            for (int q = 0; q < MAX_TAIL; ++q) m_run[q] = -INFINITY, l_run[q] = 0.f, acc0[q] = 0.f, acc1[q] = 0.f;
+            if (work) {
+                // q rows (pre-multiplied by scale * log2 e) into shared memory: thread i < n_tail*64 loads one channel
+                for (int i = threadIdx.x - 20 * 32; i < n_tail * HD; i += 128) {
+                    const int q = i / HD, d = i - q * HD;
+                    tq[i] = static_cast<float>(qkv[(static_cast<int64_t>(b) * N + row_first + q) * (3 * H * HD) + h * HD + d]) *
+                            scale_log2e;
+                }
+                ptx::named_bar_sync(11, 128);
+            }
+            for (int s = 0; s < nsteps; ++s) {
+                const int j = (s >= nkb) ? s - nkb : s;
+                const int kb = kc & 1;
+                if (s < nkb || !work) {
+                    // nothing to compute in this step: one thread waits for the data phase and releases the buffers
+                    if (tw == 0 && lane == 0) {
+                        ptx::mbar_wait(&k_full[kb], (kc >> 1) & 1);
+                        ptx::mbar_arrive(&k_empty[kb]);
+                        if (s >= nkb) {
+                            const int vb = vc & 1;
+                            ptx::mbar_wait(&v_full[vb], (vc >> 1) & 1);
+                            ptx::mbar_arrive(&v_empty[vb]);
+                        }
+                    }
+                } else {
+                    const int vb = vc & 1;
+                    if (tw == 0) {
+                        ptx::mbar_wait(&k_full[kb], (kc >> 1) & 1);
+                        ptx::mbar_wait(&v_full[vb], (vc >> 1) & 1);
+                    }
+                    ptx::named_bar_sync(11, 128);
+                    const int nv = min(KB, N - j * KB);
+                    const int per_warp = (nv + 3) / 4;
+                    const int k_begin = tw * per_warp, k_end = min(nv, k_begin + per_warp);
+                    const uint32_t sk = sbase + lay.k + kb * lay.kbytes;
+                    const uint32_t sv = sbase + lay.v + vb * lay.kbytes;
+                    for (int q = 0; q < n_tail; ++q) {
+                        const float4* q4 = reinterpret_cast<const float4*>(tq + q * HD);
+                        for (int k0 = k_begin; k0 < k_end; k0 += 32) {
+                            const int k = k0 + lane;
+                            float sc = -INFINITY;
+                            if (k < k_end) {
+                                sc = 0.f;
+#pragma unroll
+                                for (int c = 0; c < 8; ++c) {
+                                    uint32_t w0, w1, w2, w3;
+                                    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                                                 : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3)
+                                                 : "r"(sk + k * 128 + ((c ^ (k & 7)) << 4)));
+                                    const float4 qa = q4[2 * c], qb = q4[2 * c + 1];
+                                    const uint32_t w[4] = {w0, w1, w2, w3};
+                                    const float qq[8] = {qa.x, qa.y, qa.z, qa.w, qb.x, qb.y, qb.z, qb.w};
+#pragma unroll
+                                    for (int i = 0; i < 4; ++i) {
+                                        float lo, hi;
+                                        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                                            lo = __uint_as_float(w[i] << 16);
+                                            hi = __uint_as_float(w[i] & 0xffff0000u);
+                                        } else {
+                                            const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+                                            lo = f.x;
+                                            hi = f.y;
+                                        }
+                                        sc = fmaf(qq[2 * i], lo, sc);
+                                        sc = fmaf(qq[2 * i + 1], hi, sc);
+                                    }
+                                }
+                            }
+                            // block-of-32 maximum, rescale the running state, then the weighted values
+                            float bm = sc;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) bm = fmaxf(bm, __shfl_xor_sync(0xffffffffu, bm, o));
+                            const float m_new = fmaxf(m_run[q], bm);
+                            const float corr = ptx::ex2_approx(m_run[q] - m_new);  // first block: exp2(-inf) = 0
+                            const float p = (k < k_end) ? ptx::ex2_approx(sc - m_new) : 0.f;
+                            float ps = p;
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) ps += __shfl_xor_sync(0xffffffffu, ps, o);
+                            l_run[q] = l_run[q] * corr + ps;
+                            acc0[q] *= corr;
+                            acc1[q] *= corr;
+                            m_run[q] = m_new;
+                            const int cnt = min(32, k_end - k0);
+                            for (int kk = 0; kk < cnt; ++kk) {
+                                const float pk = __shfl_sync(0xffffffffu, p, kk);
+                                const int key = k0 + kk;
+                                uint32_t vw;
+                                asm volatile("ld.shared.b32 %0, [%1];"
+                                             : "=r"(vw)
+                                             : "r"(sv + key * 128 + (((lane >> 2) ^ (key & 7)) << 4) + (lane & 3) * 4));
+                                float lo, hi;
+                                if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+                                    lo = __uint_as_float(vw << 16);
+                                    hi = __uint_as_float(vw & 0xffff0000u);
+                                } else {
+                                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&vw));
+                                    lo = f.x;
+                                    hi = f.y;
+                                }
+                                acc0[q] = fmaf(pk, lo, acc0[q]);
+                                acc1[q] = fmaf(pk, hi, acc1[q]);
+                            }
+                        }
+                    }
+                    ptx::named_bar_sync(11, 128);  // all four warps are done with this step's K and V tiles
+                    if (tw == 0 && lane == 0) {
+                        ptx::mbar_arrive(&k_empty[kb]);
+                        ptx::mbar_arrive(&v_empty[vb]);
+                    }
+                }
+                ++kc;
+                if (s >= nkb) ++vc;
+            }
+            if (work) {
+                // merge the four warps' partial softmaxes and write the rows
+                for (int q = 0; q < n_tail; ++q) {
+                    float* pp = tpart + (tw * MAX_TAIL + q) * 66;
+                    pp[2 * lane] = acc0[q];
+                    pp[2 * lane + 1] = acc1[q];
+                    if (lane == 0) {
+                        pp[64] = m_run[q];
+                        pp[65] = l_run[q];
+                    }
+                }
+                ptx::named_bar_sync(11, 128);
+                if (tw == 0) {
+                    for (int q = 0; q < n_tail; ++q) {
+                        float M = -INFINITY;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) M = fmaxf(M, tpart[(w * MAX_TAIL + q) * 66 + 64]);
+                        float den = 0.f, o0 = 0.f, o1 = 0.f;
+#pragma unroll
+                        for (int w = 0; w < 4; ++w) {
+                            const float* pp = tpart + (w * MAX_TAIL + q) * 66;
+                            const float f = ptx::ex2_approx(pp[64] - M);  // a warp without keys has m = -inf, f = 0
+                            den = fmaf(f, pp[65], den);
+                            o0 = fmaf(f, pp[2 * lane], o0);
+                            o1 = fmaf(f, pp[2 * lane + 1], o1);
+                        }
+                        const float inv = 1.0f / den;
+                        const uint32_t packed = pack2<T>(o0 * inv, o1 * inv);
+                        *reinterpret_cast<uint32_t*>(out + (static_cast<int64_t>(b) * N + row_first + q) * (H * HD) + h * HD + 2 * lane) =
+                            packed;
+                    }
+                }
+                ptx::named_bar_sync(11, 128);  // tpart / tq are reused by the next item
+            }
+        }
     }
 
     ptx::tcgen05_fence_before();
@@ -491,12 +663,13 @@ int launch_long(const AttentionMaps& m, float scale, cudaStream_t stream) {
     int grid = gemm_num_sms();
     if (grid > n_items) grid = n_items;
     if (grid < 1) return 1;
-    kern<<<grid, ATL_THREADS, lay.total, stream>>>(m.q, m.kv, m.out, n_items, m.N, m.H, m.KB, m.nkb, m.n_qt,
-                                                    scale * 1.4426950408889634f);
+    kern<<<grid, ATL_THREADS, lay.total, stream>>>(m.q, m.kv, m.out, n_items, m.N, m.H, m.KB, m.nkb, m.n_qt, m.n_tail,
+                                                    scale * 1.4426950408889634f, reinterpret_cast<const T*>(m.qkv),
+                                                    reinterpret_cast<T*>(m.out_ptr));
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     const int row_first = m.n_qt * QT;
-    if (row_first < m.N) {
+    if (m.n_tail == 0 && row_first < m.N) {
         const int rows = m.B * m.H * (m.N - row_first);
         attention_rows_kernel<T><<<rows, 128, 0, stream>>>(reinterpret_cast<const T*>(m.qkv), reinterpret_cast<T*>(m.out_ptr),
                                                            m.N, m.H, row_first, scale);
@@ -524,8 +697,10 @@ int attention_tcl_prepare(AttentionMaps& m, const void* qkv, void* out, DType dt
     const int nkb = (N + MAX_KB - 1) / MAX_KB;
     const int KB = (((N + nkb - 1) / nkb) + 15) & ~15;
     // query tiles for the tcgen05 kernel; a short tail of rows goes to the per-row kernel instead of a whole extra tile
+    // (<= 4 rows: tail warps inside the kernel; <= 16: the per-row kernel)
     const int rem = N % QT;
     const int n_qt = (rem != 0 && rem <= 16) ? N / QT : (N + QT - 1) / QT;
+    m.n_tail = (rem != 0 && rem <= MAX_TAIL) ? rem : 0;
     const CUtensorMapDataType cdt = (dt == DT_BF16) ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
     const cuuint32_t estr3[3] = {1, 1, 1};
     {

@@ -89,7 +89,7 @@ struct AttentionMaps {
     bool causal = false;  // query i attends to keys 0..i only (CLIP text tower)
     // long-sequence kernel (attention_tcl.cu): key-block size, number of key blocks, query tiles done on tcgen05
     bool is_long = false;
-    int KB = 0, nkb = 0, n_qt = 0;
+    int KB = 0, nkb = 0, n_qt = 0, n_tail = 0;
 };
 // Developer hook: a device buffer of 5*16*8 int64 that CTA 0 fills with clock64 stamps of its pipeline events.
 void attention_set_trace(long long* dev_buf);
