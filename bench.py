@@ -306,9 +306,9 @@ def run_vit(args):
                      "frac": gemm_tflops / peaks["tflops_sustained"], "frac_of_burst_peak": gemm_tflops / peaks["tflops"],
                      "peak_source": peaks["source"] + ", sustained figure (kernel timed inside a long step)",
                      # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the four per-layer GEMMs of one
-                     # `ncu --set full` capture of this build (profiles/r01c_summary.md: fc1 474, fc2 824, qkv 368,
+                     # `ncu --set full` capture of this build (profiles/r01d_summary.md: fc1 471, fc2 832, qkv 366,
                      # proj 460 MB) — against 574 MB of algorithmic operand + output bytes per launch
-                     "traffic": 531.4e6 if (args.vit == "large" and B == 256 and args.image_size == 224) else None,
+                     "traffic": 532.3e6 if (args.vit == "large" and B == 256 and args.image_size == 224) else None,
                      "algorithmic_bytes_per_launch": g["bytes"] / max(g["launches"], 1),
                      "share_of_step": g["ms"] / ms_total},
         "whole_step": {"gflop_per_frame": gflop_frame, "tflops": fps / world * gflop_frame / 1e3,
