@@ -12,7 +12,7 @@ One step = one 256-frame batch through vidil_vit_forward.  Prints ONE JSON line 
             and step k-1's D2H overlapping step k's forward
   roofline  the tcgen05 GEMM kernel: algorithmic FLOPs / its event-timed device time inside the timed steps
   cpu_baseline  the oracle port of models/vit.py timed on this box's host cores (rank 0, N=1 only)
-Other workloads (not the driver's line): --workload clip | sim | text.
+Other workloads (not the driver's line): --workload clip | sim | text | tokenize.
 """
 from __future__ import annotations
 
@@ -423,13 +423,93 @@ def run_text(args):
                       "config": {"workload": "CLIP ViT-L/14 text tower, 512 phrases x 77 tokens per step"}}), flush=True)
 
 
+def run_tokenize(args):
+    """BASELINE configs[3]/[4] shape, tokenization half: synthetic videos x 8 frames through the whole CLIP branch of
+    run_visual_tokenization.py — phrase bank by the native text tower, frames through the native image tower from pinned
+    host buffers, similarity + top-k per bank on the device, aggregation on the host, one all-gather of the JSON rows,
+    rank 0 writes visual_tokens.json.  Videos are sharded over the ranks with the reference's slice formula."""
+    import tempfile as _tf
+
+    import torch
+    import torch.distributed as dist
+
+    from oracle import weights as W
+    from vidil_b200 import distributed as vdist, visual_tokenization as vt
+    from vidil_b200.clip import CLIPTextB200, CLIPVisionB200
+    rank, world, local = dist_env(args)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        vdist.init_distributed_mode("nccl")
+    torch.manual_seed(7)
+    vision = CLIPVisionB200(**W.CLIP_CONFIGS["large14"], compute_dtype=args.dtype)
+    text = CLIPTextB200(**W.CLIP_TEXT_CONFIGS["large14"], compute_dtype=args.dtype)
+    with torch.no_grad():
+        for m in (vision, text):
+            for n, p in m.named_parameters():
+                p.normal_(0.0, 0.02)
+                if "norm" in n and n.endswith("weight"):
+                    p.add_(1.0)
+    vision, text = vision.to(dev).eval(), text.to(dev).eval()
+    num_frm, k = 8, 5
+    bank_sizes = {"objects": 19965, "attributes": 16693, "scenes": 365, "verbs": 7414}  # the reference's `vg` ontology
+    phrases = {key: [f"{key} {i}" for i in range(n)] for key, n in bank_sizes.items()}
+    videos = [f"video{i}" for i in range(args.videos)]
+    start, end = vdist.shard_bounds(len(videos), world, rank)
+    mine = videos[start:end]
+    fb = args.batch - args.batch % num_frm                      # frames per tower call: whole videos
+    host = [torch.randn(fb, 3, 224, 224).pin_memory() for _ in range(2)]
+    n_calls = (len(mine) * num_frm + fb - 1) // fb
+
+    def run_once():
+        t0 = time.perf_counter()
+        reps = {}
+        for key, n in bank_sizes.items():                        # phrase bank, 512 phrases per call like the reference
+            embs = [text(W.token_ids("large14", min(512, n - i), 77, seed=i).to(dev)) for i in range(0, n, 512)]
+            reps[key] = {"text_embeds": torch.cat(embs)}
+        torch.cuda.synchronize()
+        t_bank = time.perf_counter() - t0
+        embeds = []
+        for e in vision.encode_host_stream(host[i & 1] for i in range(n_calls)):
+            embeds.append(e.to(dev, non_blocking=True))
+        image_embeds = torch.cat(embeds)[:len(mine) * num_frm]
+        torch.cuda.synchronize()
+        t_frames = time.perf_counter() - t0 - t_bank
+        rows = vt.tokens_from_embeddings(image_embeds, reps, phrases, mine, [[""]] * len(mine), num_frm, k)
+        t_tok = time.perf_counter() - t0 - t_bank - t_frames
+        out_dir = _tf.mkdtemp() if rank == 0 else None
+        merged = vdist.gather_and_write(rows, os.path.join(out_dir, "visual_tokens.json") if rank == 0 else None, device=dev)
+        t_all = time.perf_counter() - t0
+        return t_all, t_bank, t_frames, t_tok, (len(merged) if merged is not None else 0)
+
+    run_once() if args.warmup else None
+    if world > 1:
+        dist.barrier()
+    t_all, t_bank, t_frames, t_tok, n_rows = run_once()
+    if world > 1:
+        t = torch.tensor([t_all], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        t_all = float(t.item())
+    if rank == 0:
+        print(json.dumps({"metric": "frames/sec tokenized (CLIP towers + sim + top-k + JSON gather)",
+                          "value": args.videos * num_frm / t_all, "unit": "frames/s", "n_gpus": world, "seconds": t_all,
+                          "rank0_seconds": {"phrase_bank": t_bank, "frames": t_frames, "sim_topk_aggregate": t_tok},
+                          "rows_merged": n_rows,
+                          "config": {"workload": f"{args.videos} synthetic videos x {num_frm} frames, vg-sized phrase banks "
+                                                 f"{bank_sizes}, top-{k}, tower batch {fb} frames from pinned host memory"}}),
+              flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="vit", choices=["vit", "clip", "sim", "text"])
+    ap.add_argument("--workload", default="vit", choices=["vit", "clip", "sim", "text", "tokenize"])
+    ap.add_argument("--videos", type=int, default=1024, help="--workload tokenize: synthetic videos (8 frames each), all ranks")
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--vit", default="large", choices=list(VIT))
     ap.add_argument("--image-size", type=int, default=224)
@@ -447,6 +527,8 @@ def main():
         return run_clip(args)
     if args.workload == "text":
         return run_text(args)
+    if args.workload == "tokenize":
+        return run_tokenize(args)
     return run_vit(args)
 
 

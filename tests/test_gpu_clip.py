@@ -59,6 +59,10 @@ def test_clip_host_call_and_batch_invariance(cuda):
     dev_out = m(x.to(cuda))
     assert torch.equal(m.encode_host(x.pin_memory()), dev_out.cpu())
     assert torch.equal(m(x[4:6].to(cuda)), dev_out[4:6])
+    batches = [W.frames(4, c["image_size"], seed=30 + i).pin_memory() for i in range(5)]
+    want = [m(b.to(cuda)).cpu() for b in batches]
+    got = [o.clone() for o in m.encode_host_stream(iter(batches))]
+    assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, want))
 
 
 # ---- text tower (phrase bank) ------------------------------------------------------------------------------------------

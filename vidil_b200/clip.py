@@ -192,6 +192,39 @@ class CLIPVisionB200(nn.Module):
         return out
 
 
+    @torch.no_grad()
+    def encode_host_stream(self, batches, outs=None):
+        """Pipelined host API (vidil_encoder_host_submit / _wait, two slots): `batches` is an iterable of CPU fp32 frame
+        tensors [B,3,S,S] (pinned for full PCIe rate); yields one CPU tensor of image_embeds [B, projection_dim] per batch,
+        in order.  Batch k+1's H2D runs during batch k's forward."""
+        c = self.cfg
+        dev = next(self.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("vidil_b200: the module must be moved to a CUDA device first")
+        with torch.cuda.device(dev):
+            enc = self._ensure_packed()
+            pending = []
+            k = 0
+            for frames in batches:
+                if frames.is_cuda:
+                    raise RuntimeError("encode_host_stream takes host tensors")
+                _check_frames(frames, c["image_size"])
+                frames = frames.contiguous().float()
+                slot = k & 1
+                if len(pending) == 2:
+                    s0, o0, _ = pending.pop(0)
+                    enc.host_wait(s0)
+                    yield o0
+                out = outs[slot] if outs is not None else torch.empty(frames.shape[0], c["projection_dim"],
+                                                                      dtype=torch.float32, pin_memory=True)
+                enc.host_submit(frames, out, slot, dev)
+                pending.append((slot, out, frames))
+                k += 1
+            for s0, o0, _ in pending:
+                enc.host_wait(s0)
+                yield o0
+
+
 class CLIPTextB200(nn.Module):
     """CLIP text tower + text_projection on the native path (vidil_clip_text_forward).  Parameters use transformers'
     CLIPModel key names (`text_model.*`, `text_projection.weight`)."""
