@@ -10,6 +10,7 @@
  *   run_visual_tokenization.py:276,306   image_embeds @ text_embeds.t(); np.argsort(...)[::-1][:k]
  *                                                                    -> vidil_sim_topk
  *   run_visual_tokenization.py:84-96     CLIPModel(**inputs).text_embeds  -> vidil_clip_text_forward
+ *   run_video_CapFilt.py:128-137         process_frame (PIL resize + ToTensor + Normalize) -> vidil_preprocess_frames
  *
  * Conventions
  *   - Every function returns 0 on success, non-zero on failure; vidil_last_error() then returns a
@@ -145,6 +146,16 @@ int32_t vidil_text_encoder_check_loaded(const vidil_text_encoder* enc);
 size_t  vidil_text_encoder_workspace_bytes(const vidil_text_encoder* enc, int32_t batch, int32_t seq_len);
 int32_t vidil_clip_text_forward(vidil_text_encoder* enc, const int32_t* input_ids, const int32_t* eos_pos, int32_t batch,
                                 int32_t seq_len, float* out_embeds, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- frame pre-processing (run_video_CapFilt.py:128-137 process_frame) ------------------------- */
+/* frames_u8: device uint8 [B, H, W, 3] (decoded RGB frames, HWC) -> out: device fp32 [B, 3, S, S]:
+ * Pillow's antialiased BICUBIC resize to S x S reproduced bit for bit (22-bit fixed-point weights, uint8 intermediate
+ * between the horizontal and the vertical pass), then x / 255 and (x - mean) / std in float32 as torchvision's ToTensor
+ * and Normalize do.  mean3 / std3 are HOST pointers to 3 floats. */
+size_t  vidil_preprocess_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size);
+int32_t vidil_preprocess_frames(const uint8_t* frames_u8, int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size,
+                                const float* mean3, const float* std3, float* out, void* workspace, size_t workspace_bytes,
+                                void* stream);
 
 /* ---- per-kernel-class device timing (bench.py's roofline figures) ---------------------------- */
 /* With profiling on, every kernel a forward enqueues is bracketed by CUDA events on the caller's stream.

@@ -17,6 +17,8 @@ stored):
                           last_hidden_state
   clip_text_tiny.npz      transformers.CLIPModel text path (D=128, 2 layers, 12 tokens), 5 phrases: text_embeds + pooled
   clip_text_large14.npz   transformers.CLIPModel text tower of clip-vit-large-patch14's shape, 3 phrases of 20 tokens
+  preprocess.json         torchvision/PIL process_frame (run_video_CapFilt.py:128-137) on synthetic uint8 frames of 7 geometries:
+                          SHA-256 of the float32 output + a 5x5 sample per channel
   tokenization.json       sim top-k indices computed with the reference's own lines (:276, :306), and
                           aggregate_frame_tokens executed from run_visual_tokenization.py:173-187
   sharding.json           per-rank slices from the reference's partition formula for several (n, world) pairs
@@ -118,6 +120,33 @@ def golden_clip_text(name, batch, seq_len, fname):
     _save(fname, text_embeds=emb.numpy(), pooled=out.pooler_output.numpy())
 
 
+PREPROCESS_CASES = [(240, 320, 224), (360, 640, 384), (224, 224, 224), (100, 150, 224), (480, 270, 224), (7, 9, 32),
+                    (720, 1280, 224)]
+
+
+def golden_preprocess():
+    """The reference's process_frame lines executed as they stand (run_video_CapFilt.py:128-137): torchvision ToPILImage ->
+    Resize BICUBIC -> ToTensor -> Normalize.  Outputs are stored as SHA-256 digests (bit-exactness) plus a small sample."""
+    import hashlib
+
+    from torchvision import transforms
+    from torchvision.transforms.functional import InterpolationMode
+    cases = []
+    for (H, Wd, S) in PREPROCESS_CASES:
+        frames = W.u8_frames(2, H, Wd, seed=H + Wd).numpy()
+        transform = transforms.Compose([
+            transforms.ToPILImage(),
+            transforms.Resize((S, S), interpolation=InterpolationMode.BICUBIC),
+            transforms.ToTensor(),
+            transforms.Normalize((0.48145466, 0.4578275, 0.40821073), (0.26862954, 0.26130258, 0.27577711))])
+        out = np.stack([transform(f).numpy() for f in frames])
+        cases.append({"H": H, "W": Wd, "S": S, "sha256": hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest(),
+                      "sample": out[:, :, ::max(1, S // 4), ::max(1, S // 4)].tolist()})
+    with open(os.path.join(GOLDEN_DIR, "preprocess.json"), "w") as f:
+        json.dump(cases, f)
+    print("wrote preprocess.json")
+
+
 def golden_tokenization():
     # similarity + per-frame argsort exactly as run_visual_tokenization.py:276,298-306
     F_, T, D, k = 64, 1000, 768, 5
@@ -175,6 +204,7 @@ def main():
     golden_clip("large14", 1, 8, "clip_large14.npz")
     golden_clip_text("tiny", 5, 12, "clip_text_tiny.npz")
     golden_clip_text("large14", 3, 20, "clip_text_large14.npz")
+    golden_preprocess()
     golden_tokenization()
     golden_sharding()
 

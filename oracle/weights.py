@@ -180,3 +180,19 @@ def unit_rows(n: int, d: int, seed: int) -> torch.Tensor:
     a = rng.standard_normal(size=(n, d), dtype=np.float32)
     a /= np.linalg.norm(a, axis=1, keepdims=True)
     return torch.from_numpy(a)
+
+
+def u8_frames(batch: int, height: int, width: int, seed: int = 0) -> torch.Tensor:
+    """Synthetic decoded video frames: uint8 [B, H, W, 3] with smooth structure, noise and saturated patches (so that the
+    bicubic overshoot clips at both ends)."""
+    rng = np.random.Generator(np.random.PCG64(5_000_011 + seed))
+    yy, xx = np.mgrid[0:height, 0:width].astype(np.float32)
+    out = np.empty((batch, height, width, 3), dtype=np.uint8)
+    for b in range(batch):
+        f = rng.uniform(0.01, 0.2, size=(3, 2)).astype(np.float32)
+        img = np.stack([127.5 + 100 * np.sin(f[c, 0] * xx + b) * np.cos(f[c, 1] * yy) for c in range(3)], axis=-1)
+        img += rng.normal(0, 25, size=img.shape).astype(np.float32)
+        img[: height // 8, : width // 4] = 255
+        img[-(height // 8):, -(width // 4):] = 0
+        out[b] = np.clip(img, 0, 255).astype(np.uint8)
+    return torch.from_numpy(out)

@@ -1,0 +1,58 @@
+"""Frame pre-processing on a B200 (vidil_preprocess_frames): byte / integer work, so the bar is bit-exactness against the
+oracle and against the committed outputs of the reference's own process_frame lines (PIL + torchvision)."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import preprocess_oracle, weights as W
+from vidil_b200 import preprocess
+
+pytestmark = pytest.mark.gpu
+
+
+def test_preprocess_matches_pil_fixture_bit_for_bit(cuda, golden_dir):
+    for case in json.load(open(os.path.join(golden_dir, "preprocess.json"))):
+        frames = W.u8_frames(2, case["H"], case["W"], seed=case["H"] + case["W"])
+        out = preprocess.process_frames(frames.to(cuda), case["S"]).cpu().numpy()
+        assert out.shape == (2, 3, case["S"], case["S"]) and out.dtype == np.float32
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == case["sha256"], (case["H"], case["W"])
+
+
+@pytest.mark.parametrize("H,Wd,S,B", [(240, 320, 224, 5), (33, 17, 224, 2), (1080, 1920, 224, 1), (224, 224, 384, 3), (1, 1, 16, 2)])
+def test_preprocess_equals_oracle(cuda, H, Wd, S, B):
+    frames = W.u8_frames(B, H, Wd, seed=3)
+    got = preprocess.process_frames(frames.to(cuda), S).cpu().numpy()
+    want = np.stack([preprocess_oracle.process_frame(f, S) for f in frames.numpy()])
+    assert np.array_equal(got, want)
+
+
+def test_process_frame_signature_and_batch(cuda):
+    """The reference's call: process_frame(frame, config, device) per frame (run_video_CapFilt.py:161); a 256-frame batch
+    gives the same rows as 256 single calls."""
+    frames = W.u8_frames(256, 120, 160, seed=9)
+    batch = preprocess.process_frames(frames.to(cuda), 224)
+    one = preprocess.process_frame(frames[17].numpy(), {"image_size": 224}, cuda)
+    assert tuple(one.shape) == (3, 224, 224) and one.is_cuda and torch.equal(one, batch[17])
+    assert torch.equal(preprocess.process_frames(frames[:0].to(cuda), 224), torch.empty(0, 3, 224, 224, device=cuda))
+    with pytest.raises(RuntimeError, match="CUDA"):
+        preprocess.process_frames(frames, 224)
+    with pytest.raises(RuntimeError, match="uint8"):
+        preprocess.process_frames(frames.float().to(cuda), 224)
+
+
+def test_preprocessed_frames_feed_the_encoder(cuda):
+    """uint8 frames -> process_frames -> ViT: the chain the CapFilt driver runs per video."""
+    from vidil_b200.vision_transformer import VisionTransformer
+    m = VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, compute_dtype="fp16")
+    m.load_state_dict(W.vit_state_dict("tiny", 32, seed=0))
+    m = m.to(cuda).eval()
+    frames = W.u8_frames(4, 60, 80, seed=2)
+    x = preprocess.process_frames(frames.to(cuda), 32)
+    from oracle import vit_oracle
+    ref = vit_oracle.vit_forward(W.vit_state_dict("tiny", 32, seed=0), torch.from_numpy(
+        np.stack([preprocess_oracle.process_frame(f, 32) for f in frames.numpy()])), 2)
+    assert (m(x).cpu() - ref).abs().max() < 2e-2

@@ -8,7 +8,7 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import clip_oracle, clip_text_oracle, tokenization_oracle, vit_oracle, weights as W
+from oracle import clip_oracle, clip_text_oracle, preprocess_oracle, tokenization_oracle, vit_oracle, weights as W
 
 # Same ATen ops in the same order as the reference => equal up to thread-count-dependent reduction order.
 TOL = 2e-4
@@ -66,6 +66,28 @@ def test_clip_text_oracle_matches_transformers_fixture(golden_dir, name, batch, 
                                                 c["num_attention_heads"], c["eos_token_id"])
     assert np.abs(emb.numpy() - g["text_embeds"]).max() < 1e-5
     assert np.allclose(np.linalg.norm(emb.numpy(), axis=1), 1.0, atol=1e-5)
+
+
+def test_preprocess_oracle_is_bit_identical_to_pil_fixture(golden_dir):
+    """Index/byte work: the restatement of Pillow's fixed-point resize + ToTensor + Normalize must reproduce the outputs of
+    the reference's own process_frame lines exactly (SHA-256 of the float32 bytes)."""
+    import hashlib
+    for case in json.load(open(os.path.join(golden_dir, "preprocess.json"))):
+        frames = W.u8_frames(2, case["H"], case["W"], seed=case["H"] + case["W"]).numpy()
+        out = np.stack([preprocess_oracle.process_frame(f, case["S"]) for f in frames])
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == case["sha256"], case["H"]
+        st = max(1, case["S"] // 4)
+        assert np.array_equal(out[:, :, ::st, ::st], np.asarray(case["sample"], dtype=np.float32))
+
+
+def test_preprocess_oracle_vs_live_pil():
+    torchvision = pytest.importorskip("torchvision")
+    from torchvision import transforms
+    from torchvision.transforms.functional import InterpolationMode
+    frame = W.u8_frames(1, 97, 131, seed=1).numpy()[0]
+    t = transforms.Compose([transforms.ToPILImage(), transforms.Resize((64, 64), interpolation=InterpolationMode.BICUBIC),
+                            transforms.ToTensor(), transforms.Normalize(preprocess_oracle.MEAN, preprocess_oracle.STD)])
+    assert np.array_equal(t(frame).numpy(), preprocess_oracle.process_frame(frame, 64))
 
 
 def test_topk_oracle_matches_reference_lines(golden_dir):

@@ -77,6 +77,9 @@ SIGNATURES = {
     "vidil_text_encoder_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
     "vidil_clip_text_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
                                           c_void_p]),
+    "vidil_preprocess_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "vidil_preprocess_frames": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_float), POINTER(c_float),
+                                          c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_encoder_set_profiling": (c_int32, [c_void_p, c_int32]),
     "vidil_encoder_read_profile": (c_int32, [c_void_p, POINTER(KernelStats)]),
     "vidil_encoder_host_scratch_bytes": (c_size_t, [c_void_p, c_int32]),

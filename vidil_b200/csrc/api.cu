@@ -827,6 +827,26 @@ int32_t vidil_sim_topk(const float* img, const float* bank, int32_t F, int32_t T
     return topk_rerank_run(scores, ld, img, bank, F, T, D, k, out_scores, out_idx, s);
 }
 
+// ---- frame pre-processing -------------------------------------------------------------------------------
+size_t vidil_preprocess_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size) {
+    return preprocess_workspace_bytes(batch, in_h, in_w, out_size);
+}
+
+int32_t vidil_preprocess_frames(const uint8_t* frames_u8, int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size,
+                                const float* mean3, const float* std3, float* out, void* workspace, size_t workspace_bytes,
+                                void* stream) {
+    if (frames_u8 == nullptr || mean3 == nullptr || std3 == nullptr || out == nullptr || workspace == nullptr) {
+        set_error("vidil_preprocess_frames: null argument");
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    return preprocess_run(frames_u8, batch, in_h, in_w, out_size, mean3, std3, out, workspace, workspace_bytes,
+                          reinterpret_cast<cudaStream_t>(stream));
+}
+
 void vidil_debug_set_attention_trace(void* dev_buf) { attention_set_trace(reinterpret_cast<long long*>(dev_buf)); }
 
 // ---- operator-level entry points --------------------------------------------------------------------

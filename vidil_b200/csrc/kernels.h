@@ -122,6 +122,13 @@ int gather_rows_run(const float* in, const int32_t* idx, float* out, int B, int 
 int uncast_run(const void* in, float* out, DType dt, int64_t n, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------
+// Frame pre-processing (run_video_CapFilt.py:128-137): uint8 HWC -> PIL-identical bicubic resize -> /255 -> normalise.
+// ---------------------------------------------------------------------------------------
+size_t preprocess_workspace_bytes(int B, int H, int W, int S);
+int preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const float* mean, const float* stdv, float* out,
+                   void* workspace, size_t workspace_bytes, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------
 // Top-k of each row of an fp32 score matrix with exact fp32 re-ranking of the candidates
 // (run_visual_tokenization.py:276,306).
 // ---------------------------------------------------------------------------------------

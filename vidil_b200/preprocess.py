@@ -1,0 +1,53 @@
+"""Drop-in for the reference's per-frame pre-processing (run_video_CapFilt.py:128-137 `process_frame`).
+
+The reference converts every decoded frame to a PIL image on the host, resizes it with PIL's bicubic filter, converts to
+a float tensor, normalises and copies it to the GPU — one frame at a time (:161).  Here the decoded uint8 frames go to the
+GPU as they are (a third to a quarter of the bytes of the float tensor) and `vidil_preprocess_frames` produces the same
+numbers there, bit for bit, for a whole batch at once.  No CPU path.
+"""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+MEAN = (0.48145466, 0.4578275, 0.40821073)   # run_video_CapFilt.py:133
+STD = (0.26862954, 0.26130258, 0.27577711)
+
+
+@torch.no_grad()
+def process_frames(frames_u8: torch.Tensor, image_size: int, mean=MEAN, std=STD, out: torch.Tensor | None = None) -> torch.Tensor:
+    """frames_u8: uint8 [B, H, W, 3] on a CUDA device -> float32 [B, 3, S, S], identical to stacking the reference's
+    process_frame over the frames."""
+    if not frames_u8.is_cuda:
+        raise RuntimeError("vidil_b200: frames must be on a CUDA device (no CPU path exists)")
+    if frames_u8.dtype != torch.uint8 or frames_u8.dim() != 4 or frames_u8.shape[-1] != 3:
+        raise RuntimeError(f"expected uint8 frames of shape [B, H, W, 3], got {frames_u8.dtype} {tuple(frames_u8.shape)}")
+    lib = _lib.load()
+    x = frames_u8.contiguous()
+    B, H, W, _ = x.shape
+    S = int(image_size)
+    if out is None:
+        out = torch.empty(B, 3, S, S, dtype=torch.float32, device=x.device)
+    if B == 0:
+        return out
+    with torch.cuda.device(x.device):
+        need = lib.vidil_preprocess_workspace_bytes(B, H, W, S)
+        ws = torch.empty(need + 1024, dtype=torch.uint8, device=x.device)
+        off = (-ws.data_ptr()) % 1024
+        m = (ctypes.c_float * 3)(*[float(v) for v in mean])
+        s = (ctypes.c_float * 3)(*[float(v) for v in std])
+        st = lib.vidil_preprocess_frames(x.data_ptr(), B, H, W, S, m, s, out.data_ptr(), ws.data_ptr() + off, need,
+                                         torch.cuda.current_stream().cuda_stream)
+        _lib.check(st, "vidil_preprocess_frames")
+    return out
+
+
+def process_frame(frame, config, device):
+    """Same arguments and result as run_video_CapFilt.py:128-137: one decoded frame (numpy or tensor, [H, W, 3] uint8)
+    -> normalised float tensor [3, S, S] on `device`."""
+    t = torch.from_numpy(np.ascontiguousarray(frame)) if isinstance(frame, np.ndarray) else frame
+    return process_frames(t.to(device)[None], config["image_size"])[0]
