@@ -273,6 +273,19 @@ def run_vit(args):
     torch.cuda.synchronize()
     e2e_blocking_fps = world * B * 3 / max_over_ranks(time.perf_counter() - t0)
 
+    # ---- the same from DECODED frames: uint8 320x240 RGB in pinned memory -> H2D -> resize/normalise on the GPU -> ViT
+    #      -> D2H of the tokens (vidil_b200.preprocess.encode_u8_stream); what a video pipeline actually feeds
+    from vidil_b200 import preprocess as vpre
+    u8_in = [torch.randint(0, 256, (B, 240, 320, 3), dtype=torch.uint8).pin_memory() for _ in range(2)]
+    for o in vpre.encode_u8_stream(model, (u8_in[i & 1] for i in range(3)), args.image_size, outs=host_outs):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    for o in vpre.encode_u8_stream(model, (u8_in[i & 1] for i in range(K)), args.image_size, outs=host_outs):
+        checksum += float(o[0, 0, 0])
+    torch.cuda.synchronize()
+    e2e_u8_fps = world * B * K / max_over_ranks(time.perf_counter() - t0)
+
     # ---- the path's one collective: all-gather of per-rank result rows (JSON), rank-0 merge --------------------------
     t0 = time.perf_counter()
     rows = {f"rank{rank}_frame{i}": {"cls_l1": float(host_out[i, 0].abs().sum())} for i in range(0, B, 32)}
@@ -298,7 +311,10 @@ def run_vit(args):
                 "d2h_bytes_per_step": B * tokens * D * 4, "ms_per_step": e2e_s / K * 1e3,
                 "api": "VisionTransformer.encode_host_stream -> vidil_encoder_host_submit/_wait (pinned host buffers, "
                        "copies overlapped with the neighbouring steps' forwards)",
-                "blocking_call_value": e2e_blocking_fps, "checksum": checksum},
+                "blocking_call_value": e2e_blocking_fps, "checksum": checksum,
+                "from_uint8_frames": {"value": e2e_u8_fps, "unit": "frames/s", "h2d_bytes_per_step": B * 240 * 320 * 3,
+                                      "note": "decoded 320x240 uint8 frames in pinned memory; PIL-identical resize + "
+                                              "normalise on the GPU (vidil_preprocess_frames) inside the timed region"}},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (patch-embed, qkv, proj, fc1, fc2: "
                                                   f"{g['launches'] // K} launches per step)",

@@ -56,3 +56,14 @@ def test_preprocessed_frames_feed_the_encoder(cuda):
     ref = vit_oracle.vit_forward(W.vit_state_dict("tiny", 32, seed=0), torch.from_numpy(
         np.stack([preprocess_oracle.process_frame(f, 32) for f in frames.numpy()])), 2)
     assert (m(x).cpu() - ref).abs().max() < 2e-2
+
+
+def test_encode_u8_stream_equals_the_step_by_step_path(cuda):
+    from vidil_b200.vision_transformer import VisionTransformer
+    m = VisionTransformer(img_size=32, patch_size=16, embed_dim=128, depth=2, num_heads=2, compute_dtype="bf16")
+    m.load_state_dict(W.vit_state_dict("tiny", 32, seed=0))
+    m = m.to(cuda).eval()
+    batches = [W.u8_frames(3, 48, 64, seed=40 + i).pin_memory() for i in range(5)]
+    want = [m(preprocess.process_frames(b.to(cuda), 32)).cpu() for b in batches]
+    got = [o.clone() for o in preprocess.encode_u8_stream(m, iter(batches), 32)]
+    assert len(got) == 5 and all(torch.equal(a, b) for a, b in zip(got, want))

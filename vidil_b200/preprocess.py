@@ -51,3 +51,57 @@ def process_frame(frame, config, device):
     -> normalised float tensor [3, S, S] on `device`."""
     t = torch.from_numpy(np.ascontiguousarray(frame)) if isinstance(frame, np.ndarray) else frame
     return process_frames(t.to(device)[None], config["image_size"])[0]
+
+
+@torch.no_grad()
+def encode_u8_stream(visual_encoder, batches_u8, image_size: int, outs=None):
+    """Decoded frames in, tokens out, nothing else on the host: `batches_u8` is an iterable of pinned CPU uint8 tensors
+    [B, H, W, 3]; each is copied to the device on a side stream, resized / normalised there (process_frames), encoded by
+    `visual_encoder` (a vidil_b200 VisionTransformer) and its [B, N+1, D] tokens copied back to pinned host memory on the
+    side stream.  Batch k+1's upload and batch k-1's download overlap batch k's kernels.  Yields one CPU tensor per batch,
+    in order; with `outs` (two pinned tensors) the yielded tensor is only valid until two batches later."""
+    dev = visual_encoder.cls_token.device
+    if dev.type != "cuda":
+        raise RuntimeError("vidil_b200: the module must be moved to a CUDA device first")
+    with torch.cuda.device(dev):
+        main = torch.cuda.current_stream()
+        side_in, side_out = torch.cuda.Stream(), torch.cuda.Stream()
+        pending = []   # (event, host_out, keep-alive tensors)
+        dev_u8 = [None, None]
+        freed = [None, None]   # event: the kernels that read dev_u8[slot] have run
+        k = 0
+        for frames in batches_u8:
+            if frames.is_cuda or frames.dtype != torch.uint8:
+                raise RuntimeError("encode_u8_stream takes host uint8 tensors [B, H, W, 3]")
+            slot = k & 1
+            if len(pending) == 2:
+                ev, o, _ = pending.pop(0)
+                ev.synchronize()
+                yield o
+            with torch.cuda.stream(side_in):
+                if freed[slot] is not None:
+                    side_in.wait_event(freed[slot])
+                if dev_u8[slot] is None or dev_u8[slot].shape != frames.shape:
+                    dev_u8[slot] = torch.empty(frames.shape, dtype=torch.uint8, device=dev)
+                dev_u8[slot].copy_(frames, non_blocking=True)
+                uploaded = torch.cuda.Event()
+                uploaded.record(side_in)
+            main.wait_event(uploaded)
+            x = process_frames(dev_u8[slot], image_size)
+            freed[slot] = torch.cuda.Event()
+            freed[slot].record(main)
+            tokens = visual_encoder(x)
+            done = torch.cuda.Event()
+            done.record(main)
+            host = outs[slot] if outs is not None else torch.empty(tokens.shape, dtype=torch.float32, pin_memory=True)
+            with torch.cuda.stream(side_out):
+                side_out.wait_event(done)
+                host.copy_(tokens, non_blocking=True)
+                copied = torch.cuda.Event()
+                copied.record(side_out)
+            tokens.record_stream(side_out)
+            pending.append((copied, host, (frames, x)))
+            k += 1
+        for ev, o, _ in pending:
+            ev.synchronize()
+            yield o
