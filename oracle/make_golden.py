@@ -17,6 +17,8 @@ stored):
                           last_hidden_state
   clip_text_tiny.npz      transformers.CLIPModel text path (D=128, 2 layers, 12 tokens), 5 phrases: text_embeds + pooled
   clip_text_large14.npz   transformers.CLIPModel text tower of clip-vit-large-patch14's shape, 3 phrases of 20 tokens
+  med_tiny.npz            reference med.py (D=128, 2 layers): teacher-forced decoder logits, cached one-token steps, ITM logits
+  med_base_l.npz          reference med.py at BERT-base shape with ViT-L tokens (197 x 1024): the same, every 97th vocabulary entry
   preprocess.json         torchvision/PIL process_frame (run_video_CapFilt.py:128-137) on synthetic uint8 frames of 7 geometries:
                           SHA-256 of the float32 output + a 5x5 sample per channel
   tokenization.json       sim top-k indices computed with the reference's own lines (:276, :306), and
@@ -120,6 +122,40 @@ def golden_clip_text(name, batch, seq_len, fname):
     _save(fname, text_embeds=emb.numpy(), pooled=out.pooler_output.numpy())
 
 
+@torch.no_grad()
+def golden_med(name, batch, seq_len, n_img, vocab_stride, fname):
+    """Reference med.py executed on seeded inputs: teacher-forced decoder logits, one cached decode step, and the ITM
+    logits of padded captions (the three ways run_video_CapFilt.py drives the text stack)."""
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(batch, n_img, c["encoder_width"], seed=0)
+    ones = torch.ones(batch, n_img, dtype=torch.long)
+    sd = W.med_state_dict(name, "decoder", seed=0)
+    dec, _ = rs.build_reference_med(name, "decoder", sd)
+    ids, _ = W.caption_ids(name, batch, seq_len, seed=0, min_words=seq_len - 2)
+    ids[:, 0] = sp["bos"]
+    full = dec(ids, attention_mask=torch.ones_like(ids), encoder_hidden_states=enc, encoder_attention_mask=ones,
+               return_dict=True, use_cache=True, is_decoder=True)
+    # cached path exactly as generate() drives it: prompt first, then one token at a time (med.py:929-948)
+    o = dec(ids[:, :4], attention_mask=torch.ones_like(ids[:, :4]), encoder_hidden_states=enc, encoder_attention_mask=ones,
+            return_dict=True, use_cache=True, is_decoder=True)
+    step_logits = []
+    for t in range(4, seq_len):
+        o = dec(ids[:, t:t + 1], attention_mask=torch.ones_like(ids[:, :t + 1]), encoder_hidden_states=enc,
+                encoder_attention_mask=ones, past_key_values=o.past_key_values, return_dict=True, use_cache=True, is_decoder=True)
+        step_logits.append(o.logits[:, 0])
+    vs = np.arange(0, c["vocab_size"], vocab_stride)
+    arrays = dict(vocab=vs, logits=full.logits[:, :, vs].numpy(), step_logits=torch.stack(step_logits, 1)[:, :, vs].numpy(),
+                  logits_std=np.float32(full.logits.std().item()))
+    sdi = W.med_state_dict(name, "itm", seed=0)
+    enc_m, head = rs.build_reference_med(name, "itm", sdi)
+    cap, mask = W.caption_ids(name, batch, seq_len, seed=1)
+    cap[:, 0] = sp["enc"]
+    out = enc_m(cap, attention_mask=mask, encoder_hidden_states=enc, encoder_attention_mask=ones, return_dict=True)
+    arrays["itm_hidden_cls"] = out.last_hidden_state[:, 0].numpy()
+    arrays["itm_logits"] = head(out.last_hidden_state[:, 0, :]).numpy()
+    _save(fname, **arrays)
+
+
 PREPROCESS_CASES = [(240, 320, 224), (360, 640, 384), (224, 224, 224), (100, 150, 224), (480, 270, 224), (7, 9, 32),
                     (720, 1280, 224)]
 
@@ -204,6 +240,8 @@ def main():
     golden_clip("large14", 1, 8, "clip_large14.npz")
     golden_clip_text("tiny", 5, 12, "clip_text_tiny.npz")
     golden_clip_text("large14", 3, 20, "clip_text_large14.npz")
+    golden_med("tiny", 3, 9, 5, 1, "med_tiny.npz")
+    golden_med("base_l", 2, 8, 197, 97, "med_base_l.npz")
     golden_preprocess()
     golden_tokenization()
     golden_sharding()

@@ -1,0 +1,252 @@
+"""CPU restatement of the reference's `models/med.py` text stack on the CapFilt path — the parity oracle for
+the caption decoder (BLIP_Decoder.generate, models/blip.py:127-167) and the ITM filter head
+(BLIP_ITM.forward, models/blip_itm.py:41-58).
+
+TEST INFRASTRUCTURE.  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+leg may import this module; the product path (vidil_b200/) never does.
+
+Parity status
+  * The network arithmetic (embeddings, BertLayer with self- and cross-attention, LM head, ITM head) is pinned
+    against *outputs of the reference itself*: oracle/make_golden.py imports the unmodified
+    /root/reference/models/med.py (behind the import shims SURVEY.md §8c lists), runs it on seeded inputs and
+    commits the results under tests/golden/med_*.npz; tests/test_oracle_golden.py checks this file against them.
+  * Beam search: **parity unpinned.**  The reference delegates to `transformers` `generate()` (un-vendored,
+    unpinned, `docker/requirements.txt:9`; med.py is "based on v4.15.0"), which cannot drive med.py under the
+    installed transformers 5.5.  `beam_search` below restates the published v4.15.0 algorithm
+    (`GenerationMixin.beam_search`, `BeamSearchScorer.process/finalize`, `BeamHypotheses.add/is_done`,
+    `MinLengthLogitsProcessor`) with the arguments of the reference's call site (blip.py:150-158,
+    run_video_CapFilt.py:102: num_beams 3, max_length 20, min_length 5, length_penalty 1.0, early_stopping False,
+    repetition_penalty 1.0) and is anchored on that call site only.
+
+Plain functional tensor arithmetic on a parameter dict with the reference's state_dict keys.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+def embeddings(sd: dict, pre: str, input_ids: torch.Tensor, past_len: int, eps: float) -> torch.Tensor:
+    """BertEmbeddings.forward, med.py:74-96: word + absolute position -> LayerNorm (no token-type term)."""
+    T = input_ids.shape[1]
+    x = sd[pre + "embeddings.word_embeddings.weight"][input_ids]                              # :88
+    x = x + sd[pre + "embeddings.position_embeddings.weight"][past_len:past_len + T][None]     # :85,:93-94
+    D = x.shape[-1]
+    return F.layer_norm(x, (D,), sd[pre + "embeddings.LayerNorm.weight"], sd[pre + "embeddings.LayerNorm.bias"], eps)
+
+
+def _heads(x: torch.Tensor, H: int) -> torch.Tensor:
+    B, T, D = x.shape
+    return x.view(B, T, H, D // H).permute(0, 2, 1, 3)                                        # transpose_for_scores :141-144
+
+
+def attention_block(sd: dict, p: str, x: torch.Tensor, kv_src: torch.Tensor, add_mask, H: int, eps: float, past=None):
+    """BertAttention = BertSelfAttention (med.py:146-232) + BertSelfOutput (:235-246).
+    `kv_src` is x for self-attention, the image tokens for cross-attention; `past` = (K, V) of earlier positions."""
+    q = _heads(F.linear(x, sd[p + "self.query.weight"], sd[p + "self.query.bias"]), H)
+    k = _heads(F.linear(kv_src, sd[p + "self.key.weight"], sd[p + "self.key.bias"]), H)
+    v = _heads(F.linear(kv_src, sd[p + "self.value.weight"], sd[p + "self.value.bias"]), H)
+    if past is not None:
+        k = torch.cat([past[0], k], dim=2)                                                     # :173-174
+        v = torch.cat([past[1], v], dim=2)
+    s = q @ k.transpose(-1, -2) / math.sqrt(q.shape[-1])                                       # :184,:202
+    if add_mask is not None:
+        s = s + add_mask                                                                       # :205
+    pr = s.softmax(dim=-1)                                                                     # :208
+    ctx = (pr @ v).permute(0, 2, 1, 3).reshape(x.shape)                                        # :222-226
+    out = F.linear(ctx, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
+    D = x.shape[-1]
+    out = F.layer_norm(out + x, (D,), sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], eps)  # :245
+    return out, (k, v)
+
+
+def layer(sd: dict, p: str, x, self_mask, enc, H: int, eps: float, past=None, mode: str = "multimodal"):
+    """BertLayer.forward, med.py:333-384: self-attention -> (cross-attention) -> intermediate(GELU erf) -> output."""
+    x, present = attention_block(sd, p + "attention.", x, x, self_mask, H, eps, past)
+    if mode == "multimodal":
+        x, _ = attention_block(sd, p + "crossattention.", x, enc, None, H, eps)                # all-ones image mask
+    h = F.gelu(F.linear(x, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))   # :297-303
+    h = F.linear(h, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
+    D = x.shape[-1]
+    x = F.layer_norm(h + x, (D,), sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], eps)   # :316
+    return x, present
+
+
+def self_mask(attention_mask: torch.Tensor, T: int, past_len: int, causal: bool) -> torch.Tensor:
+    """get_extended_attention_mask, med.py:609-668: additive 0 / -10000 mask [B,1,T,past+T]."""
+    am = attention_mask.to(torch.float32)
+    if causal:
+        ids = torch.arange(T)
+        cm = (ids[None, :] <= ids[:, None]).to(torch.float32)                                  # :636
+        if past_len:
+            cm = torch.cat([torch.ones(T, past_len), cm], dim=-1)                              # :641-649
+        ext = cm[None, None] * am[:, None, None, :]                                            # :651
+    else:
+        ext = am[:, None, None, :]                                                             # :653
+    return (1.0 - ext) * -10000.0                                                              # :667
+
+
+def bert_forward(sd: dict, pre: str, input_ids, attention_mask, enc, H: int, depth: int, eps: float = 1e-12,
+                 causal: bool = False, past=None, mode: str = "multimodal"):
+    """BertModel.forward, med.py:700-809 (add_pooling_layer=False).  Returns (last_hidden_state, presents)."""
+    B, T = input_ids.shape
+    past_len = 0 if past is None else past[0][0].shape[2]
+    if attention_mask is None:
+        attention_mask = torch.ones(B, past_len + T)
+    x = embeddings(sd, pre, input_ids, past_len, eps)
+    m = self_mask(attention_mask, T, past_len, causal)
+    presents = []
+    for i in range(depth):
+        x, pkv = layer(sd, f"{pre}encoder.layer.{i}.", x, m, enc, H, eps, None if past is None else past[i], mode)
+        presents.append(pkv)
+    return x, presents
+
+
+def lm_head(sd: dict, pre: str, x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """BertOnlyMLMHead, med.py:501-541: dense -> GELU -> LayerNorm -> decoder (+ output-only bias)."""
+    c = pre + "cls.predictions."
+    h = F.gelu(F.linear(x, sd[c + "transform.dense.weight"], sd[c + "transform.dense.bias"]))
+    D = h.shape[-1]
+    h = F.layer_norm(h, (D,), sd[c + "transform.LayerNorm.weight"], sd[c + "transform.LayerNorm.bias"], eps)
+    return F.linear(h, sd[c + "decoder.weight"], sd[c + "bias"])
+
+
+def decoder_logits(sd: dict, pre: str, input_ids, image_embeds, H: int, depth: int, past=None):
+    """BertLMHeadModel.forward, med.py:871-893 with is_decoder=True: logits for every input position."""
+    x, presents = bert_forward(sd, pre + "bert.", input_ids, None, image_embeds, H, depth, causal=True, past=past)
+    return lm_head(sd, pre, x), presents
+
+
+def itm_logits(sd: dict, image_embeds, input_ids, attention_mask, H: int, depth: int) -> torch.Tensor:
+    """BLIP_ITM.forward(match_head='itm'), blip_itm.py:49-57: multimodal encoder -> itm_head on the [CLS]/[ENC] row."""
+    x, _ = bert_forward(sd, "text_encoder.", input_ids, attention_mask, image_embeds, H, depth, causal=False)
+    return F.linear(x[:, 0, :], sd["itm_head.weight"], sd["itm_head.bias"])
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# Beam search — transformers v4.15.0 semantics (restated; see the header).
+# ----------------------------------------------------------------------------------------------------------------------
+class _BeamHyps:
+    """BeamHypotheses (v4.15.0 generation_beam_search.py): keeps the num_beams best finished hypotheses."""
+
+    def __init__(self, num_beams: int, length_penalty: float):
+        self.num_beams, self.length_penalty = num_beams, length_penalty
+        self.beams: list = []
+        self.worst_score = 1e9
+
+    def add(self, hyp: list, sum_logprobs: float) -> None:
+        score = sum_logprobs / (len(hyp) ** self.length_penalty)
+        if len(self.beams) < self.num_beams or score > self.worst_score:
+            self.beams.append((score, hyp))
+            if len(self.beams) > self.num_beams:
+                ranked = sorted([(s, idx) for idx, (s, _) in enumerate(self.beams)])
+                del self.beams[ranked[0][1]]
+                self.worst_score = ranked[1][0]
+            else:
+                self.worst_score = min(score, self.worst_score)
+
+    def is_done(self, best_sum_logprobs: float, cur_len: int) -> bool:
+        if len(self.beams) < self.num_beams:
+            return False
+        return self.worst_score >= best_sum_logprobs / cur_len ** self.length_penalty    # early_stopping False
+
+
+def topk_candidates(scores: np.ndarray, k: int):
+    """torch.topk(largest, sorted) over the flattened [beams*V] row; equal scores are taken lowest index first."""
+    order = np.argsort(-scores, kind="stable")[:k]
+    return scores[order], order
+
+
+def beam_search_from_logits(step_logits, batch: int, prompt: list, num_beams: int = 3, max_length: int = 20,
+                            min_length: int = 5, eos: int = 102, pad: int = 0, length_penalty: float = 1.0):
+    """`step_logits(input_ids [batch*beams, n] (np.int64), beam_idx or None) -> fp32 logits [batch*beams, V]` is called
+    once per step with the full current sequences and the beam reordering of the previous step.
+    Returns (tokens list per frame incl. a trailing eos when it fits, scores, state trace per step)."""
+    K = num_beams
+    ids = np.tile(np.asarray(prompt, dtype=np.int64)[None], (batch * K, 1))
+    beam_scores = np.zeros((batch, K), dtype=np.float32)
+    beam_scores[:, 1:] = -1e9
+    beam_scores = beam_scores.reshape(-1)
+    hyps = [_BeamHyps(K, length_penalty) for _ in range(batch)]
+    done = [False] * batch
+    beam_idx = None
+    trace = []
+    while True:
+        cur_len = ids.shape[1]
+        logits = np.asarray(step_logits(ids, beam_idx), dtype=np.float32)
+        lp = torch.log_softmax(torch.from_numpy(logits), dim=-1).numpy()
+        if cur_len < min_length:
+            lp[:, eos] = -np.inf                                                          # MinLengthLogitsProcessor
+        V = lp.shape[1]
+        scores = (lp + beam_scores[:, None]).reshape(batch, K * V)
+        nb_scores = np.zeros((batch, K), dtype=np.float32)
+        nb_tokens = np.zeros((batch, K), dtype=np.int64)
+        nb_idx = np.zeros((batch, K), dtype=np.int64)
+        for b in range(batch):
+            if done[b]:
+                nb_tokens[b, :] = pad
+                nb_idx[b, :] = b * K          # v4.15 writes 0 here; the rows of a finished frame are never read again
+                continue
+            cs, ci = topk_candidates(scores[b], 2 * K)
+            slot = 0
+            for rank in range(2 * K):
+                tok, src = int(ci[rank] % V), int(ci[rank] // V)
+                row = b * K + src
+                if tok == eos:
+                    if rank >= K:
+                        continue
+                    hyps[b].add(ids[row].tolist(), float(cs[rank]))
+                else:
+                    nb_scores[b, slot], nb_tokens[b, slot], nb_idx[b, slot] = cs[rank], tok, row
+                    slot += 1
+                if slot == K:
+                    break
+            assert slot == K
+            done[b] = done[b] or hyps[b].is_done(float(cs.max()), cur_len)
+        beam_scores = nb_scores.reshape(-1)
+        beam_idx = nb_idx.reshape(-1)
+        ids = np.concatenate([ids[beam_idx], nb_tokens.reshape(-1, 1)], axis=1)
+        trace.append(dict(beam_scores=beam_scores.copy(), beam_idx=beam_idx.copy(), tokens=nb_tokens.reshape(-1).copy(),
+                          done=list(done)))
+        if all(done) or ids.shape[1] >= max_length:
+            break
+    out_tokens, out_scores = [], []
+    for b in range(batch):                                                                # BeamSearchScorer.finalize
+        if not done[b]:
+            for j in range(K):
+                hyps[b].add(ids[b * K + j].tolist(), float(beam_scores[b * K + j]))
+        best = sorted(hyps[b].beams, key=lambda x: x[0]).pop()
+        seq = list(best[1])
+        if len(seq) < max_length:
+            seq.append(eos)
+        out_tokens.append(seq)
+        out_scores.append(best[0])
+    return out_tokens, out_scores, trace
+
+
+@torch.no_grad()
+def generate(sd: dict, image_embeds: torch.Tensor, prompt: list, H: int, depth: int, pre: str = "text_decoder.",
+             num_beams: int = 3, max_length: int = 20, min_length: int = 5, eos: int = 102, pad: int = 0,
+             length_penalty: float = 1.0):
+    """BLIP_Decoder.generate(sample=False), blip.py:127-167, from the image tokens on: repeat_interleave the image
+    tokens over the beams (:130), run the cached decoder (prepare_inputs_for_generation / _reorder_cache, med.py:929-955)."""
+    B = image_embeds.shape[0]
+    enc = image_embeds.repeat_interleave(num_beams, dim=0)
+    state = {"past": None}
+
+    def step(ids, beam_idx):
+        past = state["past"]
+        if past is None:
+            inp = torch.from_numpy(ids)
+        else:
+            idx = torch.from_numpy(beam_idx)
+            past = [(k.index_select(0, idx), v.index_select(0, idx)) for k, v in past]
+            inp = torch.from_numpy(ids[:, -1:])
+        logits, presents = decoder_logits(sd, pre, inp, enc, H, depth, past)
+        state["past"] = presents
+        return logits[:, -1, :].numpy()
+
+    return beam_search_from_logits(step, B, prompt, num_beams, max_length, min_length, eos, pad, length_penalty)

@@ -115,6 +115,61 @@ def build_reference_vit(vit: str, image_size: int, state_dict: dict | None = Non
     return m.eval()
 
 
+def import_reference_med():
+    """Returns the reference's models.med module (BertConfig, BertModel, BertLMHeadModel) under the installed
+    transformers: med.py imports three helpers from `transformers.modeling_utils` that later releases moved to
+    `transformers.pytorch_utils`, and calls two PreTrainedModel methods that changed; the aliases below
+    carry no arithmetic."""
+    if not reference_available():
+        raise RuntimeError(f"reference tree not found at {REFERENCE_ROOT}")
+    import transformers.modeling_utils as mu
+    import transformers.pytorch_utils as pu
+    for name in ("apply_chunking_to_forward", "prune_linear_layer"):
+        if not hasattr(mu, name):
+            setattr(mu, name, getattr(pu, name))
+    if not hasattr(mu, "find_pruneable_heads_and_indices"):
+        mu.find_pruneable_heads_and_indices = lambda *a, **k: (set(), None)
+    if "vidil_reference_med" in sys.modules:
+        return sys.modules["vidil_reference_med"]
+    spec = importlib.util.spec_from_file_location("vidil_reference_med", os.path.join(REFERENCE_ROOT, "models", "med.py"))
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules["vidil_reference_med"] = mod
+    spec.loader.exec_module(mod)
+    mod.BertPreTrainedModel.init_weights = lambda self: self.apply(self._init_weights)
+    mod.BertPreTrainedModel.get_head_mask = lambda self, head_mask, n, *a: [None] * n
+    return mod
+
+
+def build_reference_med(name: str, kind: str, state_dict: dict):
+    """kind 'decoder': the reference's BertLMHeadModel as BLIP_Decoder builds it (blip.py:95-97); kind 'itm': BertModel
+    (add_pooling_layer=False) + the itm_head Linear as BLIP_ITM builds them (blip_itm.py:29-37).  Returns (model, head)."""
+    from .weights import MED_CONFIGS
+    med = import_reference_med()
+    c = MED_CONFIGS[name]
+    cfg = med.BertConfig(vocab_size=c["vocab_size"], hidden_size=c["hidden_size"], num_hidden_layers=c["num_hidden_layers"],
+                         num_attention_heads=c["num_attention_heads"], intermediate_size=c["intermediate_size"],
+                         max_position_embeddings=c["max_position_embeddings"], layer_norm_eps=c["layer_norm_eps"],
+                         hidden_act="gelu", pad_token_id=0, type_vocab_size=2)
+    cfg.encoder_width = c["encoder_width"]
+    cfg.add_cross_attention = True
+    if kind == "decoder":
+        m = med.BertLMHeadModel(config=cfg)
+        sd = {k[len("text_decoder."):]: v for k, v in state_dict.items()}
+        sd["cls.predictions.decoder.bias"] = sd["cls.predictions.bias"]
+        missing, unexpected = m.load_state_dict(sd, strict=False)
+        assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+        # the output matrix is a separate tensor in the synthetic dict (BLIP checkpoints store both keys)
+        assert not torch.equal(m.cls.predictions.decoder.weight, m.bert.embeddings.word_embeddings.weight)
+        return m.eval(), None
+    m = med.BertModel(config=cfg, add_pooling_layer=False)
+    sd = {k[len("text_encoder."):]: v for k, v in state_dict.items() if k.startswith("text_encoder.")}
+    missing, unexpected = m.load_state_dict(sd, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing), (missing, unexpected)
+    head = nn.Linear(c["hidden_size"], 2)
+    head.load_state_dict({"weight": state_dict["itm_head.weight"], "bias": state_dict["itm_head.bias"]})
+    return m.eval(), head.eval()
+
+
 def extract_reference_function(rel_path: str, first_line: int, last_line: int, name: str):
     """exec() a nested function of the reference straight from its source lines (nothing is copied into this
     repository) — used for `aggregate_frame_tokens`, which is a closure inside predict_video."""

@@ -196,3 +196,93 @@ def u8_frames(batch: int, height: int, width: int, seed: int = 0) -> torch.Tenso
         img[-(height // 8):, -(width // 4):] = 0
         out[b] = np.clip(img, 0, 255).astype(np.uint8)
     return torch.from_numpy(out)
+
+
+# BLIP's mixture-of-encoder-decoder text stack (configs/med_config.json + blip.py:95-97: encoder_width = vision width).
+# "tiny" is a CPU-sized stand-in with the same structure; "base_l" pairs BERT-base with ViT-L tokens (width 1024),
+# "base_b" with ViT-B tokens (width 768, the shipped pipeline config).
+MED_CONFIGS = {
+    "tiny": dict(vocab_size=200, hidden_size=128, num_hidden_layers=2, num_attention_heads=2, intermediate_size=512,
+                 max_position_embeddings=64, encoder_width=128, layer_norm_eps=1e-12),
+    "base_l": dict(vocab_size=30524, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                   max_position_embeddings=512, encoder_width=1024, layer_norm_eps=1e-12),
+    "base_b": dict(vocab_size=30524, hidden_size=768, num_hidden_layers=12, num_attention_heads=12, intermediate_size=3072,
+                   max_position_embeddings=512, encoder_width=768, layer_norm_eps=1e-12),
+}
+# bert-base-uncased ids the reference relies on (blip.py:283-291): [PAD] 0, [CLS] 101, [SEP] 102 (eos), [DEC] 30522 (bos),
+# [ENC] 30523; 'a picture of' = 1037 3861 1997.  The tiny vocabulary keeps the same roles at small ids.
+MED_SPECIAL = {
+    "tiny": dict(pad=0, cls=101, eos=102, bos=198, enc=199, prompt=[198, 37, 61, 97]),
+    "base_l": dict(pad=0, cls=101, eos=102, bos=30522, enc=30523, prompt=[30522, 1037, 3861, 1997]),
+    "base_b": dict(pad=0, cls=101, eos=102, bos=30522, enc=30523, prompt=[30522, 1037, 3861, 1997]),
+}
+
+
+def med_state_dict(name: str = "base_l", kind: str = "decoder", seed: int = 0, logit_std: float = 0.1) -> dict:
+    """Synthetic parameters under the reference's key names: kind 'decoder' -> BLIP_Decoder.text_decoder
+    (BertLMHeadModel: 'text_decoder.bert.*', 'text_decoder.cls.predictions.*'); kind 'itm' -> BLIP_ITM
+    ('text_encoder.*', 'itm_head.*').  The LM decoder matrix gets std `logit_std` so that the logits of a random-init
+    model are spread out like a trained one's (std ~ sqrt(D) * logit_std) instead of being a near-tie everywhere."""
+    c = MED_CONFIGS[name]
+    D, I, L, E, V = c["hidden_size"], c["intermediate_size"], c["num_hidden_layers"], c["encoder_width"], c["vocab_size"]
+    rng = np.random.Generator(np.random.PCG64((6_000_011 if kind == "decoder" else 7_000_003) + seed))
+    pre = "text_decoder.bert." if kind == "decoder" else "text_encoder."
+    sd = {}
+    sd[pre + "embeddings.word_embeddings.weight"] = _normal(rng, (V, D), 0.05)
+    sd[pre + "embeddings.position_embeddings.weight"] = _normal(rng, (c["max_position_embeddings"], D), 0.05)
+    sd[pre + "embeddings.LayerNorm.weight"] = _normal(rng, (D,), 0.02, 1.0)
+    sd[pre + "embeddings.LayerNorm.bias"] = _normal(rng, (D,), 0.02)
+    for i in range(L):
+        p = f"{pre}encoder.layer.{i}."
+        for att, kv_in in (("attention", D), ("crossattention", E)):
+            sd[p + att + ".self.query.weight"] = _normal(rng, (D, D), 0.04)
+            sd[p + att + ".self.query.bias"] = _normal(rng, (D,), 0.02)
+            sd[p + att + ".self.key.weight"] = _normal(rng, (D, kv_in), 0.04)
+            sd[p + att + ".self.key.bias"] = _normal(rng, (D,), 0.02)
+            sd[p + att + ".self.value.weight"] = _normal(rng, (D, kv_in), 0.04)
+            sd[p + att + ".self.value.bias"] = _normal(rng, (D,), 0.02)
+            sd[p + att + ".output.dense.weight"] = _normal(rng, (D, D), 0.04)
+            sd[p + att + ".output.dense.bias"] = _normal(rng, (D,), 0.02)
+            sd[p + att + ".output.LayerNorm.weight"] = _normal(rng, (D,), 0.02, 1.0)
+            sd[p + att + ".output.LayerNorm.bias"] = _normal(rng, (D,), 0.02)
+        sd[p + "intermediate.dense.weight"] = _normal(rng, (I, D), 0.04)
+        sd[p + "intermediate.dense.bias"] = _normal(rng, (I,), 0.02)
+        sd[p + "output.dense.weight"] = _normal(rng, (D, I), 0.04)
+        sd[p + "output.dense.bias"] = _normal(rng, (D,), 0.02)
+        sd[p + "output.LayerNorm.weight"] = _normal(rng, (D,), 0.02, 1.0)
+        sd[p + "output.LayerNorm.bias"] = _normal(rng, (D,), 0.02)
+    if kind == "decoder":
+        h = "text_decoder.cls.predictions."
+        sd[h + "transform.dense.weight"] = _normal(rng, (D, D), 0.04)
+        sd[h + "transform.dense.bias"] = _normal(rng, (D,), 0.02)
+        sd[h + "transform.LayerNorm.weight"] = _normal(rng, (D,), 0.02, 1.0)
+        sd[h + "transform.LayerNorm.bias"] = _normal(rng, (D,), 0.02)
+        sd[h + "decoder.weight"] = _normal(rng, (V, D), logit_std)
+        sd[h + "bias"] = _normal(rng, (V,), 0.5)
+    else:
+        sd["itm_head.weight"] = _normal(rng, (2, D), 0.1)
+        sd["itm_head.bias"] = _normal(rng, (2,), 0.1)
+    return sd
+
+
+def image_tokens(batch: int, n_tokens: int, width: int, seed: int = 0) -> torch.Tensor:
+    """Stand-in ViT output (post-LayerNorm tokens, ~unit scale) for tests that exercise the text stack alone."""
+    rng = np.random.Generator(np.random.PCG64(8_000_009 + seed))
+    return torch.from_numpy(rng.standard_normal(size=(batch, n_tokens, width), dtype=np.float32))
+
+
+def caption_ids(name: str, batch: int, seq_len: int, seed: int = 0, min_words: int | None = None):
+    """Synthetic tokenised captions as the ITM tokenizer call lays them out (blip_itm.py:46-47, padding='max_length'):
+    [CLS]-slot id, words, [SEP], then [PAD]; returns (ids int64 [B,T], attention_mask int64 [B,T])."""
+    c, s = MED_CONFIGS[name], MED_SPECIAL[name]
+    rng = np.random.Generator(np.random.PCG64(9_000_011 + seed))
+    ids = np.full((batch, seq_len), s["pad"], dtype=np.int64)
+    mask = np.zeros((batch, seq_len), dtype=np.int64)
+    lo = 1 if min_words is None else min_words
+    for b in range(batch):
+        n_words = int(rng.integers(lo, seq_len - 1))
+        ids[b, 0] = s["cls"]
+        ids[b, 1:1 + n_words] = rng.integers(103, min(c["vocab_size"], 30522) - 4, size=n_words)
+        ids[b, 1 + n_words] = s["eos"]
+        mask[b, :n_words + 2] = 1
+    return torch.from_numpy(ids), torch.from_numpy(mask)

@@ -1,0 +1,107 @@
+"""The CPU oracle of the med.py text stack (oracle/med_oracle.py) against fixtures produced by the reference's own
+med.py (oracle/make_golden.py golden_med), plus known-answer checks of the restated v4.15 beam search."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import med_oracle, weights as W
+
+TOL = 3e-4
+
+
+@pytest.mark.parametrize("name,batch,seq_len,n_img,fname", [("tiny", 3, 9, 5, "med_tiny.npz"), ("base_l", 2, 8, 197, "med_base_l.npz")])
+def test_med_oracle_matches_reference_fixture(golden_dir, name, batch, seq_len, n_img, fname):
+    g = np.load(os.path.join(golden_dir, fname))
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    H, depth = c["num_attention_heads"], c["num_hidden_layers"]
+    enc = W.image_tokens(batch, n_img, c["encoder_width"], seed=0)
+    sd = W.med_state_dict(name, "decoder", seed=0)
+    ids, _ = W.caption_ids(name, batch, seq_len, seed=0, min_words=seq_len - 2)
+    ids[:, 0] = sp["bos"]
+    vs = g["vocab"]
+    with torch.no_grad():
+        logits, _ = med_oracle.decoder_logits(sd, "text_decoder.", ids, enc, H, depth)
+        scale = max(1.0, float(np.abs(g["logits"]).max()))
+        assert np.abs(logits[:, :, vs].numpy() - g["logits"]).max() < TOL * scale
+        assert abs(float(logits.std()) - float(g["logits_std"])) < 1e-3
+        # cached decode: prompt, then one token at a time
+        _, past = med_oracle.decoder_logits(sd, "text_decoder.", ids[:, :4], enc, H, depth)
+        for t in range(4, seq_len):
+            lg, past = med_oracle.decoder_logits(sd, "text_decoder.", ids[:, t:t + 1], enc, H, depth, past=past)
+            assert np.abs(lg[:, 0, vs].numpy() - g["step_logits"][:, t - 4]).max() < TOL * scale
+        sdi = W.med_state_dict(name, "itm", seed=0)
+        cap, mask = W.caption_ids(name, batch, seq_len, seed=1)
+        cap[:, 0] = sp["enc"]
+        out = med_oracle.itm_logits(sdi, enc, cap, mask, H, depth)
+    assert np.abs(out.numpy() - g["itm_logits"]).max() < TOL
+
+
+def _table_logits(L):
+    it = iter(L)
+    return lambda ids, beam_idx: next(it)
+
+
+def test_beam_search_known_answers():
+    """Hand-worked cases of the v4.15 rules: eos banned before min_length, a finished hypothesis is scored by
+    sum_logprobs / len, an eos ranked below num_beams is skipped, the search stops once the worst kept hypothesis is
+    at least as good as the best candidate of the step, open beams are finalised at max_length."""
+    K, eos = 2, 1
+    # (a) token 2 dominant (.5), eos .3: with length_penalty 1 longer sequences of the dominant token keep winning, so the
+    # best open beam at max_length is returned and there is no room for an eos
+    row = np.log(np.array([0.01, 0.30, 0.50, 0.10, 0.05, 0.04], dtype=np.float32))
+    L = [np.tile(row, (K, 1)) for _ in range(8)]
+    toks, scores, trace = med_oracle.beam_search_from_logits(_table_logits(L), 1, [5], num_beams=K, max_length=6, min_length=3,
+                                                            eos=eos, pad=0)
+    assert trace[0]["tokens"].tolist() == [2, 3] and trace[0]["beam_idx"].tolist() == [0, 0]
+    assert trace[1]["tokens"].tolist() == [2, 3] and trace[1]["beam_idx"].tolist() == [0, 0]   # tie -> lower flat index
+    assert toks[0] == [5, 2, 2, 2, 2, 2] and abs(scores[0] - 5 * np.log(0.5) / 6) < 1e-5
+    assert len(trace) == 5
+    # (b) eos dominant (.6) once allowed: hypotheses [5,2,2] (score (2 ln .3 + ln .6)/3) and [5,2,2,2]; after the second one
+    # worst_score == best candidate / cur_len, so the frame is done after 4 steps
+    row = np.log(np.array([0.01, 0.60, 0.30, 0.05, 0.02, 0.02], dtype=np.float32))
+    L = [np.tile(row, (K, 1)) for _ in range(8)]
+    toks, scores, trace = med_oracle.beam_search_from_logits(_table_logits(L), 1, [5], num_beams=K, max_length=8, min_length=3,
+                                                            eos=eos, pad=0)
+    assert toks[0] == [5, 2, 2, eos]
+    assert abs(scores[0] - (2 * np.log(0.3) + np.log(0.6)) / 3) < 1e-5
+    assert len(trace) == 4 and trace[-1]["done"] == [True]
+    assert trace[2]["tokens"].tolist() == [2, 3]            # ranks 1 and 3; the eos at rank 2 (>= num_beams) was skipped
+
+
+def test_beam_search_open_beams_finalised_at_max_length():
+    V, K = 5, 3
+    rng = np.random.default_rng(0)
+    L = [rng.standard_normal((K * 2, V)).astype(np.float32) for _ in range(10)]
+    for l in L:
+        l[:, 1] = -50.0                                   # eos never competitive
+    toks, scores, trace = med_oracle.beam_search_from_logits(_table_logits(L), 2, [4, 3], num_beams=K, max_length=7,
+                                                            min_length=0, eos=1, pad=0)
+    assert all(len(t) == 7 and 1 not in t for t in toks)   # max_length reached: no room for an eos
+    assert len(trace) == 5
+    # the winner is the best open beam: score = beam_score / 7
+    for b in range(2):
+        assert abs(scores[b] - trace[-1]["beam_scores"][b * K] / 7) < 1e-6
+
+
+def test_generate_runs_cached_and_uncached_identically():
+    """The cached decoder path (prepare_inputs_for_generation + _reorder_cache) and a full re-forward of the current
+    sequences give the same captions on the tiny model."""
+    name = "tiny"
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    H, depth = c["num_attention_heads"], c["num_hidden_layers"]
+    sd = W.med_state_dict(name, "decoder", seed=0)
+    enc = W.image_tokens(4, 5, c["encoder_width"], seed=2)
+    toks, scores, _ = med_oracle.generate(sd, enc, sp["prompt"], H, depth, num_beams=3, max_length=12, min_length=5, eos=sp["eos"])
+    enc3 = enc.repeat_interleave(3, dim=0)
+
+    def full(ids, beam_idx):
+        with torch.no_grad():
+            lg, _ = med_oracle.decoder_logits(sd, "text_decoder.", torch.from_numpy(ids), enc3, H, depth)
+        return lg[:, -1].numpy()
+
+    toks2, scores2, _ = med_oracle.beam_search_from_logits(full, 4, sp["prompt"], 3, 12, 5, sp["eos"], 0)
+    assert toks == toks2
+    assert np.allclose(scores, scores2, atol=1e-5)
+    assert all(t[:4] == sp["prompt"] for t in toks)
