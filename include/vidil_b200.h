@@ -11,6 +11,10 @@
  *                                                                    -> vidil_sim_topk
  *   run_visual_tokenization.py:84-96     CLIPModel(**inputs).text_embeds  -> vidil_clip_text_forward
  *   run_video_CapFilt.py:128-137         process_frame (PIL resize + ToTensor + Normalize) -> vidil_preprocess_frames
+ *   models/blip.py:127-167 BLIP_Decoder.generate(sample=False) from the image tokens on: models/med.py:811-955
+ *                                        BertLMHeadModel + transformers' beam search      -> vidil_med_generate
+ *   models/blip_itm.py:49-57 text_encoder(mode multimodal) + itm_head; models/med.py:871-893 teacher-forced logits
+ *                                                                                         -> vidil_med_forward
  *
  * Conventions
  *   - Every function returns 0 on success, non-zero on failure; vidil_last_error() then returns a
@@ -146,6 +150,74 @@ int32_t vidil_text_encoder_check_loaded(const vidil_text_encoder* enc);
 size_t  vidil_text_encoder_workspace_bytes(const vidil_text_encoder* enc, int32_t batch, int32_t seq_len);
 int32_t vidil_clip_text_forward(vidil_text_encoder* enc, const int32_t* input_ids, const int32_t* eos_pos, int32_t batch,
                                 int32_t seq_len, float* out_embeds, void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- med.py text stack: caption decoder and ITM filter (run_video_CapFilt.py:95-123) ------------ */
+/* BertModel with cross-attention onto the image tokens (models/med.py), optionally followed by the LM head
+ * (BertLMHeadModel, lm_head = 1) or by a Linear on the first token (BLIP_ITM.itm_head, cls_out = 2).
+ * Parameter names for vidil_med_load (matrices [out, in] as nn.Linear stores them; q,k,v of the self-attention and
+ * k,v of the cross-attention are concatenated along the output dim by the caller):
+ *   word_embeddings [V*D]  position_embeddings [P*D]  emb_ln.weight|bias
+ *   layer.<i>.self.qkv.weight [3D*D]|bias  layer.<i>.self.out.weight [D*D]|bias  layer.<i>.self.ln.weight|bias
+ *   layer.<i>.cross.q.weight [D*D]|bias    layer.<i>.cross.kv.weight [2D*E]|bias  layer.<i>.cross.out.weight|bias
+ *   layer.<i>.cross.ln.weight|bias         layer.<i>.ffn.fc1.weight [I*D]|bias    layer.<i>.ffn.fc2.weight [D*I]|bias
+ *   layer.<i>.ffn.ln.weight|bias
+ *   lm_head: head.dense.weight [D*D]|bias  head.ln.weight|bias  head.decoder.weight [V*D]  head.decoder.bias [V]
+ *   cls_out: cls.weight [cls_out*D]  cls.bias [cls_out] */
+typedef struct vidil_med_cfg {
+    int32_t vocab_size;     /* multiple of 4 (30524 for BLIP) */
+    int32_t max_positions;
+    int32_t hidden;         /* D = 64 * num_heads; 128/256/512/768/1024 */
+    int32_t depth;
+    int32_t num_heads;
+    int32_t mlp_dim;        /* I */
+    int32_t encoder_width;  /* E: width of the image tokens (vision_width, blip.py:96), multiple of 64 */
+    float   ln_eps;         /* 1e-12 */
+    int32_t lm_head;        /* 1: BertOnlyMLMHead present */
+    int32_t cls_out;        /* >0: Linear(D, cls_out) on token 0 */
+    int32_t dtype;          /* VIDIL_DTYPE_* */
+    int32_t cta_group;      /* 0 = library default */
+} vidil_med_cfg;
+typedef struct vidil_med vidil_med;
+int32_t vidil_med_create(const vidil_med_cfg* cfg, vidil_med** out);
+void    vidil_med_destroy(vidil_med* med);
+int32_t vidil_med_load(vidil_med* med, const char* name, const float* dev_ptr, int64_t numel, void* stream);
+int32_t vidil_med_check_loaded(const vidil_med* med);
+
+/* Whole-sequence forward.  image_embeds fp32 [n_frames, n_img_tokens, E]; input_ids int32 [n_seq, seq_len];
+ * frame_of_seq int32 [n_seq] (NULL: sequence i reads frame i, n_seq == n_frames); all device pointers.
+ *   causal = 1: decoder (BertLMHeadModel.forward is_decoder=True, all-ones attention mask, med.py:871-893)
+ *   causal = 0: encoder with the padding mask attention_mask int32 [n_seq, seq_len] (blip_itm.py:49-54)
+ * Outputs, each optional (NULL): out_hidden fp32 [n_seq, seq_len, D] (last_hidden_state), out_logits fp32
+ * [n_seq, seq_len, V] (needs lm_head), out_cls fp32 [n_seq, cls_out] (needs cls_out). */
+size_t  vidil_med_forward_workspace_bytes(const vidil_med* med, int32_t n_seq, int32_t seq_len, int32_t n_frames,
+                                          int32_t n_img_tokens);
+int32_t vidil_med_forward(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens,
+                          const int32_t* input_ids, const int32_t* attention_mask, const int32_t* frame_of_seq, int32_t n_seq,
+                          int32_t seq_len, int32_t causal, float* out_hidden, float* out_logits, float* out_cls, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* Beam-search captioning, BLIP_Decoder.generate(sample=False) after the ViT (blip.py:130-167): the prompt (HOST pointer,
+ * prompt_len ids, id 0 already replaced by bos as blip.py:136-137 does) is decoded once per frame, then
+ * max_length - prompt_len - 1 single-token steps run on n_frames * num_beams rows with a K/V cache that is never
+ * re-ordered (a per-beam ancestry table replaces transformers' _reorder_cache, med.py:951-955).  Cross-attention K/V of the
+ * image tokens are projected once per frame.  Search rules: transformers v4.15 beam_search / BeamSearchScorer with
+ * early_stopping False, repetition_penalty 1.0.  Outputs (device): out_tokens int32 [n_frames, max_length] = best
+ * hypothesis incl. the prompt, followed by eos when it fits, padded with pad; out_lengths int32 [n_frames];
+ * out_scores fp32 [n_frames] (sum of log-probs / len^length_penalty).  num_beams <= 4, max_length <= 64. */
+size_t  vidil_med_generate_workspace_bytes(const vidil_med* med, int32_t n_frames, int32_t n_img_tokens, int32_t num_beams,
+                                           int32_t max_length, int32_t prompt_len);
+int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens,
+                           const int32_t* prompt_ids_host, int32_t prompt_len, int32_t num_beams, int32_t max_length,
+                           int32_t min_length, int32_t eos_token, int32_t pad_token, float length_penalty, int32_t* out_tokens,
+                           int32_t* out_lengths, float* out_scores, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The search alone over given logits (parity of the bookkeeping): step_logits fp32 [n_steps, n_frames*num_beams, V]
+ * (device) plays the decoder; step 0 reads the row of beam 0 of every frame. */
+size_t  vidil_op_beam_search_workspace_bytes(int32_t n_frames, int32_t num_beams, int32_t max_length);
+int32_t vidil_op_beam_search(const float* step_logits, int32_t n_steps, int32_t n_frames, int32_t num_beams, int32_t V,
+                             const int32_t* prompt_ids_host, int32_t prompt_len, int32_t max_length, int32_t min_length,
+                             int32_t eos_token, int32_t pad_token, float length_penalty, int32_t* out_tokens,
+                             int32_t* out_lengths, float* out_scores, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- frame pre-processing (run_video_CapFilt.py:128-137 process_frame) ------------------------- */
 /* frames_u8: device uint8 [B, H, W, 3] (decoded RGB frames, HWC) -> out: device fp32 [B, 3, S, S]:

@@ -1,0 +1,258 @@
+"""The med.py text stack on a B200, through the C ABI (vidil_med_forward / vidil_med_generate / vidil_op_beam_search)
+behind the drop-in modules, against the CPU oracle and the fixtures made by the reference's own med.py."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import med_oracle, weights as W
+from vidil_b200 import _lib
+from vidil_b200.med import BertConfig, BertLMHeadModel, BertModel
+
+pytestmark = pytest.mark.gpu
+
+# Tolerances on logits, as a fraction of the logits' standard deviation (1.2 for the tiny model, 2.8 for BERT-base; |logit| up
+# to ~12): max / mean absolute error.  Measured on B200: fp16 9.5e-3 / 2.3e-3, bf16 6.7e-2 / 1.3e-2 at BERT-base depth — the
+# post-LayerNorm stack re-normalises after each of its 36 sub-layers, so operand rounding is not diluted by a growing residual
+# as in the pre-LN ViT; 16-bit operand rounding (2^-11 fp16, 2^-8 bf16) is the whole error, accumulation is fp32.
+LOGIT_MAX = {"fp16": 2e-2, "bf16": 1.2e-1}
+LOGIT_MEAN = {"fp16": 5e-3, "bf16": 2.5e-2}
+LOGIT_TOL = {k: v * 1.2 for k, v in LOGIT_MAX.items()}   # tiny model, absolute
+
+
+def _cfg(name):
+    return BertConfig(**W.MED_CONFIGS[name])
+
+
+def _decoder(name, dtype, dev, seed=0):
+    sd = W.med_state_dict(name, "decoder", seed=seed)
+    m = BertLMHeadModel(_cfg(name), compute_dtype=dtype)
+    missing, unexpected = m.load_state_dict({k[len("text_decoder."):]: v for k, v in sd.items()}, strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing)
+    return m.to(dev).eval(), sd
+
+
+def _itm(name, dtype, dev):
+    sd = W.med_state_dict(name, "itm", seed=0)
+    m = BertModel(_cfg(name), compute_dtype=dtype)
+    missing, unexpected = m.load_state_dict({k[len("text_encoder."):]: v for k, v in sd.items() if k.startswith("text_encoder.")},
+                                            strict=False)
+    assert not unexpected and all("position_ids" in k for k in missing)
+    head = torch.nn.Linear(W.MED_CONFIGS[name]["hidden_size"], 2)
+    head.load_state_dict({"weight": sd["itm_head.weight"], "bias": sd["itm_head.bias"]})
+    m, head = m.to(dev).eval(), head.to(dev)
+    m.attach_cls_head(head)
+    return m, sd
+
+
+# ---- beam search bookkeeping alone: bit-exact tokens against the restated v4.15 rules ----------------------------------
+def _op_beam_search(dev, L, F, K, V, prompt, max_length, min_length, eos, pad=0, lp=1.0):
+    lib = _lib.load()
+    S = len(L)
+    logits = torch.from_numpy(np.stack(L)).to(dev).contiguous()
+    need = lib.vidil_op_beam_search_workspace_bytes(F, K, max_length)
+    buf = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+    off = (-buf.data_ptr()) % 1024
+    toks = torch.empty(F, max_length, dtype=torch.int32, device=dev)
+    lens = torch.empty(F, dtype=torch.int32, device=dev)
+    scores = torch.empty(F, dtype=torch.float32, device=dev)
+    p = (ctypes.c_int32 * len(prompt))(*prompt)
+    st = lib.vidil_op_beam_search(logits.data_ptr(), S, F, K, V, ctypes.cast(p, ctypes.c_void_p), len(prompt), max_length, min_length,
+                                  eos, pad, lp, toks.data_ptr(), lens.data_ptr(), scores.data_ptr(), buf.data_ptr() + off, need,
+                                  torch.cuda.current_stream().cuda_stream)
+    _lib.check(st, "vidil_op_beam_search")
+    torch.cuda.synchronize()
+    return [toks[b, :int(lens[b])].tolist() for b in range(F)], scores.cpu().numpy()
+
+
+@pytest.mark.parametrize("K,V,eos_boost,quantise", [(3, 200, 3.0, False), (3, 30524, 6.0, False), (1, 64, 2.0, False),
+                                                    (4, 400, 4.0, False), (2, 120, 1.0, False), (3, 200, 3.0, True)])
+def test_beam_search_op_matches_oracle(cuda, K, V, eos_boost, quantise):
+    F, prompt, max_length, min_length, eos = 7, [V - 2, 5, 9, 11], 14, 6, 2
+    rng = np.random.default_rng(K * 1000 + V)
+    S = max_length - len(prompt)
+    L = []
+    for s in range(S):
+        x = rng.standard_normal((F * K, V)).astype(np.float32) * 2.0
+        x[:, eos] += eos_boost * rng.random((F * K,)).astype(np.float32) * 2
+        if quantise:
+            x = np.round(x * 2) / 2        # many exact ties inside a row: lowest token index must win
+        L.append(x)
+    it = iter(L)
+    ref_toks, ref_scores, trace = med_oracle.beam_search_from_logits(lambda ids, bi: next(it), F, prompt, K, max_length, min_length,
+                                                                     eos, 0)
+    toks, scores = _op_beam_search(cuda, L, F, K, V, prompt, max_length, min_length, eos)
+    if eos_boost >= 2.0:
+        assert any(t[-1] == eos for t in ref_toks), "the case should exercise finished hypotheses"
+    if quantise:   # equal-score alternatives across beams may legitimately resolve differently by one ulp of the lse
+        assert all(t == r or abs(s - rs) < 1e-5 for t, r, s, rs in zip(toks, ref_toks, scores, ref_scores))
+    else:
+        assert toks == ref_toks
+    assert np.allclose(scores, np.asarray(ref_scores, dtype=np.float32), atol=2e-5)
+
+
+def test_beam_search_op_known_answer(cuda):
+    """The hand-worked case (b) of tests/test_med_oracle.py."""
+    K, V, eos = 2, 8, 1
+    row = np.full(V, -30.0, dtype=np.float32)
+    row[:6] = np.log(np.array([0.01, 0.60, 0.30, 0.05, 0.02, 0.02], dtype=np.float32))
+    L = [np.tile(row, (K, 1)) for _ in range(7)]
+    toks, scores = _op_beam_search(cuda, L, 1, K, V, [5], 8, 3, eos)
+    assert toks[0] == [5, 2, 2, eos]
+    assert abs(scores[0] - (2 * np.log(0.3) + np.log(0.6)) / 3) < 1e-4
+
+
+# ---- network arithmetic ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_decoder_logits_tiny_vs_fixture_and_oracle(cuda, golden_dir, dtype):
+    name, batch, T, n_img = "tiny", 3, 9, 5
+    g = np.load(os.path.join(golden_dir, "med_tiny.npz"))
+    m, sd = _decoder(name, dtype, cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(batch, n_img, c["encoder_width"], seed=0)
+    ids, _ = W.caption_ids(name, batch, T, seed=0, min_words=T - 2)
+    ids[:, 0] = sp["bos"]
+    out = m(ids, encoder_hidden_states=enc.to(cuda)).logits.cpu().numpy()
+    err = np.abs(out[:, :, g["vocab"]] - g["logits"]).max()
+    print(f"med tiny {dtype}: logits max-abs err {err:.3e} (std {float(g['logits_std']):.2f})")
+    assert err < LOGIT_TOL[dtype]
+    with torch.no_grad():
+        ref, _ = med_oracle.decoder_logits(sd, "text_decoder.", ids, enc, c["num_attention_heads"], c["num_hidden_layers"])
+    assert np.abs(out - ref.numpy()).max() < LOGIT_TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_decoder_logits_base_vs_reference_fixture(cuda, golden_dir, dtype):
+    """BERT-base decoder on ViT-L tokens (197 x 1024) against the reference's med.py output."""
+    name, batch, T, n_img = "base_l", 2, 8, 197
+    g = np.load(os.path.join(golden_dir, "med_base_l.npz"))
+    m, _ = _decoder(name, dtype, cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(batch, n_img, c["encoder_width"], seed=0)
+    ids, _ = W.caption_ids(name, batch, T, seed=0, min_words=T - 2)
+    ids[:, 0] = sp["bos"]
+    out = m(ids, encoder_hidden_states=enc.to(cuda)).logits.cpu().numpy()
+    err = np.abs(out[:, :, g["vocab"]] - g["logits"])
+    print(f"med base_l {dtype}: logits max-abs err {err.max():.3e} mean {err.mean():.3e} (std {float(g['logits_std']):.2f})")
+    std = float(g["logits_std"])
+    assert err.max() < LOGIT_MAX[dtype] * std and err.mean() < LOGIT_MEAN[dtype] * std
+    # the top token of every position agrees with the reference wherever the reference's margin is clear
+    ref = g["logits"]
+    top2 = np.sort(ref, axis=-1)[..., -2:]
+    clear = (top2[..., 1] - top2[..., 0]) > 2 * LOGIT_MAX[dtype] * std
+    assert (out[:, :, g["vocab"]].argmax(-1) == ref.argmax(-1))[clear].all()
+
+
+@pytest.mark.parametrize("name,n_img,dtype", [("tiny", 5, "fp16"), ("tiny", 5, "bf16"), ("base_l", 197, "bf16")])
+def test_itm_logits_vs_fixture(cuda, golden_dir, name, n_img, dtype):
+    batch, T = (3, 9) if name == "tiny" else (2, 8)
+    g = np.load(os.path.join(golden_dir, f"med_{name}.npz"))
+    m, sd = _itm(name, dtype, cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(batch, n_img, c["encoder_width"], seed=0)
+    cap, mask = W.caption_ids(name, batch, T, seed=1)
+    cap[:, 0] = sp["enc"]
+    hidden, _, cls = m.run(cap, mask, enc.to(cuda), causal=False, want_hidden=True, want_cls=True)
+    err_h = np.abs(hidden[:, 0].cpu().numpy() - g["itm_hidden_cls"]).max()
+    err = np.abs(cls.cpu().numpy() - g["itm_logits"]).max()
+    print(f"itm {name} {dtype}: cls hidden err {err_h:.3e}, itm logits err {err:.3e}")
+    assert err_h < (1e-2 if dtype == "fp16" else 1e-1)      # max over the 768 unit-scale components of the [ENC] row
+    assert err < (1e-2 if dtype == "fp16" else 8e-2)
+    # module call surface of blip_itm.py:49-56
+    out = m(cap, attention_mask=mask, encoder_hidden_states=enc.to(cuda), return_dict=True)
+    assert torch.equal(out.last_hidden_state, hidden)
+
+
+def test_itm_pairs_share_frames(cuda):
+    """frame_of_seq: every (caption, frame) pair of a video in one call equals one call per caption (run_video_CapFilt.py:108-112)."""
+    name = "tiny"
+    m, sd = _itm(name, "bf16", cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    n_frames, n_caps, T = 4, 3, 12
+    enc = W.image_tokens(n_frames, 7, c["encoder_width"], seed=5).to(cuda)
+    cap, mask = W.caption_ids(name, n_caps, T, seed=2)
+    cap[:, 0] = sp["enc"]
+    pair_ids = cap.repeat_interleave(n_frames, 0)
+    pair_mask = mask.repeat_interleave(n_frames, 0)
+    frame_of = torch.arange(n_frames).repeat(n_caps)
+    _, _, all_pairs = m.run(pair_ids, pair_mask, enc, frame_of_seq=frame_of, want_hidden=False, want_cls=True)
+    for i in range(n_caps):
+        _, _, one = m.run(cap[i:i + 1].repeat(n_frames, 1), mask[i:i + 1].repeat(n_frames, 1), enc, want_hidden=False, want_cls=True)
+        assert torch.equal(one, all_pairs[i * n_frames:(i + 1) * n_frames])
+    with torch.no_grad():
+        ref = med_oracle.itm_logits(sd, enc.cpu()[frame_of], pair_ids, pair_mask, c["num_attention_heads"], c["num_hidden_layers"])
+    assert (all_pairs.cpu() - ref).abs().max() < 8e-2
+
+
+# ---- generation ----------------------------------------------------------------------------------------------------------
+def _generate_case(cuda, name, dtype, F, n_img, max_length, min_length, seed):
+    m, sd = _decoder(name, dtype, cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(F, n_img, c["encoder_width"], seed=seed)
+    prompt = torch.tensor([sp["prompt"]], dtype=torch.long).repeat(F, 1)
+    out, scores, lens = m.generate(input_ids=prompt, max_length=max_length, min_length=min_length, num_beams=3,
+                                   eos_token_id=sp["eos"], pad_token_id=sp["pad"], encoder_hidden_states=enc.to(cuda),
+                                   return_scores=True)
+    ref_toks, ref_scores, _ = med_oracle.generate(sd, enc, sp["prompt"], c["num_attention_heads"], c["num_hidden_layers"],
+                                                  num_beams=3, max_length=max_length, min_length=min_length, eos=sp["eos"],
+                                                  pad=sp["pad"])
+    got = [out[b, :int(lens[b])].tolist() for b in range(F)]
+    return got, scores.cpu().numpy(), ref_toks, np.asarray(ref_scores, dtype=np.float32), out, sp
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_generate_tiny_vs_oracle(cuda, dtype):
+    got, scores, ref, ref_scores, out, sp = _generate_case(cuda, "tiny", dtype, F=24, n_img=5, max_length=14, min_length=5, seed=3)
+    same = sum(g == r for g, r in zip(got, ref))
+    print(f"generate tiny {dtype}: {same}/24 captions identical; score err {np.abs(scores - ref_scores).max():.3e}")
+    # 16-bit operands move logits by ~1e-2: a near-tie between two beams can legitimately pick the other branch.  Where the
+    # caption differs its score must still be as good as the oracle's to within that noise.
+    assert same >= (22 if dtype == "fp16" else 18)
+    tol = 0.02 if dtype == "fp16" else 0.08
+    assert all(g == r or s > rs - tol for g, r, s, rs in zip(got, ref, scores, ref_scores))
+    assert np.abs(scores - ref_scores)[[g == r for g, r in zip(got, ref)]].max() < tol
+    assert all(g[:4] == sp["prompt"] for g in got)
+    assert out.dtype == torch.int64 and out.shape[1] == max(len(g) for g in got)
+
+
+def test_generate_base_vs_oracle(cuda):
+    """BLIP's real decoder shape (BERT-base, 30 524-token vocabulary, 197 ViT-L tokens per frame), reference call-site
+    arguments (run_video_CapFilt.py:102: beams 3, max_length 20, min_length 5)."""
+    got, scores, ref, ref_scores, out, sp = _generate_case(cuda, "base_l", "bf16", F=6, n_img=197, max_length=20, min_length=5, seed=1)
+    same = sum(g == r for g, r in zip(got, ref))
+    print(f"generate base_l bf16: {same}/6 captions identical; scores {scores} vs {ref_scores}")
+    assert same >= 4
+    assert all(g == r or s > rs - 0.1 for g, r, s, rs in zip(got, ref, scores, ref_scores))
+
+
+def test_generate_is_batch_invariant_and_accepts_expanded_tokens(cuda):
+    """A frame's caption does not depend on what else is in the batch, and the reference's repeat_interleaved image tokens
+    (blip.py:130) are accepted."""
+    name = "tiny"
+    m, _ = _decoder(name, "bf16", cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(9, 6, c["encoder_width"], seed=7).to(cuda)
+    kw = dict(max_length=12, min_length=5, num_beams=3, eos_token_id=sp["eos"], pad_token_id=sp["pad"], return_scores=True)
+    p = lambda n: torch.tensor([sp["prompt"]], dtype=torch.long).repeat(n, 1)  # noqa: E731
+    full, fs, fl = m.generate(input_ids=p(9), encoder_hidden_states=enc, **kw)
+    part, ps, pl = m.generate(input_ids=p(4), encoder_hidden_states=enc[2:6], **kw)
+    for i in range(4):
+        assert full[2 + i, :int(fl[2 + i])].tolist() == part[i, :int(pl[i])].tolist()
+    exp, es, el = m.generate(input_ids=p(9), encoder_hidden_states=enc.repeat_interleave(3, dim=0), **kw)
+    assert torch.equal(exp, full) and torch.equal(es, fs)
+
+
+def test_med_errors_are_loud(cuda):
+    m, _ = _decoder("tiny", "bf16", cuda)
+    sp = W.MED_SPECIAL["tiny"]
+    enc = W.image_tokens(2, 5, 128, seed=0)
+    with pytest.raises(RuntimeError):          # CPU tensors: no fallback
+        m(torch.tensor([sp["prompt"]] * 2), encoder_hidden_states=enc)
+    with pytest.raises(NotImplementedError):
+        m.generate(input_ids=torch.tensor([sp["prompt"]] * 2), do_sample=True, eos_token_id=sp["eos"],
+                   encoder_hidden_states=enc.to(cuda))
+    with pytest.raises(RuntimeError):          # max_length beyond the 64-token limit of the search state
+        m.generate(input_ids=torch.tensor([sp["prompt"]] * 2), max_length=100, num_beams=3, eos_token_id=sp["eos"],
+                   encoder_hidden_states=enc.to(cuda))

@@ -57,6 +57,14 @@ class TextCfg(ctypes.Structure):
                 ("dtype", c_int32), ("cta_group", c_int32)]
 
 
+class MedCfg(ctypes.Structure):
+    """Mirror of `vidil_med_cfg`."""
+
+    _fields_ = [("vocab_size", c_int32), ("max_positions", c_int32), ("hidden", c_int32), ("depth", c_int32),
+                ("num_heads", c_int32), ("mlp_dim", c_int32), ("encoder_width", c_int32), ("ln_eps", c_float),
+                ("lm_head", c_int32), ("cls_out", c_int32), ("dtype", c_int32), ("cta_group", c_int32)]
+
+
 # name -> (restype, argtypes); the single source of truth the symbol test checks against the header
 SIGNATURES = {
     "vidil_abi_version": (c_int32, []),
@@ -77,6 +85,19 @@ SIGNATURES = {
     "vidil_text_encoder_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32]),
     "vidil_clip_text_forward": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
                                           c_void_p]),
+    "vidil_med_create": (c_int32, [POINTER(MedCfg), POINTER(c_void_p)]),
+    "vidil_med_destroy": (None, [c_void_p]),
+    "vidil_med_load": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
+    "vidil_med_check_loaded": (c_int32, [c_void_p]),
+    "vidil_med_forward_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32, c_int32, c_int32]),
+    "vidil_med_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32,
+                                    c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vidil_med_generate_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32]),
+    "vidil_med_generate": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                                     c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vidil_op_beam_search_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "vidil_op_beam_search": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_int32, c_int32, c_int32,
+                                       c_int32, c_int32, c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_preprocess_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "vidil_preprocess_frames": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_float), POINTER(c_float),
                                           c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -73,6 +73,14 @@ int gemm_num_sms();
 int layernorm_run(const float* in, int64_t in_row_stride, const float* gamma, const float* beta, void* out,
                   bool out_f32, DType dt, int rows, int D, float eps, cudaStream_t stream);
 
+// Post-LayerNorm of the BERT-style text stack (med.py:245,316): resid[r,:] = LN(resid[r,:]) in place (fp32) and, when
+// out16 != null, the same row as the 16-bit operand of the next GEMM.
+int layernorm_post_run(float* resid, const float* gamma, const float* beta, void* out16, DType dt, int rows, int D, float eps,
+                       cudaStream_t stream);
+// LayerNorm of a 16-bit matrix into a 16-bit matrix (BertPredictionHeadTransform, med.py:513-517)
+int layernorm16_run(const void* in16, const float* gamma, const float* beta, void* out16, DType dt, int rows, int D, float eps,
+                    cudaStream_t stream);
+
 // ---------------------------------------------------------------------------------------
 // Fused softmax attention over packed qkv [B, N, 3, H, 64] -> out [B, N, H*64] (vit.py:72-83).
 // ---------------------------------------------------------------------------------------
@@ -134,5 +142,48 @@ int preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const floa
 // ---------------------------------------------------------------------------------------
 int topk_rerank_run(const float* scores, int64_t ld_scores, const float* img, const float* bank, int F, int T,
                     int D, int k, float* out_scores, int32_t* out_idx, cudaStream_t stream);
+
+// ---------------------------------------------------------------------------------------
+// med.py text stack (caption decoder / ITM encoder): SIMT kernels around the GEMMs (med.cu).
+// ---------------------------------------------------------------------------------------
+enum MedAttnMode : int {
+    MED_ATTN_FULL = 0,    // every query sees every key of its sequence that the padding mask allows (encoder, blip_itm.py:49)
+    MED_ATTN_CAUSAL = 1,  // query i sees keys 0..i of its sequence (decoder over whole sequences / the prompt)
+    MED_ATTN_DECODE = 2   // one new token per row at position `pos`; earlier keys come from the cache via the ancestry table
+};
+// Device-side state of a beam search over `frames` frames x `beams` beams (row r = frame * beams + beam).
+struct BeamState {
+    int frames = 0, beams = 0, t_max = 0, eos = 0, pad = 0;
+    float length_penalty = 1.f;
+    int32_t* seq = nullptr;        // [2][R][t_max] token sequences (ping-pong across steps)
+    int32_t* anc = nullptr;        // [2][R][t_max] row whose cache slot holds position t of this beam's history
+    float* beam_scores = nullptr;  // [R] sum of log-probs
+    int32_t* cur_tok = nullptr;    // [R] token fed to the next step
+    int32_t* hyp_n = nullptr;      // [frames] finished hypotheses kept (<= beams)
+    double* hyp_score = nullptr;   // [frames][beams+1]
+    int32_t* hyp_len = nullptr;    // [frames][beams+1]
+    int32_t* hyp_tok = nullptr;    // [frames][beams+1][t_max]
+    double* worst = nullptr;       // [frames]
+    int32_t* done = nullptr;       // [frames]
+};
+// resid[r,:] = word[ids[ids_mod ? r % ids_mod : r],:] + pos[pos0 + r % T,:]
+int med_embed_run(const int32_t* ids, const float* word, const float* pos, float* resid, int64_t rows, int T, int pos0, int ids_mod,
+                  int D, int vocab, int max_pos, cudaStream_t s);
+// qkv [rows, 3D] 16-bit -> out [rows, D]; cache [R][Tmax][2D] (K then V) or null; anc [R][Tmax]; mask int32 [n_seq][T_seq] or null
+int med_self_attn_run(const void* qkv, void* cache, const int32_t* anc, const int32_t* mask, void* out, DType dt, int rows, int T_seq,
+                      int H, int mode, int pos, int Tmax, int beams, float scale, cudaStream_t s);
+// q [groups*nq, D], kv [F, Nv, 2D] -> out [groups*nq, D]; group g reads frame frame_of_group[g] (g when null)
+int med_cross_attn_run(const void* q, const void* kv, const int32_t* frame_of_group, void* out, DType dt, int groups, int nq, int Nv,
+                       int H, float scale, cudaStream_t s);
+// list l scans logits row l*row_mul: log_softmax, ban_token excluded (-1: none), + beam_scores[l] -> nc best (score, token)
+int med_logits_topk_run(const float* logits, int64_t ld, int row_mul, const float* beam_scores, int n_lists, int V, int nc, int ban_token,
+                        float* cand_score, int32_t* cand_tok, cudaStream_t s);
+int med_beam_init_run(const BeamState& st, const int32_t* prompt_dev, int prompt_len, cudaStream_t s);
+int med_beam_step_run(const BeamState& st, const float* cand_score, const int32_t* cand_tok, int lists_per_frame, int nc, int V,
+                      int cur_len, int parity, cudaStream_t s);
+int med_beam_finalize_run(const BeamState& st, int cur_len, int parity, int max_length, int32_t* out_tokens, int32_t* out_len,
+                          float* out_score, cudaStream_t s);
+int med_cls_head_run(const float* hidden, const float* W, const float* bias, float* out, int n_seq, int T, int D, int n_out,
+                     cudaStream_t s);
 
 }  // namespace vidil

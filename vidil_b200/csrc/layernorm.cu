@@ -78,6 +78,77 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
     }
 }
 
+// Post-LN of the text stack: the normalised row replaces the fp32 row in place and is also emitted as the next GEMM's
+// 16-bit operand; or (IN16) a 16-bit row in, 16-bit row out.  Same one-warp-per-row, registers-only scheme.
+template <typename T, int VPL, bool IN16>
+__global__ void __launch_bounds__(LN_WARPS * 32)
+    layernorm_post_kernel(float* __restrict__ resid, const T* __restrict__ in16, const float* __restrict__ gamma,
+                          const float* __restrict__ beta, T* __restrict__ out16, int rows, float eps) {
+    constexpr int D = VPL * 128;
+    const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (row >= rows) return;
+    float4 x[VPL];
+    if (IN16) {
+        const uint2* src = reinterpret_cast<const uint2*>(in16 + static_cast<int64_t>(row) * D);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) {
+            const uint2 u = src[lane + 32 * j];
+            const T* h = reinterpret_cast<const T*>(&u);
+            x[j] = make_float4(static_cast<float>(h[0]), static_cast<float>(h[1]), static_cast<float>(h[2]), static_cast<float>(h[3]));
+        }
+    } else {
+        const float4* src = reinterpret_cast<const float4*>(resid + static_cast<int64_t>(row) * D);
+#pragma unroll
+        for (int j = 0; j < VPL; ++j) x[j] = src[lane + 32 * j];
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) s += (x[j].x + x[j].y) + (x[j].z + x[j].w);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * (1.0f / D);
+    float q = 0.f;
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const float a = x[j].x - mean, b = x[j].y - mean, c = x[j].z - mean, d = x[j].w - mean;
+        q += (a * a + b * b) + (c * c + d * d);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * (1.0f / D) + eps);
+    const float4* g4 = reinterpret_cast<const float4*>(gamma);
+    const float4* b4 = reinterpret_cast<const float4*>(beta);
+#pragma unroll
+    for (int j = 0; j < VPL; ++j) {
+        const float4 g = __ldg(g4 + lane + 32 * j);
+        const float4 b = __ldg(b4 + lane + 32 * j);
+        const float y0 = (x[j].x - mean) * rstd * g.x + b.x, y1 = (x[j].y - mean) * rstd * g.y + b.y;
+        const float y2 = (x[j].z - mean) * rstd * g.z + b.z, y3 = (x[j].w - mean) * rstd * g.w + b.w;
+        if (!IN16) store4<float>(resid + static_cast<int64_t>(row) * D + 4 * (lane + 32 * j), y0, y1, y2, y3);
+        if (out16 != nullptr) store4<T>(out16 + static_cast<int64_t>(row) * D + 4 * (lane + 32 * j), y0, y1, y2, y3);
+    }
+}
+
+template <typename T, bool IN16>
+int launch_ln_post(float* resid, const void* in16, const float* g, const float* b, void* out16, int rows, int D, float eps,
+                   cudaStream_t s) {
+    const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+    const T* i16 = reinterpret_cast<const T*>(in16);
+    T* o = reinterpret_cast<T*>(out16);
+    switch (D) {
+        case 768: layernorm_post_kernel<T, 6, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
+        case 1024: layernorm_post_kernel<T, 8, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
+        case 512: layernorm_post_kernel<T, 4, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
+        case 256: layernorm_post_kernel<T, 2, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
+        case 128: layernorm_post_kernel<T, 1, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
+        default: set_error("layernorm: unsupported width %d (supported: 128, 256, 512, 768, 1024)", D); return 1;
+    }
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
 template <typename OutT>
 int launch_ln(const float* in, int64_t stride, const float* g, const float* b, void* out, int rows, int D, float eps,
               cudaStream_t s) {
@@ -109,6 +180,20 @@ int layernorm_run(const float* in, int64_t in_row_stride, const float* gamma, co
     if (out_f32) return launch_ln<float>(in, in_row_stride, gamma, beta, out, rows, D, eps, stream);
     if (dt == DT_BF16) return launch_ln<__nv_bfloat16>(in, in_row_stride, gamma, beta, out, rows, D, eps, stream);
     return launch_ln<__half>(in, in_row_stride, gamma, beta, out, rows, D, eps, stream);
+}
+
+int layernorm_post_run(float* resid, const float* gamma, const float* beta, void* out16, DType dt, int rows, int D, float eps,
+                       cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    if (dt == DT_BF16) return launch_ln_post<__nv_bfloat16, false>(resid, nullptr, gamma, beta, out16, rows, D, eps, stream);
+    return launch_ln_post<__half, false>(resid, nullptr, gamma, beta, out16, rows, D, eps, stream);
+}
+
+int layernorm16_run(const void* in16, const float* gamma, const float* beta, void* out16, DType dt, int rows, int D, float eps,
+                    cudaStream_t stream) {
+    if (rows <= 0) return 0;
+    if (dt == DT_BF16) return launch_ln_post<__nv_bfloat16, true>(nullptr, in16, gamma, beta, out16, rows, D, eps, stream);
+    return launch_ln_post<__half, true>(nullptr, in16, gamma, beta, out16, rows, D, eps, stream);
 }
 
 }  // namespace vidil

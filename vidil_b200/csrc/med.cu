@@ -1,0 +1,688 @@
+// SIMT kernels of the med.py text stack (caption decoder / ITM encoder) around the tcgen05 GEMMs:
+// token embedding, short-sequence self-attention with a beam-indexed K/V cache, cross-attention of a few query rows onto
+// the image tokens, fused log-softmax + top-2K over the vocabulary, and the beam-search bookkeeping
+// (transformers v4.15 BeamSearchScorer semantics, driven from models/blip.py:150-158).
+//
+// Shapes are small on the query side (<= 40 text tokens, 3 beams) and large on the key side of the cross-attention
+// (197 / 577 image tokens per frame) and of the vocabulary scan (30 524 logits per row): all of these kernels are
+// HBM/L2-bound streaming kernels with 128-bit loads; none of them is GEMM-shaped enough for the tensor cores.
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
+
+#include "kernels.h"
+
+namespace vidil {
+namespace {
+
+template <typename T>
+__device__ __forceinline__ float to_f(T x);
+template <>
+__device__ __forceinline__ float to_f<__nv_bfloat16>(__nv_bfloat16 x) {
+    return __bfloat162float(x);
+}
+template <>
+__device__ __forceinline__ float to_f<__half>(__half x) {
+    return __half2float(x);
+}
+template <typename T>
+__device__ __forceinline__ T from_f(float x);
+template <>
+__device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) {
+    return __float2bfloat16_rn(x);
+}
+template <>
+__device__ __forceinline__ __half from_f<__half>(float x) {
+    return __float2half_rn(x);
+}
+
+// 8 consecutive 16-bit values (one 128-bit load) -> 8 floats
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float (&v)[8]) {
+    const uint4 u = *reinterpret_cast<const uint4*>(p);
+    const T* h = reinterpret_cast<const T*>(&u);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = to_f<T>(h[i]);
+}
+
+__device__ __forceinline__ float warp_sum(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+    return x;
+}
+__device__ __forceinline__ float warp_max(float x) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
+    return x;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BertEmbeddings (med.py:74-96) before its LayerNorm: resid[r,:] = word[ids[r],:] + pos[pos0 + r % T,:]
+// ---------------------------------------------------------------------------------------------------------------------
+__global__ void med_embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
+                                 float* __restrict__ resid, int64_t rows, int T, int pos0, int ids_mod, int D, int vocab, int max_pos) {
+    const int d4 = D / 4;
+    const int64_t total = rows * d4;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t r = i / d4;
+        const int c = static_cast<int>(i - r * d4);
+        int id = ids[ids_mod > 0 ? r % ids_mod : r];  // ids_mod: the same short sequence (the prompt) for every frame
+        id = id < 0 ? 0 : (id >= vocab ? vocab - 1 : id);
+        int t = pos0 + static_cast<int>(r % T);
+        t = t >= max_pos ? max_pos - 1 : t;
+        const float4 a = reinterpret_cast<const float4*>(word + static_cast<int64_t>(id) * D)[c];
+        const float4 b = reinterpret_cast<const float4*>(pos + static_cast<int64_t>(t) * D)[c];
+        reinterpret_cast<float4*>(resid + r * D)[c] = make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Self-attention of BertSelfAttention (med.py:146-232) for short text sequences.  One warp per (query row, head);
+// lane l owns dims 2l, 2l+1 of the 64-wide head.  q/k/v of the rows being processed come from the fused projection
+// output qkv [rows, 3D]; in decode mode the earlier positions come from the cache through the beam ancestry table.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SA_WARPS = 8;
+constexpr int SA_MAX_KEYS = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(SA_WARPS * 32)
+    med_self_attn_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ anc,
+                         const int32_t* __restrict__ mask, T* __restrict__ out, int rows, int T_seq, int H, int mode, int pos,
+                         int Tmax, int beams, float scale) {
+    __shared__ float s_sc[SA_WARPS][SA_MAX_KEYS];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int item = blockIdx.x * SA_WARPS + w;
+    if (item >= rows * H) return;
+    const int r = item / H, h = item - r * H;
+    const int D = H * 64;
+    const int64_t ld = 3 * static_cast<int64_t>(D);
+    const int col = h * 64 + 2 * lane;
+    float* sc = s_sc[w];
+
+    const T* qp = qkv + r * ld + col;
+    const float q0 = to_f<T>(qp[0]) * scale, q1 = to_f<T>(qp[1]) * scale;
+    int nkeys;
+    int b = 0, i = 0;
+    if (mode == MED_ATTN_DECODE) {
+        nkeys = pos + 1;
+    } else {
+        b = r / T_seq;
+        i = r - b * T_seq;
+        nkeys = (mode == MED_ATTN_CAUSAL) ? i + 1 : T_seq;
+    }
+    // own K/V -> cache (decode: slot (r, pos); prefill: slot (b*beams, i))
+    if (cache != nullptr && mode != MED_ATTN_FULL) {
+        const int crow = (mode == MED_ATTN_DECODE) ? r : b * beams;
+        const int cpos = (mode == MED_ATTN_DECODE) ? pos : i;
+        T* cp = cache + (static_cast<int64_t>(crow) * Tmax + cpos) * (2 * D) + col;
+        *reinterpret_cast<uint32_t*>(cp) = *reinterpret_cast<const uint32_t*>(qp + D);
+        *reinterpret_cast<uint32_t*>(cp + D) = *reinterpret_cast<const uint32_t*>(qp + 2 * D);
+    }
+    auto key_ptr = [&](int j) -> const T* {
+        if (mode == MED_ATTN_DECODE) {
+            if (j == pos) return qkv + r * ld + D + col;
+            const int src = anc[static_cast<int64_t>(r) * Tmax + j];
+            return cache + (static_cast<int64_t>(src) * Tmax + j) * (2 * D) + col;
+        }
+        return qkv + (static_cast<int64_t>(b) * T_seq + j) * ld + D + col;
+    };
+    const int v_off = (mode == MED_ATTN_DECODE) ? D : D;  // V sits D elements after K in both layouts
+    float mx = -INFINITY;
+    for (int j = 0; j < nkeys; ++j) {
+        const T* kp = key_ptr(j);
+        float d = q0 * to_f<T>(kp[0]) + q1 * to_f<T>(kp[1]);
+        d = warp_sum(d);
+        if (mode == MED_ATTN_FULL && mask != nullptr && mask[b * T_seq + j] == 0) d += -10000.0f;  // med.py:667
+        if (lane == 0) sc[j] = d;
+        mx = fmaxf(mx, d);
+    }
+    __syncwarp();
+    float sum = 0.f;
+    for (int j = lane; j < nkeys; j += 32) {
+        const float e = __expf(sc[j] - mx);
+        sc[j] = e;
+        sum += e;
+    }
+    sum = warp_sum(sum);
+    __syncwarp();
+    const float inv = 1.0f / sum;
+    float a0 = 0.f, a1 = 0.f;
+    for (int j = 0; j < nkeys; ++j) {
+        const T* vp = key_ptr(j) + v_off;
+        const float p = sc[j];
+        a0 += p * to_f<T>(vp[0]);
+        a1 += p * to_f<T>(vp[1]);
+    }
+    T* op = out + static_cast<int64_t>(r) * D + col;
+    op[0] = from_f<T>(a0 * inv);
+    op[1] = from_f<T>(a1 * inv);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Cross-attention onto the image tokens (BertSelfAttention with is_cross_attention, med.py:160-163): query group g =
+// rows [g*nq, (g+1)*nq) of q [rows, D] attends to the Nv tokens of frame f = frame_of_group[g] (identity when null),
+// whose keys/values were projected once per frame into kv [F, Nv, 2D].  One CTA per (head, group).
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CA_THREADS = 128;
+constexpr int CA_QCHUNK = 4;
+
+template <typename T>
+__global__ void __launch_bounds__(CA_THREADS)
+    med_cross_attn_kernel(const T* __restrict__ q, const T* __restrict__ kv, const int32_t* __restrict__ frame_of_group,
+                          T* __restrict__ out, int nq, int Nv, int H, float scale) {
+    extern __shared__ float smem[];
+    const int h = blockIdx.x, g = blockIdx.y;
+    const int D = H * 64;
+    const int f = frame_of_group ? frame_of_group[g] : g;
+    float* q_s = smem;                               // [nq][64]
+    float* s_s = q_s + nq * 64;                      // [nq][Nv]
+    float* red = s_s + static_cast<size_t>(nq) * Nv;  // [4 warps][CA_QCHUNK][64]
+    const int t = threadIdx.x;
+    const T* qbase = q + (static_cast<int64_t>(g) * nq) * D + h * 64;
+    for (int i = t; i < nq * 64; i += CA_THREADS) q_s[i] = to_f<T>(qbase[static_cast<int64_t>(i >> 6) * D + (i & 63)]) * scale;
+    __syncthreads();
+    const T* kbase = kv + static_cast<int64_t>(f) * Nv * (2 * D) + h * 64;
+    // scores: one key per thread and pass
+    for (int j = t; j < Nv; j += CA_THREADS) {
+        float k[64];
+        const T* kp = kbase + static_cast<int64_t>(j) * (2 * D);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+            float v8[8];
+            load8<T>(kp + 8 * c, v8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) k[8 * c + e] = v8[e];
+        }
+        for (int qi = 0; qi < nq; ++qi) {
+            const float* qr = q_s + qi * 64;
+            float d = 0.f;
+#pragma unroll
+            for (int e = 0; e < 64; ++e) d += k[e] * qr[e];
+            s_s[static_cast<size_t>(qi) * Nv + j] = d;
+        }
+    }
+    __syncthreads();
+    // softmax per query row: warp w takes rows w, w+4, ...
+    const int w = t >> 5, lane = t & 31;
+    for (int qi = w; qi < nq; qi += CA_THREADS / 32) {
+        float* row = s_s + static_cast<size_t>(qi) * Nv;
+        float mx = -INFINITY;
+        for (int j = lane; j < Nv; j += 32) mx = fmaxf(mx, row[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < Nv; j += 32) {
+            const float e = __expf(row[j] - mx);
+            row[j] = e;
+            sum += e;
+        }
+        sum = warp_sum(sum);
+        const float inv = 1.0f / sum;
+        for (int j = lane; j < Nv; j += 32) row[j] *= inv;
+    }
+    __syncthreads();
+    // P V: thread = (8 dims, 1 of 16 key lanes); CA_QCHUNK query rows per sweep over V
+    const int dg = t & 7, kl = t >> 3;
+    const T* vbase = kbase + D + dg * 8;
+    for (int q0 = 0; q0 < nq; q0 += CA_QCHUNK) {
+        float acc[CA_QCHUNK][8];
+#pragma unroll
+        for (int c = 0; c < CA_QCHUNK; ++c)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
+        for (int j = kl; j < Nv; j += 16) {
+            float v8[8];
+            load8<T>(vbase + static_cast<int64_t>(j) * (2 * D), v8);
+#pragma unroll
+            for (int c = 0; c < CA_QCHUNK; ++c) {
+                const float p = (q0 + c < nq) ? s_s[static_cast<size_t>(q0 + c) * Nv + j] : 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[c][e] += p * v8[e];
+            }
+        }
+        // lanes dg + 8*{0..3} of a warp hold partial sums of the same dims
+#pragma unroll
+        for (int c = 0; c < CA_QCHUNK; ++c)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float x = acc[c][e];
+                x += __shfl_xor_sync(0xffffffffu, x, 8);
+                x += __shfl_xor_sync(0xffffffffu, x, 16);
+                acc[c][e] = x;
+            }
+        if (lane < 8) {
+#pragma unroll
+            for (int c = 0; c < CA_QCHUNK; ++c)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) red[(w * CA_QCHUNK + c) * 64 + dg * 8 + e] = acc[c][e];
+        }
+        __syncthreads();
+        for (int i = t; i < CA_QCHUNK * 64; i += CA_THREADS) {
+            const int c = i >> 6, d = i & 63;
+            if (q0 + c < nq) {
+                const float x = red[(0 * CA_QCHUNK + c) * 64 + d] + red[(1 * CA_QCHUNK + c) * 64 + d] +
+                                red[(2 * CA_QCHUNK + c) * 64 + d] + red[(3 * CA_QCHUNK + c) * 64 + d];
+                out[(static_cast<int64_t>(g) * nq + q0 + c) * D + h * 64 + d] = from_f<T>(x);
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// log_softmax over the vocabulary + MinLengthLogitsProcessor + beam score + the row's best NC candidates
+// (the per-row half of `torch.topk(next_token_scores.view(batch, beams*V), 2*beams)`).  One CTA per candidate list.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int TK_THREADS = 256;
+constexpr int TK_MAX_NC = 8;
+
+__device__ __forceinline__ bool cand_better(float v, int i, float v2, int i2) { return v > v2 || (v == v2 && i < i2); }
+
+__global__ void __launch_bounds__(TK_THREADS)
+    med_logits_topk_kernel(const float* __restrict__ logits, int64_t ld, int row_mul, const float* __restrict__ beam_scores, int V,
+                           int nc, int ban_token, float* __restrict__ cand_score, int32_t* __restrict__ cand_tok) {
+    __shared__ float s_red[TK_THREADS / 32];
+    __shared__ float s_v[TK_THREADS / 32];
+    __shared__ int s_i[TK_THREADS / 32];
+    __shared__ int s_owner[TK_THREADS / 32];
+    __shared__ float s_m, s_l;
+    __shared__ int s_win;
+    const int list = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const float* row = logits + static_cast<int64_t>(list) * row_mul * ld;
+    float tv[TK_MAX_NC];
+    int ti[TK_MAX_NC];
+#pragma unroll
+    for (int c = 0; c < TK_MAX_NC; ++c) {
+        tv[c] = -INFINITY;
+        ti[c] = 0x7fffffff;
+    }
+    float m = -INFINITY, s = 0.f;
+    const int v4 = V / 4;
+    for (int i4 = t; i4 < v4; i4 += TK_THREADS) {
+        const float4 x4 = reinterpret_cast<const float4*>(row)[i4];
+        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float x = xs[e];
+            const int idx = 4 * i4 + e;
+            if (x > m) {
+                s = s * __expf(m - x) + 1.0f;
+                m = x;
+            } else {
+                s += __expf(x - m);
+            }
+            if (idx != ban_token && cand_better(x, idx, tv[TK_MAX_NC - 1], ti[TK_MAX_NC - 1])) {
+                tv[TK_MAX_NC - 1] = x;
+                ti[TK_MAX_NC - 1] = idx;
+#pragma unroll
+                for (int c = TK_MAX_NC - 1; c > 0; --c) {
+                    if (cand_better(tv[c], ti[c], tv[c - 1], ti[c - 1])) {
+                        const float fv = tv[c]; tv[c] = tv[c - 1]; tv[c - 1] = fv;
+                        const int fi = ti[c]; ti[c] = ti[c - 1]; ti[c - 1] = fi;
+                    }
+                }
+            }
+        }
+    }
+    // block max, then rescaled sum
+    float bm = warp_max(m);
+    if (lane == 0) s_red[w] = bm;
+    __syncthreads();
+    if (t == 0) {
+        float x = s_red[0];
+        for (int i = 1; i < TK_THREADS / 32; ++i) x = fmaxf(x, s_red[i]);
+        s_m = x;
+    }
+    __syncthreads();
+    const float gm = s_m;
+    float bs = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - gm));
+    __syncthreads();
+    if (lane == 0) s_red[w] = bs;
+    __syncthreads();
+    if (t == 0) {
+        float x = 0.f;
+        for (int i = 0; i < TK_THREADS / 32; ++i) x += s_red[i];
+        s_l = logf(x);
+    }
+    __syncthreads();
+    const float lse = s_l;
+    const float add = beam_scores ? beam_scores[list] : 0.f;
+    // nc rounds of block arg-max over the heads of the per-thread lists
+    for (int c = 0; c < nc; ++c) {
+        float v = tv[0];
+        int i = ti[0];
+        int owner = t;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+            const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+            const int o2 = __shfl_xor_sync(0xffffffffu, owner, o);
+            if (cand_better(v2, i2, v, i)) {
+                v = v2; i = i2; owner = o2;
+            }
+        }
+        if (lane == 0) {
+            s_v[w] = v; s_i[w] = i; s_owner[w] = owner;
+        }
+        __syncthreads();
+        if (t == 0) {
+            int best = 0;
+            for (int k = 1; k < TK_THREADS / 32; ++k)
+                if (cand_better(s_v[k], s_i[k], s_v[best], s_i[best])) best = k;
+            s_win = s_owner[best];
+            cand_score[static_cast<int64_t>(list) * nc + c] = ((s_v[best] - gm) - lse) + add;  // log_softmax, then + beam score
+            cand_tok[static_cast<int64_t>(list) * nc + c] = s_i[best];
+        }
+        __syncthreads();
+        if (t == s_win) {
+#pragma unroll
+            for (int k = 0; k < TK_MAX_NC - 1; ++k) {
+                tv[k] = tv[k + 1];
+                ti[k] = ti[k + 1];
+            }
+            tv[TK_MAX_NC - 1] = -INFINITY;
+            ti[TK_MAX_NC - 1] = 0x7fffffff;
+        }
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Beam bookkeeping: BeamSearchScorer.process of transformers v4.15 for one frame per thread.
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ void hyp_add(const BeamState& st, int b, const int32_t* toks, int len, float sum_logprobs) {
+    const int K = st.beams, Tm = st.t_max;
+    const double score = static_cast<double>(sum_logprobs) / pow(static_cast<double>(len), static_cast<double>(st.length_penalty));
+    int n = st.hyp_n[b];
+    double* hs = st.hyp_score + static_cast<int64_t>(b) * (K + 1);
+    int32_t* hl = st.hyp_len + static_cast<int64_t>(b) * (K + 1);
+    int32_t* ht = st.hyp_tok + static_cast<int64_t>(b) * (K + 1) * Tm;
+    if (n < K || score > st.worst[b]) {
+        hs[n] = score;
+        hl[n] = len;
+        for (int i = 0; i < len; ++i) ht[n * Tm + i] = toks[i];
+        ++n;
+        if (n > K) {
+            // drop the lowest (score, position) entry; keep list order (BeamHypotheses.add)
+            int lo = 0;
+            for (int i = 1; i < n; ++i)
+                if (hs[i] < hs[lo]) lo = i;
+            for (int i = lo; i + 1 < n; ++i) {
+                hs[i] = hs[i + 1];
+                hl[i] = hl[i + 1];
+                for (int k = 0; k < hl[i]; ++k) ht[i * Tm + k] = ht[(i + 1) * Tm + k];
+            }
+            --n;
+            double wmin = hs[0];
+            for (int i = 1; i < n; ++i) wmin = fmin(wmin, hs[i]);
+            st.worst[b] = wmin;
+        } else {
+            st.worst[b] = fmin(score, st.worst[b]);
+        }
+        st.hyp_n[b] = n;
+    }
+}
+
+__global__ void med_beam_step_kernel(BeamState st, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_tok,
+                                     int lists_per_frame, int nc, int V, int cur_len, int parity) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= st.frames) return;
+    const int K = st.beams, Tm = st.t_max;
+    const int64_t R = static_cast<int64_t>(st.frames) * K;
+    const int32_t* seq_in = st.seq + parity * R * Tm;
+    int32_t* seq_out = st.seq + (parity ^ 1) * R * Tm;
+    const int32_t* anc_in = st.anc + parity * R * Tm;
+    int32_t* anc_out = st.anc + (parity ^ 1) * R * Tm;
+    if (st.done[b]) {
+        for (int j = 0; j < K; ++j) {
+            const int64_t r = static_cast<int64_t>(b) * K + j;
+            st.beam_scores[r] = 0.f;
+            st.cur_tok[r] = st.pad;
+            for (int i = 0; i < cur_len; ++i) {
+                seq_out[r * Tm + i] = seq_in[r * Tm + i];
+                anc_out[r * Tm + i] = (i < cur_len - 1) ? anc_in[r * Tm + i] : static_cast<int32_t>(r);
+            }
+            seq_out[r * Tm + cur_len] = st.pad;
+        }
+        return;
+    }
+    // merge the frame's candidate lists: the 2K best of (score desc, flat index beam*V + token asc)
+    constexpr int MAXC = 4 * TK_MAX_NC;
+    float cs[MAXC];
+    int cflat[MAXC];
+    const int total = lists_per_frame * nc;
+    for (int l = 0; l < lists_per_frame; ++l)
+        for (int c = 0; c < nc; ++c) {
+            const int64_t list = (lists_per_frame == 1) ? b : static_cast<int64_t>(b) * K + l;
+            cs[l * nc + c] = cand_score[list * nc + c];
+            cflat[l * nc + c] = l * V + cand_tok[list * nc + c];
+        }
+    float top_s[TK_MAX_NC];
+    int top_f[TK_MAX_NC];
+    for (int c = 0; c < nc; ++c) {
+        int best = -1;
+        for (int i = 0; i < total; ++i) {
+            if (cflat[i] < 0) continue;
+            if (best < 0 || cs[i] > cs[best] || (cs[i] == cs[best] && cflat[i] < cflat[best])) best = i;
+        }
+        top_s[c] = cs[best];
+        top_f[c] = cflat[best];
+        cflat[best] = -1;
+    }
+    int slot = 0;
+    float new_score[4];
+    int new_tok[4], new_parent[4];
+    for (int rank = 0; rank < nc && slot < K; ++rank) {
+        const int tok = top_f[rank] % V, src = top_f[rank] / V;
+        const int64_t prow = static_cast<int64_t>(b) * K + src;
+        if (tok == st.eos) {
+            if (rank >= K) continue;
+            hyp_add(st, b, seq_in + prow * Tm, cur_len, top_s[rank]);
+        } else {
+            new_score[slot] = top_s[rank];
+            new_tok[slot] = tok;
+            new_parent[slot] = static_cast<int>(prow);
+            ++slot;
+        }
+    }
+    // fewer than K continuations can only happen when nc < 2K; the caller guarantees nc == 2K
+    for (int j = 0; j < K; ++j) {
+        const int64_t r = static_cast<int64_t>(b) * K + j;
+        const int jj = j < slot ? j : slot - 1;
+        const int64_t p = new_parent[jj];
+        st.beam_scores[r] = j < slot ? new_score[jj] : -1e9f;
+        st.cur_tok[r] = new_tok[jj];
+        for (int i = 0; i < cur_len; ++i) {
+            seq_out[r * Tm + i] = seq_in[p * Tm + i];
+            anc_out[r * Tm + i] = (i < cur_len - 1) ? anc_in[p * Tm + i] : static_cast<int32_t>(p);
+        }
+        seq_out[r * Tm + cur_len] = new_tok[jj];
+    }
+    // BeamHypotheses.is_done(best_sum_logprobs = max of the step's candidates, cur_len), early_stopping False
+    if (st.hyp_n[b] >= K) {
+        const double cur = static_cast<double>(top_s[0]) / pow(static_cast<double>(cur_len), static_cast<double>(st.length_penalty));
+        if (st.worst[b] >= cur) st.done[b] = 1;
+    }
+}
+
+// BeamSearchScorer.finalize: open beams of unfinished frames become hypotheses; the best one is written out, followed by
+// eos when it fits (len < max_length), padded with pad.
+__global__ void med_beam_finalize_kernel(BeamState st, int cur_len, int parity, int max_length, int32_t* __restrict__ out_tokens,
+                                         int32_t* __restrict__ out_len, float* __restrict__ out_score) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= st.frames) return;
+    const int K = st.beams, Tm = st.t_max;
+    const int64_t R = static_cast<int64_t>(st.frames) * K;
+    const int32_t* seq_in = st.seq + parity * R * Tm;
+    if (!st.done[b])
+        for (int j = 0; j < K; ++j) {
+            const int64_t r = static_cast<int64_t>(b) * K + j;
+            hyp_add(st, b, seq_in + r * Tm, cur_len, st.beam_scores[r]);
+        }
+    const int n = st.hyp_n[b];
+    const double* hs = st.hyp_score + static_cast<int64_t>(b) * (K + 1);
+    const int32_t* hl = st.hyp_len + static_cast<int64_t>(b) * (K + 1);
+    const int32_t* ht = st.hyp_tok + static_cast<int64_t>(b) * (K + 1) * Tm;
+    int best = 0;
+    for (int i = 1; i < n; ++i)
+        if (hs[i] >= hs[best]) best = i;  // sorted(key=score).pop(): among equal scores the later entry
+    int len = hl[best];
+    int32_t* o = out_tokens + static_cast<int64_t>(b) * max_length;
+    for (int i = 0; i < len; ++i) o[i] = ht[best * Tm + i];
+    if (len < max_length) o[len++] = st.eos;
+    for (int i = len; i < max_length; ++i) o[i] = st.pad;
+    out_len[b] = len;
+    out_score[b] = static_cast<float>(hs[best]);
+}
+
+__global__ void med_beam_init_kernel(BeamState st, const int32_t* __restrict__ prompt, int prompt_len) {
+    const int64_t r = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x;
+    const int K = st.beams, Tm = st.t_max;
+    const int64_t R = static_cast<int64_t>(st.frames) * K;
+    if (r >= R) return;
+    const int b = static_cast<int>(r / K);
+    for (int p = 0; p < 2; ++p)
+        for (int i = 0; i < Tm; ++i) {
+            st.seq[(p * R + r) * Tm + i] = i < prompt_len ? prompt[i] : st.pad;
+            st.anc[(p * R + r) * Tm + i] = b * K;
+        }
+    st.beam_scores[r] = (r % K == 0) ? 0.f : -1e9f;
+    st.cur_tok[r] = prompt[prompt_len - 1];
+    if (r % K == 0) {
+        st.hyp_n[b] = 0;
+        st.worst[b] = 1e9;
+        st.done[b] = 0;
+    }
+}
+
+// out[p, j] = hidden[p * T, :] . W[j, :] + bias[j]   (itm_head on the first token, blip_itm.py:56)
+__global__ void med_cls_head_kernel(const float* __restrict__ hidden, const float* __restrict__ W, const float* __restrict__ bias,
+                                    float* __restrict__ out, int n_seq, int T, int D, int n_out) {
+    const int item = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (item >= n_seq * n_out) return;
+    const int p = item / n_out, j = item - p * n_out;
+    const float* x = hidden + static_cast<int64_t>(p) * T * D;
+    const float* wr = W + static_cast<int64_t>(j) * D;
+    float d = 0.f;
+    for (int i = lane; i < D; i += 32) d += x[i] * wr[i];
+    d = warp_sum(d);
+    if (lane == 0) out[item] = d + (bias ? bias[j] : 0.f);
+}
+
+inline int grid_for(int64_t n, int block) {
+    int64_t g = (n + block - 1) / block;
+    if (g > 148 * 32) g = 148 * 32;
+    return static_cast<int>(g < 1 ? 1 : g);
+}
+
+}  // namespace
+
+int med_embed_run(const int32_t* ids, const float* word, const float* pos, float* resid, int64_t rows, int T, int pos0, int ids_mod,
+                  int D, int vocab, int max_pos, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    med_embed_kernel<<<grid_for(rows * (D / 4), 256), 256, 0, s>>>(ids, word, pos, resid, rows, T, pos0, ids_mod, D, vocab, max_pos);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_self_attn_run(const void* qkv, void* cache, const int32_t* anc, const int32_t* mask, void* out, DType dt, int rows, int T_seq,
+                      int H, int mode, int pos, int Tmax, int beams, float scale, cudaStream_t s) {
+    if (rows <= 0) return 0;
+    const int nkeys_max = (mode == MED_ATTN_DECODE) ? pos + 1 : T_seq;
+    if (nkeys_max > SA_MAX_KEYS) {
+        set_error("med self-attention: %d keys, at most %d supported", nkeys_max, SA_MAX_KEYS);
+        return 1;
+    }
+    const int grid = (rows * H + SA_WARPS - 1) / SA_WARPS;
+    if (dt == DT_BF16)
+        med_self_attn_kernel<__nv_bfloat16><<<grid, SA_WARPS * 32, 0, s>>>(
+            reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(cache), anc, mask,
+            reinterpret_cast<__nv_bfloat16*>(out), rows, T_seq, H, mode, pos, Tmax, beams, scale);
+    else
+        med_self_attn_kernel<__half><<<grid, SA_WARPS * 32, 0, s>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(cache),
+                                                                   anc, mask, reinterpret_cast<__half*>(out), rows, T_seq, H, mode,
+                                                                   pos, Tmax, beams, scale);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_cross_attn_run(const void* q, const void* kv, const int32_t* frame_of_group, void* out, DType dt, int groups, int nq, int Nv,
+                       int H, float scale, cudaStream_t s) {
+    if (groups <= 0) return 0;
+    const size_t smem = (static_cast<size_t>(nq) * 64 + static_cast<size_t>(nq) * Nv + 4 * CA_QCHUNK * 64) * sizeof(float);
+    if (smem > 200 * 1024) {
+        set_error("med cross-attention: %d query rows x %d image tokens need %zu bytes of shared memory", nq, Nv, smem);
+        return 1;
+    }
+    const dim3 grid(H, groups);
+    if (dt == DT_BF16) {
+        auto k = med_cross_attn_kernel<__nv_bfloat16>;
+        if (smem > 48 * 1024) VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k<<<grid, CA_THREADS, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(kv),
+                                         frame_of_group, reinterpret_cast<__nv_bfloat16*>(out), nq, Nv, H, scale);
+    } else {
+        auto k = med_cross_attn_kernel<__half>;
+        if (smem > 48 * 1024) VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k<<<grid, CA_THREADS, smem, s>>>(reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(kv), frame_of_group,
+                                         reinterpret_cast<__half*>(out), nq, Nv, H, scale);
+    }
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_logits_topk_run(const float* logits, int64_t ld, int row_mul, const float* beam_scores, int n_lists, int V, int nc, int ban_token,
+                        float* cand_score, int32_t* cand_tok, cudaStream_t s) {
+    if (n_lists <= 0) return 0;
+    if (nc < 1 || nc > TK_MAX_NC || V % 4 != 0 || ld % 4 != 0) {
+        set_error("med top-k: nc=%d (1..%d), V=%d and ld=%lld must be multiples of 4", nc, TK_MAX_NC, V, (long long)ld);
+        return 1;
+    }
+    med_logits_topk_kernel<<<n_lists, TK_THREADS, 0, s>>>(logits, ld, row_mul, beam_scores, V, nc, ban_token, cand_score, cand_tok);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_beam_init_run(const BeamState& st, const int32_t* prompt_dev, int prompt_len, cudaStream_t s) {
+    const int64_t R = static_cast<int64_t>(st.frames) * st.beams;
+    med_beam_init_kernel<<<static_cast<int>((R + 127) / 128), 128, 0, s>>>(st, prompt_dev, prompt_len);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_beam_step_run(const BeamState& st, const float* cand_score, const int32_t* cand_tok, int lists_per_frame, int nc, int V,
+                      int cur_len, int parity, cudaStream_t s) {
+    if (st.beams > 4 || nc != 2 * st.beams) {
+        set_error("beam step: num_beams=%d (at most 4) with %d candidates per list (must be 2*num_beams)", st.beams, nc);
+        return 1;
+    }
+    med_beam_step_kernel<<<(st.frames + 63) / 64, 64, 0, s>>>(st, cand_score, cand_tok, lists_per_frame, nc, V, cur_len, parity);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_beam_finalize_run(const BeamState& st, int cur_len, int parity, int max_length, int32_t* out_tokens, int32_t* out_len,
+                          float* out_score, cudaStream_t s) {
+    med_beam_finalize_kernel<<<(st.frames + 63) / 64, 64, 0, s>>>(st, cur_len, parity, max_length, out_tokens, out_len, out_score);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_cls_head_run(const float* hidden, const float* W, const float* bias, float* out, int n_seq, int T, int D, int n_out,
+                     cudaStream_t s) {
+    if (n_seq <= 0 || n_out <= 0) return 0;
+    const int items = n_seq * n_out;
+    med_cls_head_kernel<<<(items + 7) / 8, 256, 0, s>>>(hidden, W, bias, out, n_seq, T, D, n_out);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+}  // namespace vidil
