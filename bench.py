@@ -12,7 +12,7 @@ One step = one 256-frame batch through vidil_vit_forward.  Prints ONE JSON line 
             and step k-1's D2H overlapping step k's forward
   roofline  the tcgen05 GEMM kernel: algorithmic FLOPs / its event-timed device time inside the timed steps
   cpu_baseline  the oracle port of models/vit.py timed on this box's host cores (rank 0, N=1 only)
-Other workloads (not the driver's line): --workload clip | sim | text | tokenize.
+Other workloads (not the driver's line): --workload clip | sim | text | tokenize | capfilt.
 """
 from __future__ import annotations
 
@@ -518,14 +518,116 @@ def run_tokenize(args):
         dist.destroy_process_group()
 
 
+def _randomise(module, std=0.02):
+    import torch
+    with torch.no_grad():
+        for n, p in module.named_parameters():
+            p.normal_(0.0, std)
+            if ("norm" in n or "LayerNorm" in n) and n.endswith("weight"):
+                p.add_(1.0)
+
+
+def run_capfilt(args):
+    """BASELINE.json configs[2]: `--videos` synthetic videos x 8 frames through the CapFilt models of run_video_CapFilt.py —
+    captioner = BLIP ViT + med.py decoder with beam search (beams 3, max_length 20, min_length 5, :102), filterer = BLIP_ITM
+    (its own ViT + the multimodal text encoder + itm_head) over every (caption, frame) pair of a video (:108-120).  One step =
+    all videos once; frames start on the device.  Not the driver's line."""
+    import torch
+
+    from vidil_b200.blip import BLIP_Decoder, BLIP_ITM
+    dev = torch.device("cuda", 0)
+    torch.manual_seed(0)
+    V, Fv = args.videos, 8
+    n_frames = V * Fv
+    cap = BLIP_Decoder(image_size=args.image_size, vit=args.vit, compute_dtype=args.dtype)
+    _randomise(cap)
+    with torch.no_grad():
+        cap.text_decoder.cls.predictions.decoder.weight.normal_(0.0, 0.1)     # spread-out logits, like a trained head
+    cap = cap.to(dev).eval()
+    itm = BLIP_ITM(image_size=args.image_size, vit=args.vit, compute_dtype=args.dtype, cache_identical_inputs=False)
+    _randomise(itm)
+    itm = itm.to(dev).eval()
+    frames = torch.randn(n_frames, 3, args.image_size, args.image_size, device=dev)
+    chunk = args.batch
+    T_itm = 35
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+    lib = __import__("vidil_b200._lib", fromlist=["_lib"])
+
+    def step(timed):
+        # captioner: ViT per `chunk` frames, then one beam search over all frames
+        if timed:
+            ev[0].record()
+        toks = torch.cat([cap.visual_encoder(frames[i:i + chunk]) for i in range(0, n_frames, chunk)])
+        if timed:
+            ev[1].record()
+        ids = torch.tensor([cap._prompt_ids], dtype=torch.long).repeat(n_frames, 1)
+        ids[:, 0] = cap.bos_token_id
+        out, scores, lens = cap.text_decoder.generate(input_ids=ids[:, :-1], max_length=20, min_length=5, num_beams=3,
+                                                      eos_token_id=cap.sep_token_id, pad_token_id=cap.pad_token_id,
+                                                      encoder_hidden_states=toks, return_scores=True)
+        if timed:
+            ev[2].record()
+        # filterer: every generated caption of a video against each of its 8 frames (duplicates are not removed here: worst case)
+        cap_ids = torch.zeros(n_frames, T_itm, dtype=torch.int32, device=dev)
+        L = min(out.shape[1], T_itm)
+        cap_ids[:, :L] = out[:, :L].int()
+        cap_ids[:, 0] = 101                                     # [CLS], as the tokenizer call of blip_itm.py:46 produces
+        mask = (torch.arange(T_itm, device=dev)[None] < lens[:, None].clamp(max=T_itm)).int()
+        itoks = torch.cat([itm.visual_encoder(frames[i:i + chunk]) for i in range(0, n_frames, chunk)])
+        if timed:
+            ev[3].record()
+        pair_ids = cap_ids.repeat_interleave(Fv, 0)                                       # caption c of video v x its 8 frames
+        pair_mask = mask.repeat_interleave(Fv, 0)
+        vid = torch.arange(n_frames, device=dev) // Fv
+        frame_of = (vid.repeat_interleave(Fv) * Fv + torch.arange(Fv, device=dev).repeat(n_frames)).int()
+        logits = []
+        pc = args.pair_chunk
+        for i in range(0, pair_ids.shape[0], pc):                # whole videos per call: only their frames' K/V are projected
+            j = min(i + pc, pair_ids.shape[0])
+            f0, f1 = (i // Fv // Fv) * Fv, ((j - 1) // Fv // Fv + 1) * Fv
+            _, _, cls = itm.text_encoder.run(pair_ids[i:j], pair_mask[i:j], itoks[f0:f1], frame_of_seq=frame_of[i:j] - f0,
+                                             want_hidden=False, want_cls=True)
+            logits.append(cls)
+        prob = torch.softmax(torch.cat(logits), dim=1)[:, 1].view(n_frames, Fv).max(dim=1).values   # max_filter, :117-118
+        keep = (prob > 0.5).cpu()
+        if timed:
+            ev[4].record()
+        return out.cpu(), keep
+
+    for _ in range(args.warmup):
+        step(False)
+    torch.cuda.synchronize()
+    before = lib.launch_count()
+    acc = [0.0] * 4
+    for _ in range(args.steps):
+        step(True)
+        torch.cuda.synchronize()
+        for i in range(4):
+            acc[i] += ev[i].elapsed_time(ev[i + 1])
+    launches = lib.launch_count() - before
+    ms = [a / args.steps for a in acc]
+    total = sum(ms)
+    tokens = (args.image_size // 16) ** 2 + 1
+    D, depth, _ = VIT[args.vit]
+    print(json.dumps({"metric": "frames/sec through CapFilt (caption + filter)", "value": n_frames / (total / 1e3), "unit": "frames/s",
+                      "ms_per_step": total, "steps": args.steps, "warmup": args.warmup, "gpu_launches": launches,
+                      "stages_ms": {"captioner_vit": ms[0], "caption_beam_search": ms[1], "filterer_vit": ms[2], "itm_pairs": ms[3]},
+                      "caption_frames_per_s": n_frames / ((ms[0] + ms[1]) / 1e3),
+                      "decode_rows": n_frames * 3, "itm_pairs": n_frames * Fv, "dtype": args.dtype, "data": "synthetic",
+                      "config": {"workload": f"{V} synthetic videos x 8 frames @{args.image_size}, BLIP ViT-{args.vit[0].upper()}/16 + "
+                                 f"med.py decoder (beam 3, max_length 20, min_length 5) + BLIP_ITM filter over {n_frames * Fv} "
+                                 f"(caption, frame) pairs x 35 tokens; {tokens} image tokens per frame"}}), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--workload", default="vit", choices=["vit", "clip", "sim", "text", "tokenize"])
-    ap.add_argument("--videos", type=int, default=1024, help="--workload tokenize: synthetic videos (8 frames each), all ranks")
+    ap.add_argument("--workload", default="vit", choices=["vit", "clip", "sim", "text", "tokenize", "capfilt"])
+    ap.add_argument("--pair-chunk", type=int, default=2048, help="--workload capfilt: (caption, frame) pairs per ITM call")
+    ap.add_argument("--videos", type=int, default=1024, help="--workload tokenize | capfilt: synthetic videos (8 frames each), all ranks")
     ap.add_argument("--batch", type=int, default=256, help="frames per GPU per step")
     ap.add_argument("--vit", default="large", choices=list(VIT))
     ap.add_argument("--image-size", type=int, default=224)
@@ -545,6 +647,8 @@ def main():
         return run_text(args)
     if args.workload == "tokenize":
         return run_tokenize(args)
+    if args.workload == "capfilt":
+        return run_capfilt(args)
     return run_vit(args)
 
 

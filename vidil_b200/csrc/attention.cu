@@ -269,6 +269,221 @@ __global__ void __launch_bounds__(ATT_THREADS)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The same mma.sync pipeline with separate query and key/value sequences — the attentions of the med.py text stack
+// (models/med.py:146-232): self-attention over short text sequences read in place from the fused projection output
+// (padding mask, blip_itm.py:49-51, or causal mask, med.py:636), and cross-attention of a group's nq text rows onto the nk
+// image tokens of its frame, whose K/V were projected once per frame (med.py:160-163).  grid = (ceil(nq/64), H, groups).
+// Masked keys get -10000 added to the scaled score like the reference (med.py:667); warps whose 16 query rows lie beyond
+// nq (decode: 3 beams per frame) only help with the loads.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(ATT_THREADS)
+    attention_x_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ k, const T* __restrict__ v,
+                       int64_t kv_stride, const int32_t* __restrict__ frame_of_group, const int32_t* __restrict__ key_mask,
+                       T* __restrict__ out, int64_t out_stride, int nq, int nk, int causal, float scale_log2e) {
+    __shared__ __align__(128) uint8_t smem[BQ * HD * 2 + 2 * 2 * BKV * HD * 2];
+    const uint32_t sQ = ptx::smem_u32(smem);
+    const uint32_t sKV = sQ + BQ * HD * 2;
+    constexpr float MASKV = -10000.0f * 1.4426950408889634f;
+
+    const int qblk = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int f = frame_of_group ? frame_of_group[g] : g;
+    const T* q_base = q + static_cast<int64_t>(g) * nq * q_stride + h * HD;
+    const T* k_base = k + static_cast<int64_t>(f) * nk * kv_stride + h * HD;
+    const T* v_base = v + static_cast<int64_t>(f) * nk * kv_stride + h * HD;
+    const int32_t* mrow = key_mask ? key_mask + static_cast<int64_t>(g) * nk : nullptr;
+    const int q0 = qblk * BQ;
+    const int num_kb = (nk + BKV - 1) / BKV;
+    const bool active = q0 + warp * 16 < nq;
+
+    load_tile_async<T>(sQ, q_base, q_stride, q0, nq);
+    load_tile_async<T>(sKV, k_base, kv_stride, 0, nk);
+    load_tile_async<T>(sKV + 8192, v_base, kv_stride, 0, nk);
+    cp_async_commit();
+
+    uint32_t qf[4][4];
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run[2] = {-INFINITY, -INFINITY};
+    float l_run[2] = {0.f, 0.f};
+    const int qrow0 = q0 + warp * 16 + (lane >> 2), qrow1 = qrow0 + 8;
+
+    for (int kb = 0; kb < num_kb; ++kb) {
+        const int stage = kb & 1;
+        if (kb + 1 < num_kb) {
+            const uint32_t nxt = sKV + (stage ^ 1) * 16384;
+            load_tile_async<T>(nxt, k_base, kv_stride, (kb + 1) * BKV, nk);
+            load_tile_async<T>(nxt + 8192, v_base, kv_stride, (kb + 1) * BKV, nk);
+            cp_async_commit();
+            cp_async_wait<1>();
+        } else {
+            cp_async_wait<0>();
+        }
+        __syncthreads();
+
+        if (active) {
+            if (kb == 0) {
+#pragma unroll
+                for (int kk = 0; kk < 4; ++kk) {
+                    const int r = warp * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const int c = kk * 2 + (lane >> 4);
+                    ldsm_x4(sQ + tile_off(r, c), qf[kk][0], qf[kk][1], qf[kk][2], qf[kk][3]);
+                }
+            }
+            const uint32_t sK = sKV + stage * 16384;
+            const uint32_t sV = sK + 8192;
+            float s[8][4];
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+                for (int kk2 = 0; kk2 < 2; ++kk2) {
+                    uint32_t b0, b1, b2, b3;
+                    ldsm_x4(sK + tile_off(nt * 8 + (lane & 7), kk2 * 4 + (lane >> 3)), b0, b1, b2, b3);
+                    mma16816<T>(s[nt], qf[2 * kk2], b0, b1);
+                    mma16816<T>(s[nt], qf[2 * kk2 + 1], b2, b3);
+                }
+            }
+            const int key0 = kb * BKV + (lane & 3) * 2;
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int key = key0 + nt * 8 + (e & 1);
+                    const int row = (e < 2) ? qrow0 : qrow1;
+                    float x = s[nt][e] * scale_log2e;
+                    if (key >= nk) {
+                        x = -INFINITY;
+                    } else {
+                        if (mrow != nullptr && mrow[key] == 0) x += MASKV;
+                        if (causal && key > row) x += MASKV;
+                    }
+                    s[nt][e] = x;
+                }
+            }
+            float mx[2] = {m_run[0], m_run[1]};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                mx[0] = fmaxf(mx[0], fmaxf(s[nt][0], s[nt][1]));
+                mx[1] = fmaxf(mx[1], fmaxf(s[nt][2], s[nt][3]));
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+                mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+            }
+            const float corr0 = exp2f(m_run[0] - mx[0]);
+            const float corr1 = exp2f(m_run[1] - mx[1]);
+            m_run[0] = mx[0];
+            m_run[1] = mx[1];
+            float rs[2] = {0.f, 0.f};
+#pragma unroll
+            for (int nt = 0; nt < 8; ++nt) {
+                s[nt][0] = exp2f(s[nt][0] - mx[0]);
+                s[nt][1] = exp2f(s[nt][1] - mx[0]);
+                s[nt][2] = exp2f(s[nt][2] - mx[1]);
+                s[nt][3] = exp2f(s[nt][3] - mx[1]);
+                rs[0] += s[nt][0] + s[nt][1];
+                rs[1] += s[nt][2] + s[nt][3];
+            }
+            l_run[0] = l_run[0] * corr0 + rs[0];
+            l_run[1] = l_run[1] * corr1 + rs[1];
+#pragma unroll
+            for (int nd = 0; nd < 8; ++nd) {
+                o[nd][0] *= corr0;
+                o[nd][1] *= corr0;
+                o[nd][2] *= corr1;
+                o[nd][3] *= corr1;
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                uint32_t pa[4];
+                pa[0] = pack2<T>(s[2 * j][0], s[2 * j][1]);
+                pa[1] = pack2<T>(s[2 * j][2], s[2 * j][3]);
+                pa[2] = pack2<T>(s[2 * j + 1][0], s[2 * j + 1][1]);
+                pa[3] = pack2<T>(s[2 * j + 1][2], s[2 * j + 1][3]);
+#pragma unroll
+                for (int nd2 = 0; nd2 < 4; ++nd2) {
+                    uint32_t b0, b1, b2, b3;
+                    const int r = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                    const int c = nd2 * 2 + (lane >> 4);
+                    ldsm_x4_trans(sV + tile_off(r, c), b0, b1, b2, b3);
+                    mma16816<T>(o[2 * nd2], pa, b0, b1);
+                    mma16816<T>(o[2 * nd2 + 1], pa, b2, b3);
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (!active) return;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 1);
+        l_run[i] += __shfl_xor_sync(0xffffffffu, l_run[i], 2);
+    }
+    const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
+    const int gq = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+        const int r0 = warp * 16 + gq, r1 = r0 + 8;
+        const uint32_t v0 = pack2<T>(o[nd][0] * inv0, o[nd][1] * inv0);
+        const uint32_t v1 = pack2<T>(o[nd][2] * inv1, o[nd][3] * inv1);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + tile_off(r0, nd) + tq * 4), "r"(v0) : "memory");
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(sQ + tile_off(r1, nd) + tq * 4), "r"(v1) : "memory");
+    }
+    __syncwarp();
+    T* o_base = out + static_cast<int64_t>(g) * nq * out_stride + h * HD;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int idx = lane + i * 32;
+        const int r = warp * 16 + (idx >> 3), c = idx & 7;
+        const int n = q0 + r;
+        if (n < nq) {
+            uint4 val;
+            asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];"
+                         : "=r"(val.x), "=r"(val.y), "=r"(val.z), "=r"(val.w)
+                         : "r"(sQ + tile_off(r, c)));
+            *reinterpret_cast<uint4*>(o_base + static_cast<int64_t>(n) * out_stride + c * 8) = val;
+        }
+    }
+}
+
+}  // namespace
+
+int attention_x_run(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_stride, const int32_t* frame_of_group,
+                    const int32_t* key_mask, void* out, int64_t out_stride, DType dt, int groups, int nq, int nk, int H, bool causal,
+                    float scale, cudaStream_t stream) {
+    if (groups <= 0 || nq <= 0 || nk <= 0 || H <= 0) return 0;
+    if (H > 65535 || groups > 65535) {
+        set_error("attention: H and the number of query groups must be <= 65535 (grid y/z limits); got H=%d groups=%d", H, groups);
+        return 1;
+    }
+    if ((q_stride | kv_stride | out_stride) % 8 != 0 || ((reinterpret_cast<uintptr_t>(q) | reinterpret_cast<uintptr_t>(k) |
+                                                            reinterpret_cast<uintptr_t>(v) | reinterpret_cast<uintptr_t>(out)) & 15)) {
+        set_error("attention: operands must be 16-byte aligned with row strides that are multiples of 8 elements");
+        return 1;
+    }
+    const dim3 grid((nq + BQ - 1) / BQ, H, groups);
+    const float sl2 = scale * 1.4426950408889634f;
+    if (dt == DT_BF16)
+        attention_x_kernel<__nv_bfloat16><<<grid, ATT_THREADS, 0, stream>>>(
+            reinterpret_cast<const __nv_bfloat16*>(q), q_stride, reinterpret_cast<const __nv_bfloat16*>(k),
+            reinterpret_cast<const __nv_bfloat16*>(v), kv_stride, frame_of_group, key_mask, reinterpret_cast<__nv_bfloat16*>(out),
+            out_stride, nq, nk, causal ? 1 : 0, sl2);
+    else
+        attention_x_kernel<__half><<<grid, ATT_THREADS, 0, stream>>>(
+            reinterpret_cast<const __half*>(q), q_stride, reinterpret_cast<const __half*>(k), reinterpret_cast<const __half*>(v),
+            kv_stride, frame_of_group, key_mask, reinterpret_cast<__half*>(out), out_stride, nq, nk, causal ? 1 : 0, sl2);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+namespace {
 }  // namespace
 
 int attention_run(const void* qkv, void* out, DType dt, int B, int N, int H, float scale, cudaStream_t stream) {

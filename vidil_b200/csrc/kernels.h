@@ -146,6 +146,14 @@ int topk_rerank_run(const float* scores, int64_t ld_scores, const float* img, co
 // ---------------------------------------------------------------------------------------
 // med.py text stack (caption decoder / ITM encoder): SIMT kernels around the GEMMs (med.cu).
 // ---------------------------------------------------------------------------------------
+// Attention with separate query and key/value sequences on the mma.sync pipeline (attention.cu): group g = query rows
+// [g*nq, (g+1)*nq) at q + row*q_stride + head*64 attends to the nk keys/values of frame f = frame_of_group[g] (g when null) at
+// k|v + (f*nk + j)*kv_stride + head*64.  key_mask int32 [groups][nk] (0 = masked, -10000 added) or null; causal: key j > row i
+// masked.  out rows at out + row*out_stride + head*64.
+int attention_x_run(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_stride, const int32_t* frame_of_group,
+                    const int32_t* key_mask, void* out, int64_t out_stride, DType dt, int groups, int nq, int nk, int H, bool causal,
+                    float scale, cudaStream_t stream);
+
 enum MedAttnMode : int {
     MED_ATTN_FULL = 0,    // every query sees every key of its sequence that the padding mask allows (encoder, blip_itm.py:49)
     MED_ATTN_CAUSAL = 1,  // query i sees keys 0..i of its sequence (decoder over whole sequences / the prompt)
@@ -169,12 +177,12 @@ struct BeamState {
 // resid[r,:] = word[ids[ids_mod ? r % ids_mod : r],:] + pos[pos0 + r % T,:]
 int med_embed_run(const int32_t* ids, const float* word, const float* pos, float* resid, int64_t rows, int T, int pos0, int ids_mod,
                   int D, int vocab, int max_pos, cudaStream_t s);
-// qkv [rows, 3D] 16-bit -> out [rows, D]; cache [R][Tmax][2D] (K then V) or null; anc [R][Tmax]; mask int32 [n_seq][T_seq] or null
-int med_self_attn_run(const void* qkv, void* cache, const int32_t* anc, const int32_t* mask, void* out, DType dt, int rows, int T_seq,
-                      int H, int mode, int pos, int Tmax, int beams, float scale, cudaStream_t s);
-// q [groups*nq, D], kv [F, Nv, 2D] -> out [groups*nq, D]; group g reads frame frame_of_group[g] (g when null)
-int med_cross_attn_run(const void* q, const void* kv, const int32_t* frame_of_group, void* out, DType dt, int groups, int nq, int Nv,
-                       int H, float scale, cudaStream_t s);
+// decode step: qkv [rows, 3D] (one new token per row at position pos) -> out [rows, D]; cache [R][Tmax][2D] (K then V) receives the
+// new K/V at slot (row, pos); earlier keys are read from slot (anc[row][t], t)
+int med_self_attn_decode_run(const void* qkv, void* cache, const int32_t* anc, void* out, DType dt, int rows, int H, int pos, int Tmax,
+                             float scale, cudaStream_t s);
+// K/V of whole sequences, qkv [n_seq*T_seq, 3D] -> cache slots (seq*beams, t)
+int med_cache_fill_run(const void* qkv, void* cache, DType dt, int64_t n_rows, int T_seq, int D, int Tmax, int beams, cudaStream_t s);
 // list l scans logits row l*row_mul: log_softmax, ban_token excluded (-1: none), + beam_scores[l] -> nc best (score, token)
 int med_logits_topk_run(const float* logits, int64_t ld, int row_mul, const float* beam_scores, int n_lists, int V, int nc, int ban_token,
                         float* cand_score, int32_t* cand_tok, cudaStream_t s);

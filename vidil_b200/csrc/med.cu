@@ -78,194 +78,103 @@ __global__ void med_embed_kernel(const int32_t* __restrict__ ids, const float* _
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Self-attention of BertSelfAttention (med.py:146-232) for short text sequences.  One warp per (query row, head);
-// lane l owns dims 2l, 2l+1 of the 64-wide head.  q/k/v of the rows being processed come from the fused projection
-// output qkv [rows, 3D]; in decode mode the earlier positions come from the cache through the beam ancestry table.
+// Decode-step self-attention (BertSelfAttention with past_key_value, med.py:169-175): every row holds ONE new token at
+// position `pos`; keys/values of earlier positions live in cache slots [row][t][2D] that are never moved — row r's history
+// is found through anc[r][t] = the row that computed position t of this beam's prefix (replaces _reorder_cache,
+// med.py:951-955).  One warp per (row, head): lane j scores key j (a full 128-byte K row per lane, q broadcast), the
+// softmax is two warp reductions, then lane l accumulates dims 2l, 2l+1 of P.V with the key loop's addresses known up front.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SA_WARPS = 8;
-constexpr int SA_MAX_KEYS = 128;
+constexpr int SA_WARPS = 4;
+constexpr int SA_MAX_KEYS = 64;
 
 template <typename T>
 __global__ void __launch_bounds__(SA_WARPS * 32)
-    med_self_attn_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ anc,
-                         const int32_t* __restrict__ mask, T* __restrict__ out, int rows, int T_seq, int H, int mode, int pos,
-                         int Tmax, int beams, float scale) {
-    __shared__ float s_sc[SA_WARPS][SA_MAX_KEYS];
+    med_self_attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ anc, T* __restrict__ out,
+                                int rows, int H, int pos, int Tmax, float scale) {
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * SA_WARPS + w;
     if (item >= rows * H) return;
     const int r = item / H, h = item - r * H;
     const int D = H * 64;
-    const int64_t ld = 3 * static_cast<int64_t>(D);
-    const int col = h * 64 + 2 * lane;
-    float* sc = s_sc[w];
-
-    const T* qp = qkv + r * ld + col;
-    const float q0 = to_f<T>(qp[0]) * scale, q1 = to_f<T>(qp[1]) * scale;
-    int nkeys;
-    int b = 0, i = 0;
-    if (mode == MED_ATTN_DECODE) {
-        nkeys = pos + 1;
-    } else {
-        b = r / T_seq;
-        i = r - b * T_seq;
-        nkeys = (mode == MED_ATTN_CAUSAL) ? i + 1 : T_seq;
+    const T* own = qkv + static_cast<int64_t>(r) * 3 * D + h * 64;  // q | +D: k | +2D: v of the new token
+    // the new token's K/V go to slot (r, pos): lanes 0..7 copy K, 8..15 copy V, 16 bytes each
+    if (lane < 16) {
+        const int part = lane >> 3, c = lane & 7;
+        T* dst = cache + (static_cast<int64_t>(r) * Tmax + pos) * (2 * D) + part * D + h * 64 + c * 8;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(own + (1 + part) * D + c * 8);
     }
-    // own K/V -> cache (decode: slot (r, pos); prefill: slot (b*beams, i))
-    if (cache != nullptr && mode != MED_ATTN_FULL) {
-        const int crow = (mode == MED_ATTN_DECODE) ? r : b * beams;
-        const int cpos = (mode == MED_ATTN_DECODE) ? pos : i;
-        T* cp = cache + (static_cast<int64_t>(crow) * Tmax + cpos) * (2 * D) + col;
-        *reinterpret_cast<uint32_t*>(cp) = *reinterpret_cast<const uint32_t*>(qp + D);
-        *reinterpret_cast<uint32_t*>(cp + D) = *reinterpret_cast<const uint32_t*>(qp + 2 * D);
-    }
-    auto key_ptr = [&](int j) -> const T* {
-        if (mode == MED_ATTN_DECODE) {
-            if (j == pos) return qkv + r * ld + D + col;
-            const int src = anc[static_cast<int64_t>(r) * Tmax + j];
-            return cache + (static_cast<int64_t>(src) * Tmax + j) * (2 * D) + col;
-        }
-        return qkv + (static_cast<int64_t>(b) * T_seq + j) * ld + D + col;
-    };
-    const int v_off = (mode == MED_ATTN_DECODE) ? D : D;  // V sits D elements after K in both layouts
-    float mx = -INFINITY;
-    for (int j = 0; j < nkeys; ++j) {
-        const T* kp = key_ptr(j);
-        float d = q0 * to_f<T>(kp[0]) + q1 * to_f<T>(kp[1]);
-        d = warp_sum(d);
-        if (mode == MED_ATTN_FULL && mask != nullptr && mask[b * T_seq + j] == 0) d += -10000.0f;  // med.py:667
-        if (lane == 0) sc[j] = d;
-        mx = fmaxf(mx, d);
-    }
-    __syncwarp();
-    float sum = 0.f;
-    for (int j = lane; j < nkeys; j += 32) {
-        const float e = __expf(sc[j] - mx);
-        sc[j] = e;
-        sum += e;
-    }
-    sum = warp_sum(sum);
-    __syncwarp();
-    const float inv = 1.0f / sum;
-    float a0 = 0.f, a1 = 0.f;
-    for (int j = 0; j < nkeys; ++j) {
-        const T* vp = key_ptr(j) + v_off;
-        const float p = sc[j];
-        a0 += p * to_f<T>(vp[0]);
-        a1 += p * to_f<T>(vp[1]);
-    }
-    T* op = out + static_cast<int64_t>(r) * D + col;
-    op[0] = from_f<T>(a0 * inv);
-    op[1] = from_f<T>(a1 * inv);
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
-// Cross-attention onto the image tokens (BertSelfAttention with is_cross_attention, med.py:160-163): query group g =
-// rows [g*nq, (g+1)*nq) of q [rows, D] attends to the Nv tokens of frame f = frame_of_group[g] (identity when null),
-// whose keys/values were projected once per frame into kv [F, Nv, 2D].  One CTA per (head, group).
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int CA_THREADS = 128;
-constexpr int CA_QCHUNK = 4;
-
-template <typename T>
-__global__ void __launch_bounds__(CA_THREADS)
-    med_cross_attn_kernel(const T* __restrict__ q, const T* __restrict__ kv, const int32_t* __restrict__ frame_of_group,
-                          T* __restrict__ out, int nq, int Nv, int H, float scale) {
-    extern __shared__ float smem[];
-    const int h = blockIdx.x, g = blockIdx.y;
-    const int D = H * 64;
-    const int f = frame_of_group ? frame_of_group[g] : g;
-    float* q_s = smem;                               // [nq][64]
-    float* s_s = q_s + nq * 64;                      // [nq][Nv]
-    float* red = s_s + static_cast<size_t>(nq) * Nv;  // [4 warps][CA_QCHUNK][64]
-    const int t = threadIdx.x;
-    const T* qbase = q + (static_cast<int64_t>(g) * nq) * D + h * 64;
-    for (int i = t; i < nq * 64; i += CA_THREADS) q_s[i] = to_f<T>(qbase[static_cast<int64_t>(i >> 6) * D + (i & 63)]) * scale;
-    __syncthreads();
-    const T* kbase = kv + static_cast<int64_t>(f) * Nv * (2 * D) + h * 64;
-    // scores: one key per thread and pass
-    for (int j = t; j < Nv; j += CA_THREADS) {
-        float k[64];
-        const T* kp = kbase + static_cast<int64_t>(j) * (2 * D);
+    float q[64];
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-            float v8[8];
-            load8<T>(kp + 8 * c, v8);
+    for (int c = 0; c < 8; ++c) {
+        float v8[8];
+        load8<T>(own + 8 * c, v8);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) k[8 * c + e] = v8[e];
-        }
-        for (int qi = 0; qi < nq; ++qi) {
-            const float* qr = q_s + qi * 64;
+        for (int e = 0; e < 8; ++e) q[8 * c + e] = v8[e] * scale;
+    }
+    const int nkeys = pos + 1;
+    float sc[2];
+    int src[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+        const int j = lane + 32 * u;
+        sc[u] = -INFINITY;
+        src[u] = r;
+        if (j < nkeys) {
+            const T* kp;
+            if (j == pos) {
+                kp = own + D;
+            } else {
+                src[u] = anc[static_cast<int64_t>(r) * Tmax + j];
+                kp = cache + (static_cast<int64_t>(src[u]) * Tmax + j) * (2 * D) + h * 64;
+            }
             float d = 0.f;
 #pragma unroll
-            for (int e = 0; e < 64; ++e) d += k[e] * qr[e];
-            s_s[static_cast<size_t>(qi) * Nv + j] = d;
+            for (int c = 0; c < 8; ++c) {
+                float v8[8];
+                load8<T>(kp + 8 * c, v8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d += q[8 * c + e] * v8[e];
+            }
+            sc[u] = d;
         }
     }
-    __syncthreads();
-    // softmax per query row: warp w takes rows w, w+4, ...
-    const int w = t >> 5, lane = t & 31;
-    for (int qi = w; qi < nq; qi += CA_THREADS / 32) {
-        float* row = s_s + static_cast<size_t>(qi) * Nv;
-        float mx = -INFINITY;
-        for (int j = lane; j < Nv; j += 32) mx = fmaxf(mx, row[j]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < Nv; j += 32) {
-            const float e = __expf(row[j] - mx);
-            row[j] = e;
-            sum += e;
-        }
-        sum = warp_sum(sum);
-        const float inv = 1.0f / sum;
-        for (int j = lane; j < Nv; j += 32) row[j] *= inv;
+    const float mx = warp_max(fmaxf(sc[0], sc[1]));
+    float p[2];
+    p[0] = (lane < nkeys) ? __expf(sc[0] - mx) : 0.f;
+    p[1] = (lane + 32 < nkeys) ? __expf(sc[1] - mx) : 0.f;
+    const float inv = 1.0f / warp_sum(p[0] + p[1]);
+    float a0 = 0.f, a1 = 0.f;
+    const int col = h * 64 + 2 * lane;
+    for (int j = 0; j < nkeys; ++j) {
+        const float pj = __shfl_sync(0xffffffffu, j < 32 ? p[0] : p[1], j & 31);
+        const int sj = __shfl_sync(0xffffffffu, j < 32 ? src[0] : src[1], j & 31);
+        const T* vp = (j == pos) ? qkv + static_cast<int64_t>(r) * 3 * D + 2 * D + col
+                                 : cache + (static_cast<int64_t>(sj) * Tmax + j) * (2 * D) + D + col;
+        const uint32_t u = *reinterpret_cast<const uint32_t*>(vp);
+        const T* hv = reinterpret_cast<const T*>(&u);
+        a0 += pj * to_f<T>(hv[0]);
+        a1 += pj * to_f<T>(hv[1]);
     }
-    __syncthreads();
-    // P V: thread = (8 dims, 1 of 16 key lanes); CA_QCHUNK query rows per sweep over V
-    const int dg = t & 7, kl = t >> 3;
-    const T* vbase = kbase + D + dg * 8;
-    for (int q0 = 0; q0 < nq; q0 += CA_QCHUNK) {
-        float acc[CA_QCHUNK][8];
-#pragma unroll
-        for (int c = 0; c < CA_QCHUNK; ++c)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[c][e] = 0.f;
-        for (int j = kl; j < Nv; j += 16) {
-            float v8[8];
-            load8<T>(vbase + static_cast<int64_t>(j) * (2 * D), v8);
-#pragma unroll
-            for (int c = 0; c < CA_QCHUNK; ++c) {
-                const float p = (q0 + c < nq) ? s_s[static_cast<size_t>(q0 + c) * Nv + j] : 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) acc[c][e] += p * v8[e];
-            }
-        }
-        // lanes dg + 8*{0..3} of a warp hold partial sums of the same dims
-#pragma unroll
-        for (int c = 0; c < CA_QCHUNK; ++c)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                float x = acc[c][e];
-                x += __shfl_xor_sync(0xffffffffu, x, 8);
-                x += __shfl_xor_sync(0xffffffffu, x, 16);
-                acc[c][e] = x;
-            }
-        if (lane < 8) {
-#pragma unroll
-            for (int c = 0; c < CA_QCHUNK; ++c)
-#pragma unroll
-                for (int e = 0; e < 8; ++e) red[(w * CA_QCHUNK + c) * 64 + dg * 8 + e] = acc[c][e];
-        }
-        __syncthreads();
-        for (int i = t; i < CA_QCHUNK * 64; i += CA_THREADS) {
-            const int c = i >> 6, d = i & 63;
-            if (q0 + c < nq) {
-                const float x = red[(0 * CA_QCHUNK + c) * 64 + d] + red[(1 * CA_QCHUNK + c) * 64 + d] +
-                                red[(2 * CA_QCHUNK + c) * 64 + d] + red[(3 * CA_QCHUNK + c) * 64 + d];
-                out[(static_cast<int64_t>(g) * nq + q0 + c) * D + h * 64 + d] = from_f<T>(x);
-            }
-        }
-        __syncthreads();
+    T* op = out + static_cast<int64_t>(r) * D + col;
+    T o2[2] = {from_f<T>(a0 * inv), from_f<T>(a1 * inv)};
+    *reinterpret_cast<uint32_t*>(op) = *reinterpret_cast<const uint32_t*>(o2);
+}
+
+// K/V of whole sequences (the prompt) -> cache slots (seq * beams, t): the decode steps of every beam of a frame start from
+// the same prompt prefix.  qkv [n_seq*T, 3D]; one thread per 16 bytes.
+template <typename T>
+__global__ void med_cache_fill_kernel(const T* __restrict__ qkv, T* __restrict__ cache, int64_t n_rows, int T_seq, int D, int Tmax,
+                                      int beams) {
+    const int chunks = 2 * D / 8;
+    const int64_t total = n_rows * chunks;
+    for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
+         i += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+        const int64_t row = i / chunks;
+        const int c = static_cast<int>(i - row * chunks);
+        const int64_t b = row / T_seq;
+        const int t = static_cast<int>(row - b * T_seq);
+        const uint4 val = *reinterpret_cast<const uint4*>(qkv + row * 3 * D + D + c * 8);
+        *reinterpret_cast<uint4*>(cache + ((b * beams) * Tmax + t) * (2 * static_cast<int64_t>(D)) + c * 8) = val;
     }
 }
 
@@ -587,48 +496,34 @@ int med_embed_run(const int32_t* ids, const float* word, const float* pos, float
     return 0;
 }
 
-int med_self_attn_run(const void* qkv, void* cache, const int32_t* anc, const int32_t* mask, void* out, DType dt, int rows, int T_seq,
-                      int H, int mode, int pos, int Tmax, int beams, float scale, cudaStream_t s) {
+int med_self_attn_decode_run(const void* qkv, void* cache, const int32_t* anc, void* out, DType dt, int rows, int H, int pos, int Tmax,
+                             float scale, cudaStream_t s) {
     if (rows <= 0) return 0;
-    const int nkeys_max = (mode == MED_ATTN_DECODE) ? pos + 1 : T_seq;
-    if (nkeys_max > SA_MAX_KEYS) {
-        set_error("med self-attention: %d keys, at most %d supported", nkeys_max, SA_MAX_KEYS);
+    if (pos + 1 > SA_MAX_KEYS || pos >= Tmax) {
+        set_error("med decode self-attention: position %d, at most %d keys / cache length %d", pos, SA_MAX_KEYS, Tmax);
         return 1;
     }
     const int grid = (rows * H + SA_WARPS - 1) / SA_WARPS;
     if (dt == DT_BF16)
-        med_self_attn_kernel<__nv_bfloat16><<<grid, SA_WARPS * 32, 0, s>>>(
-            reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(cache), anc, mask,
-            reinterpret_cast<__nv_bfloat16*>(out), rows, T_seq, H, mode, pos, Tmax, beams, scale);
+        med_self_attn_decode_kernel<__nv_bfloat16><<<grid, SA_WARPS * 32, 0, s>>>(
+            reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(cache), anc,
+            reinterpret_cast<__nv_bfloat16*>(out), rows, H, pos, Tmax, scale);
     else
-        med_self_attn_kernel<__half><<<grid, SA_WARPS * 32, 0, s>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(cache),
-                                                                   anc, mask, reinterpret_cast<__half*>(out), rows, T_seq, H, mode,
-                                                                   pos, Tmax, beams, scale);
+        med_self_attn_decode_kernel<__half><<<grid, SA_WARPS * 32, 0, s>>>(reinterpret_cast<const __half*>(qkv),
+                                                                          reinterpret_cast<__half*>(cache), anc,
+                                                                          reinterpret_cast<__half*>(out), rows, H, pos, Tmax, scale);
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;
 }
 
-int med_cross_attn_run(const void* q, const void* kv, const int32_t* frame_of_group, void* out, DType dt, int groups, int nq, int Nv,
-                       int H, float scale, cudaStream_t s) {
-    if (groups <= 0) return 0;
-    const size_t smem = (static_cast<size_t>(nq) * 64 + static_cast<size_t>(nq) * Nv + 4 * CA_QCHUNK * 64) * sizeof(float);
-    if (smem > 200 * 1024) {
-        set_error("med cross-attention: %d query rows x %d image tokens need %zu bytes of shared memory", nq, Nv, smem);
-        return 1;
-    }
-    const dim3 grid(H, groups);
-    if (dt == DT_BF16) {
-        auto k = med_cross_attn_kernel<__nv_bfloat16>;
-        if (smem > 48 * 1024) VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        k<<<grid, CA_THREADS, smem, s>>>(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(kv),
-                                         frame_of_group, reinterpret_cast<__nv_bfloat16*>(out), nq, Nv, H, scale);
-    } else {
-        auto k = med_cross_attn_kernel<__half>;
-        if (smem > 48 * 1024) VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        k<<<grid, CA_THREADS, smem, s>>>(reinterpret_cast<const __half*>(q), reinterpret_cast<const __half*>(kv), frame_of_group,
-                                         reinterpret_cast<__half*>(out), nq, Nv, H, scale);
-    }
+int med_cache_fill_run(const void* qkv, void* cache, DType dt, int64_t n_rows, int T_seq, int D, int Tmax, int beams, cudaStream_t s) {
+    if (n_rows <= 0) return 0;
+    const int grid = grid_for(n_rows * (2 * D / 8), 256);
+    // 16-bit payload is only moved: one instantiation serves both operand types
+    med_cache_fill_kernel<__half><<<grid, 256, 0, s>>>(reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(cache), n_rows,
+                                                      T_seq, D, Tmax, beams);
+    (void)dt;
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;

@@ -227,14 +227,23 @@ int run_stack(const vidil_med* m, const StackPlan& pl, const StackBufs& b, const
     for (int i = 0; i < c.depth; ++i) {
         const MedLayer& ly = *m->layers[i];
         if (gemm_run(pl.sqkv[i], s)) return 1;
-        void* cache_l = a.cache ? reinterpret_cast<uint8_t*>(a.cache) + static_cast<size_t>(i) * a.cache_layer_elems * 2 : nullptr;
-        if (med_self_attn_run(b.qkv, cache_l, a.anc, a.mask, b.attn, m->dt, rows, a.T_seq, H, a.mode, a.pos, a.Tmax, a.beams, 0.125f, s))
-            return 1;
+        uint8_t* cache_l = a.cache ? reinterpret_cast<uint8_t*>(a.cache) + static_cast<size_t>(i) * a.cache_layer_elems * 2 : nullptr;
+        const uint8_t* qkv8 = reinterpret_cast<const uint8_t*>(b.qkv);
+        if (a.mode == MED_ATTN_DECODE) {
+            if (med_self_attn_decode_run(b.qkv, cache_l, a.anc, b.attn, m->dt, rows, H, a.pos, a.Tmax, 0.125f, s)) return 1;
+        } else {
+            if (attention_x_run(b.qkv, 3 * D, qkv8 + static_cast<size_t>(D) * 2, qkv8 + static_cast<size_t>(2 * D) * 2, 3 * D, nullptr,
+                                a.mask, b.attn, D, m->dt, rows / a.T_seq, a.T_seq, a.T_seq, H, a.mode == MED_ATTN_CAUSAL, 0.125f, s))
+                return 1;
+            if (cache_l && med_cache_fill_run(b.qkv, cache_l, m->dt, rows, a.T_seq, D, a.Tmax, a.beams, s)) return 1;
+        }
         if (gemm_run(pl.so[i], s)) return 1;
         if (layernorm_post_run(b.resid, ly.sln_w.f(), ly.sln_b.f(), b.xn, m->dt, rows, D, eps, s)) return 1;
         if (gemm_run(pl.cq[i], s)) return 1;
         const void* kv_l = reinterpret_cast<const uint8_t*>(a.cross_kv) + static_cast<size_t>(i) * a.cross_layer_elems * 2;
-        if (med_cross_attn_run(b.qc, kv_l, a.frame_of_group, b.attn, m->dt, a.groups, a.nq, a.Nv, H, 0.125f, s)) return 1;
+        if (attention_x_run(b.qc, D, kv_l, reinterpret_cast<const uint8_t*>(kv_l) + static_cast<size_t>(D) * 2, 2 * D, a.frame_of_group,
+                            nullptr, b.attn, D, m->dt, a.groups, a.nq, a.Nv, H, false, 0.125f, s))
+            return 1;
         if (gemm_run(pl.co[i], s)) return 1;
         if (layernorm_post_run(b.resid, ly.cln_w.f(), ly.cln_b.f(), b.xn, m->dt, rows, D, eps, s)) return 1;
         if (gemm_run(pl.fc1[i], s)) return 1;
