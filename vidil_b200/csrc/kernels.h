@@ -181,6 +181,16 @@ int med_embed_run(const int32_t* ids, const float* word, const float* pos, float
 // new K/V at slot (row, pos); earlier keys are read from slot (anc[row][t], t)
 int med_self_attn_decode_run(const void* qkv, void* cache, const int32_t* anc, void* out, DType dt, int rows, int H, int pos, int Tmax,
                              float scale, cudaStream_t s);
+// decode step: the nq beams of frame f (rows f*nq.. of q [F*nq, D]) attend to kv [F, Nv, 2D] -> out [F*nq, D].  With a prepared
+// CrossKvMap (one tensor map over the cross K/V of all layers, [depth*F*Nv, 2D]) the K/V tiles come in by TMA.
+struct CrossKvMap {
+    CUtensorMap map;
+    bool valid = false;
+    int F = 0, Nv = 0, H = 0, box_rows = 0, n_box = 0;
+};
+int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, int Nv, int H);
+int med_cross_attn_decode_run(const CrossKvMap* map, int layer, const void* q, const void* kv, void* out, DType dt, int F, int nq,
+                              int Nv, int H, float scale, cudaStream_t s);
 // K/V of whole sequences, qkv [n_seq*T_seq, 3D] -> cache slots (seq*beams, t)
 int med_cache_fill_run(const void* qkv, void* cache, DType dt, int64_t n_rows, int T_seq, int D, int Tmax, int beams, cudaStream_t s);
 // list l scans logits row l*row_mul: log_softmax, ban_token excluded (-1: none), + beam_scores[l] -> nc best (score, token)

@@ -11,6 +11,7 @@
 #include <math.h>
 
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace vidil {
 namespace {
@@ -84,80 +85,315 @@ __global__ void med_embed_kernel(const int32_t* __restrict__ ids, const float* _
 // med.py:951-955).  One warp per (row, head): lane j scores key j (a full 128-byte K row per lane, q broadcast), the
 // softmax is two warp reductions, then lane l accumulates dims 2l, 2l+1 of P.V with the key loop's addresses known up front.
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int SA_WARPS = 4;
+constexpr int SA_WARPS = 8;
 constexpr int SA_MAX_KEYS = 64;
 
+// 8 lanes share one 128-byte K or V row (16 bytes each), 4 rows per warp-wide load.
 template <typename T>
 __global__ void __launch_bounds__(SA_WARPS * 32)
     med_self_attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ anc, T* __restrict__ out,
                                 int rows, int H, int pos, int Tmax, float scale) {
+    __shared__ float s_sc[SA_WARPS][SA_MAX_KEYS];
+    __shared__ int s_src[SA_WARPS][SA_MAX_KEYS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int item = blockIdx.x * SA_WARPS + w;
     if (item >= rows * H) return;
     const int r = item / H, h = item - r * H;
     const int D = H * 64;
+    const int c = lane & 7, kq = lane >> 3;
     const T* own = qkv + static_cast<int64_t>(r) * 3 * D + h * 64;  // q | +D: k | +2D: v of the new token
     // the new token's K/V go to slot (r, pos): lanes 0..7 copy K, 8..15 copy V, 16 bytes each
     if (lane < 16) {
-        const int part = lane >> 3, c = lane & 7;
-        T* dst = cache + (static_cast<int64_t>(r) * Tmax + pos) * (2 * D) + part * D + h * 64 + c * 8;
-        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(own + (1 + part) * D + c * 8);
+        T* dst = cache + (static_cast<int64_t>(r) * Tmax + pos) * (2 * D) + kq * D + h * 64 + c * 8;
+        *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(own + (1 + kq) * D + c * 8);
     }
-    float q[64];
+    float q[8];
+    load8<T>(own + 8 * c, q);
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
-        float v8[8];
-        load8<T>(own + 8 * c, v8);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) q[8 * c + e] = v8[e] * scale;
-    }
+    for (int e = 0; e < 8; ++e) q[e] *= scale;
     const int nkeys = pos + 1;
-    float sc[2];
-    int src[2];
+    float* sc = s_sc[w];
+    int* srcs = s_src[w];
+    for (int j0 = 0; j0 < nkeys; j0 += 4) {   // warp-uniform trip count: the shuffles below need every lane
+        const int j = j0 + kq;
+        const bool valid = j < nkeys;
+        int src = r;
+        const T* kp = own + D;
+        if (valid && j != pos) {
+            src = anc[static_cast<int64_t>(r) * Tmax + j];
+            kp = cache + (static_cast<int64_t>(src) * Tmax + j) * (2 * D) + h * 64;
+        }
+        float k8[8];
+        load8<T>(kp + 8 * c, k8);
+        float d = 0.f;
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-        const int j = lane + 32 * u;
-        sc[u] = -INFINITY;
-        src[u] = r;
-        if (j < nkeys) {
-            const T* kp;
-            if (j == pos) {
-                kp = own + D;
-            } else {
-                src[u] = anc[static_cast<int64_t>(r) * Tmax + j];
-                kp = cache + (static_cast<int64_t>(src[u]) * Tmax + j) * (2 * D) + h * 64;
-            }
-            float d = 0.f;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) {
-                float v8[8];
-                load8<T>(kp + 8 * c, v8);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) d += q[8 * c + e] * v8[e];
-            }
-            sc[u] = d;
+        for (int e = 0; e < 8; ++e) d += q[e] * k8[e];
+        d += __shfl_xor_sync(0xffffffffu, d, 1);
+        d += __shfl_xor_sync(0xffffffffu, d, 2);
+        d += __shfl_xor_sync(0xffffffffu, d, 4);
+        if (valid && c == 0) {
+            sc[j] = d;
+            srcs[j] = src;
         }
     }
-    const float mx = warp_max(fmaxf(sc[0], sc[1]));
-    float p[2];
-    p[0] = (lane < nkeys) ? __expf(sc[0] - mx) : 0.f;
-    p[1] = (lane + 32 < nkeys) ? __expf(sc[1] - mx) : 0.f;
-    const float inv = 1.0f / warp_sum(p[0] + p[1]);
-    float a0 = 0.f, a1 = 0.f;
-    const int col = h * 64 + 2 * lane;
-    for (int j = 0; j < nkeys; ++j) {
-        const float pj = __shfl_sync(0xffffffffu, j < 32 ? p[0] : p[1], j & 31);
-        const int sj = __shfl_sync(0xffffffffu, j < 32 ? src[0] : src[1], j & 31);
-        const T* vp = (j == pos) ? qkv + static_cast<int64_t>(r) * 3 * D + 2 * D + col
-                                 : cache + (static_cast<int64_t>(sj) * Tmax + j) * (2 * D) + D + col;
-        const uint32_t u = *reinterpret_cast<const uint32_t*>(vp);
-        const T* hv = reinterpret_cast<const T*>(&u);
-        a0 += pj * to_f<T>(hv[0]);
-        a1 += pj * to_f<T>(hv[1]);
+    __syncwarp();
+    const float s0 = lane < nkeys ? sc[lane] : -INFINITY, s1 = lane + 32 < nkeys ? sc[lane + 32] : -INFINITY;
+    const float mx = warp_max(fmaxf(s0, s1));
+    const float p0 = lane < nkeys ? __expf(s0 - mx) : 0.f, p1 = lane + 32 < nkeys ? __expf(s1 - mx) : 0.f;
+    const float inv = 1.0f / warp_sum(p0 + p1);
+    __syncwarp();
+    if (lane < nkeys) sc[lane] = p0 * inv;
+    if (lane + 32 < nkeys) sc[lane + 32] = p1 * inv;
+    __syncwarp();
+    float acc[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[e] = 0.f;
+    for (int j = kq; j < nkeys; j += 4) {
+        const T* vp = (j == pos) ? own + 2 * D : cache + (static_cast<int64_t>(srcs[j]) * Tmax + j) * (2 * D) + D + h * 64;
+        float v8[8];
+        load8<T>(vp + 8 * c, v8);
+        const float p = sc[j];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[e] += p * v8[e];
     }
-    T* op = out + static_cast<int64_t>(r) * D + col;
-    T o2[2] = {from_f<T>(a0 * inv), from_f<T>(a1 * inv)};
-    *reinterpret_cast<uint32_t*>(op) = *reinterpret_cast<const uint32_t*>(o2);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 8);
+        acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], 16);
+    }
+    if (kq == 0) {
+        T o8[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o8[e] = from_f<T>(acc[e]);
+        *reinterpret_cast<uint4*>(out + static_cast<int64_t>(r) * D + h * 64 + c * 8) = *reinterpret_cast<const uint4*>(o8);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode-step cross-attention: the NQ beams of frame f (rows f*NQ .. f*NQ+NQ-1 of q [rows, D]) attend to the frame's Nv image
+// tokens, kv [F, Nv, 2D].  One CTA per (head, frame) streams the frame's K rows, then its V rows, exactly once with 16-byte
+// loads (8 lanes per 128-byte row, 4 rows in flight per thread): HBM-bound on reading kv — 2*Nv*128 bytes per CTA — which
+// no amount of query-side work can hide, so the tensor cores are left out here.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int CD_THREADS = 128;
+
+template <typename T, int NQ>
+__global__ void __launch_bounds__(CD_THREADS)
+    med_cross_attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out, int Nv, int H, float scale) {
+    extern __shared__ float smem[];
+    float* s_s = smem;                                   // [NQ][Nv]
+    float* red = smem + static_cast<size_t>(NQ) * Nv;    // [4 warps][NQ][64]
+    const int h = blockIdx.x, f = blockIdx.y;
+    const int D = H * 64;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int c = t & 7, kl = t >> 3;                    // 16-byte chunk of the row, key lane 0..15
+    float qv[NQ][8];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        load8<T>(q + (static_cast<int64_t>(f) * NQ + i) * D + h * 64 + c * 8, qv[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qv[i][e] *= scale;
+    }
+    const T* kbase = kv + static_cast<int64_t>(f) * Nv * (2 * D) + h * 64 + c * 8;
+    constexpr int U = 4;
+    for (int jb = 0; jb < Nv; jb += 16 * U) {   // warp-uniform trip count: the shuffles below need every lane
+        const int j0 = jb + kl;
+        float k8[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + 16 * u;
+            load8<T>(kbase + static_cast<int64_t>(j < Nv ? j : Nv - 1) * (2 * D), k8[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + 16 * u;
+#pragma unroll
+            for (int i = 0; i < NQ; ++i) {
+                float d = 0.f;
+#pragma unroll
+                for (int e = 0; e < 8; ++e) d += qv[i][e] * k8[u][e];
+                d += __shfl_xor_sync(0xffffffffu, d, 1);
+                d += __shfl_xor_sync(0xffffffffu, d, 2);
+                d += __shfl_xor_sync(0xffffffffu, d, 4);
+                if (c == 0 && j < Nv) s_s[i * Nv + j] = d;
+            }
+        }
+    }
+    __syncthreads();
+    if (w < NQ) {
+        float* row = s_s + w * Nv;
+        float mx = -INFINITY;
+        for (int j = lane; j < Nv; j += 32) mx = fmaxf(mx, row[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < Nv; j += 32) {
+            const float e = __expf(row[j] - mx);
+            row[j] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / warp_sum(sum);
+        for (int j = lane; j < Nv; j += 32) row[j] *= inv;
+    }
+    __syncthreads();
+    float acc[NQ][8];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+    const T* vbase = kbase + D;
+    for (int j0 = kl; j0 < Nv; j0 += 16 * U) {
+        float v8[U][8];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + 16 * u;
+            if (j < Nv) load8<T>(vbase + static_cast<int64_t>(j) * (2 * D), v8[u]);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const int j = j0 + 16 * u;
+            if (j < Nv) {
+#pragma unroll
+                for (int i = 0; i < NQ; ++i) {
+                    const float p = s_s[i * Nv + j];
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) acc[i][e] += p * v8[u][e];
+                }
+            }
+        }
+    }
+    // lanes c + 8*{0..3} of a warp hold partial sums of the same dims
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = acc[i][e];
+            x += __shfl_xor_sync(0xffffffffu, x, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            acc[i][e] = x;
+        }
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) red[(w * NQ + i) * 64 + c * 8 + e] = acc[i][e];
+    }
+    __syncthreads();
+    for (int i = t; i < NQ * 64; i += CD_THREADS) {
+        const int qi = i >> 6, d = i & 63;
+        const float x = red[(0 * NQ + qi) * 64 + d] + red[(1 * NQ + qi) * 64 + d] + red[(2 * NQ + qi) * 64 + d] + red[(3 * NQ + qi) * 64 + d];
+        out[(static_cast<int64_t>(f) * NQ + qi) * D + h * 64 + d] = from_f<T>(x);
+    }
+}
+
+// The same computation with the frame's K and V tiles brought into shared memory by TMA (two bulk tensor loads per box of
+// <= 256 rows, issued up front, one mbarrier for K and one for V): ~50 KB in flight per CTA instead of 8 KB of register loads,
+// which is what it takes to keep HBM busy (Little: 7.7 TB/s x ~0.8 us = 42 KB per SM).  kv_map views the cross K/V of ALL layers
+// as one [depth*F*Nv, 2D] matrix with a [box_rows, 64] box; row0 = layer * F * Nv.
+template <typename T, int NQ>
+__global__ void __launch_bounds__(CD_THREADS)
+    med_cross_attn_decode_tma_kernel(const __grid_constant__ CUtensorMap kv_map, const T* __restrict__ q, T* __restrict__ out,
+                                     int row0, int Nv, int box_rows, int n_box, int H, float scale) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    const int h = blockIdx.x, f = blockIdx.y;
+    const int D = H * 64;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const int c = t & 7, kl = t >> 3;
+    const uint32_t tile_bytes = static_cast<uint32_t>(n_box) * box_rows * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                                  // 2 mbarriers in the first 128 bytes
+    uint8_t* sK = smem_raw + 128;
+    uint8_t* sV = sK + tile_bytes;
+    float* s_s = reinterpret_cast<float*>(sV + tile_bytes);                                  // [NQ][Nv]
+    float* red = s_s + static_cast<size_t>(NQ) * Nv;                                         // [4 warps][NQ][64]
+    if (t == 0) {
+        ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[1], 1);
+        ptx::fence_mbar_init();
+    }
+    __syncthreads();
+    if (t == 0) {
+        const int r = row0 + f * Nv;
+        ptx::mbar_arrive_expect_tx(&bars[0], tile_bytes);
+        for (int b = 0; b < n_box; ++b) ptx::tma_load_2d(&kv_map, &bars[0], sK + static_cast<size_t>(b) * box_rows * 128, h * 64, r + b * box_rows);
+        ptx::mbar_arrive_expect_tx(&bars[1], tile_bytes);
+        for (int b = 0; b < n_box; ++b)
+            ptx::tma_load_2d(&kv_map, &bars[1], sV + static_cast<size_t>(b) * box_rows * 128, D + h * 64, r + b * box_rows);
+    }
+    float qv[NQ][8];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i) {
+        load8<T>(q + (static_cast<int64_t>(f) * NQ + i) * D + h * 64 + c * 8, qv[i]);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) qv[i][e] *= scale;
+    }
+    ptx::mbar_wait(&bars[0], 0);
+    for (int jb = 0; jb < Nv; jb += 16) {      // warp-uniform trip count
+        const int j = jb + kl;
+        float k8[8];
+        load8<T>(reinterpret_cast<const T*>(sK + static_cast<size_t>(j < Nv ? j : Nv - 1) * 128) + c * 8, k8);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            float d = 0.f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) d += qv[i][e] * k8[e];
+            d += __shfl_xor_sync(0xffffffffu, d, 1);
+            d += __shfl_xor_sync(0xffffffffu, d, 2);
+            d += __shfl_xor_sync(0xffffffffu, d, 4);
+            if (c == 0 && j < Nv) s_s[i * Nv + j] = d;
+        }
+    }
+    __syncthreads();
+    if (w < NQ) {
+        float* row = s_s + w * Nv;
+        float mx = -INFINITY;
+        for (int j = lane; j < Nv; j += 32) mx = fmaxf(mx, row[j]);
+        mx = warp_max(mx);
+        float sum = 0.f;
+        for (int j = lane; j < Nv; j += 32) {
+            const float e = __expf(row[j] - mx);
+            row[j] = e;
+            sum += e;
+        }
+        const float inv = 1.0f / warp_sum(sum);
+        for (int j = lane; j < Nv; j += 32) row[j] *= inv;
+    }
+    __syncthreads();
+    ptx::mbar_wait(&bars[1], 0);
+    float acc[NQ][8];
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
+    for (int j = kl; j < Nv; j += 16) {
+        float v8[8];
+        load8<T>(reinterpret_cast<const T*>(sV + static_cast<size_t>(j) * 128) + c * 8, v8);
+#pragma unroll
+        for (int i = 0; i < NQ; ++i) {
+            const float p = s_s[i * Nv + j];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[i][e] += p * v8[e];
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NQ; ++i)
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            float x = acc[i][e];
+            x += __shfl_xor_sync(0xffffffffu, x, 8);
+            x += __shfl_xor_sync(0xffffffffu, x, 16);
+            acc[i][e] = x;
+        }
+    if (lane < 8) {
+#pragma unroll
+        for (int i = 0; i < NQ; ++i)
+#pragma unroll
+            for (int e = 0; e < 8; ++e) red[(w * NQ + i) * 64 + c * 8 + e] = acc[i][e];
+    }
+    __syncthreads();
+    for (int i = t; i < NQ * 64; i += CD_THREADS) {
+        const int qi = i >> 6, d = i & 63;
+        const float x = red[(0 * NQ + qi) * 64 + d] + red[(1 * NQ + qi) * 64 + d] + red[(2 * NQ + qi) * 64 + d] + red[(3 * NQ + qi) * 64 + d];
+        out[(static_cast<int64_t>(f) * NQ + qi) * D + h * 64 + d] = from_f<T>(x);
+    }
 }
 
 // K/V of whole sequences (the prompt) -> cache slots (seq * beams, t): the decode steps of every beam of a frame start from
@@ -207,27 +443,38 @@ __global__ void __launch_bounds__(TK_THREADS)
     }
     float m = -INFINITY, s = 0.f;
     const int v4 = V / 4;
-    for (int i4 = t; i4 < v4; i4 += TK_THREADS) {
-        const float4 x4 = reinterpret_cast<const float4*>(row)[i4];
-        const float xs[4] = {x4.x, x4.y, x4.z, x4.w};
+    constexpr int TU = 4;   // independent 16-byte loads in flight per thread
+    for (int base = t; base < v4; base += TK_THREADS * TU) {
+        float4 x4s[TU];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-            const float x = xs[e];
-            const int idx = 4 * i4 + e;
-            if (x > m) {
-                s = s * __expf(m - x) + 1.0f;
-                m = x;
-            } else {
-                s += __expf(x - m);
-            }
-            if (idx != ban_token && cand_better(x, idx, tv[TK_MAX_NC - 1], ti[TK_MAX_NC - 1])) {
-                tv[TK_MAX_NC - 1] = x;
-                ti[TK_MAX_NC - 1] = idx;
+        for (int u = 0; u < TU; ++u) {
+            const int i4 = base + u * TK_THREADS;
+            x4s[u] = (i4 < v4) ? reinterpret_cast<const float4*>(row)[i4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
 #pragma unroll
-                for (int c = TK_MAX_NC - 1; c > 0; --c) {
-                    if (cand_better(tv[c], ti[c], tv[c - 1], ti[c - 1])) {
-                        const float fv = tv[c]; tv[c] = tv[c - 1]; tv[c - 1] = fv;
-                        const int fi = ti[c]; ti[c] = ti[c - 1]; ti[c - 1] = fi;
+        for (int u = 0; u < TU; ++u) {
+            const int i4 = base + u * TK_THREADS;
+            if (i4 >= v4) break;
+            const float xs[4] = {x4s[u].x, x4s[u].y, x4s[u].z, x4s[u].w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float x = xs[e];
+                const int idx = 4 * i4 + e;
+                if (x > m) {
+                    s = s * __expf(m - x) + 1.0f;
+                    m = x;
+                } else {
+                    s += __expf(x - m);
+                }
+                if (idx != ban_token && cand_better(x, idx, tv[TK_MAX_NC - 1], ti[TK_MAX_NC - 1])) {
+                    tv[TK_MAX_NC - 1] = x;
+                    ti[TK_MAX_NC - 1] = idx;
+#pragma unroll
+                    for (int c = TK_MAX_NC - 1; c > 0; --c) {
+                        if (cand_better(tv[c], ti[c], tv[c - 1], ti[c - 1])) {
+                            const float fv = tv[c]; tv[c] = tv[c - 1]; tv[c - 1] = fv;
+                            const int fi = ti[c]; ti[c] = ti[c - 1]; ti[c - 1] = fi;
+                        }
                     }
                 }
             }
@@ -515,6 +762,88 @@ int med_self_attn_decode_run(const void* qkv, void* cache, const int32_t* anc, v
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;
+}
+
+template <typename T, int NQ>
+int launch_cross_decode(const void* q, const void* kv, void* out, int F, int Nv, int H, float scale, cudaStream_t s) {
+    const size_t smem = (static_cast<size_t>(NQ) * Nv + 4 * NQ * 64) * sizeof(float);
+    auto k = med_cross_attn_decode_kernel<T, NQ>;
+    if (smem > 48 * 1024) VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k<<<dim3(H, F), CD_THREADS, smem, s>>>(reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(kv), reinterpret_cast<T*>(out), Nv, H,
+                                           scale);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+template <typename T, int NQ>
+int launch_cross_decode_tma(const CrossKvMap& m, int layer, const void* q, void* out, float scale, cudaStream_t s) {
+    const size_t tile = static_cast<size_t>(m.n_box) * m.box_rows * 128;
+    const size_t smem = 128 + 2 * tile + (static_cast<size_t>(NQ) * m.Nv + 4 * NQ * 64) * sizeof(float);
+    auto k = med_cross_attn_decode_tma_kernel<T, NQ>;
+    VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    k<<<dim3(m.H, m.F), CD_THREADS, smem, s>>>(m.map, reinterpret_cast<const T*>(q), reinterpret_cast<T*>(out), layer * m.F * m.Nv, m.Nv,
+                                               m.box_rows, m.n_box, m.H, scale);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, int Nv, int H) {
+    typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+    static EncodeTiledFn fn = nullptr;
+    if (fn == nullptr) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    m.valid = false;
+    m.F = F; m.Nv = Nv; m.H = H;
+    m.n_box = (Nv + 255) / 256;
+    m.box_rows = (Nv + m.n_box - 1) / m.n_box;
+    const int64_t rows = static_cast<int64_t>(depth) * F * Nv;
+    const size_t smem = 128 + 2 * static_cast<size_t>(m.n_box) * m.box_rows * 128 + (4 * static_cast<size_t>(Nv) + 4 * 4 * 64) * sizeof(float);
+    if (fn == nullptr || smem > 200 * 1024 || rows > 0x7fffffffLL) return 0;   // the register-load kernel serves these cases
+    const cuuint64_t dims[2] = {static_cast<cuuint64_t>(2 * H * 64), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t strides[1] = {static_cast<cuuint64_t>(2 * H * 64) * 2};
+    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(m.box_rows)};
+    const cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(&m.map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ckv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (cross K/V) failed with CUresult %d", static_cast<int>(r));
+        return 1;
+    }
+    m.valid = true;
+    return 0;
+}
+
+int med_cross_attn_decode_run(const CrossKvMap* map, int layer, const void* q, const void* kv, void* out, DType dt, int F, int nq,
+                              int Nv, int H, float scale, cudaStream_t s) {
+    if (F <= 0) return 0;
+    if (nq < 1 || nq > 4 || Nv > 8192 || F > 65535) {
+        set_error("med decode cross-attention: %d beams (1..4), %d image tokens (<= 8192), %d frames (<= 65535)", nq, Nv, F);
+        return 1;
+    }
+    const bool tma = map != nullptr && map->valid && map->F == F && map->Nv == Nv && map->H == H;
+#define VIDIL_CD(NQ)                                                                                                      \
+    case NQ:                                                                                                              \
+        if (tma)                                                                                                          \
+            return dt == DT_BF16 ? launch_cross_decode_tma<__nv_bfloat16, NQ>(*map, layer, q, out, scale, s)              \
+                                 : launch_cross_decode_tma<__half, NQ>(*map, layer, q, out, scale, s);                    \
+        return dt == DT_BF16 ? launch_cross_decode<__nv_bfloat16, NQ>(q, kv, out, F, Nv, H, scale, s)                     \
+                             : launch_cross_decode<__half, NQ>(q, kv, out, F, Nv, H, scale, s);
+    switch (nq) {
+        VIDIL_CD(1)
+        VIDIL_CD(2)
+        VIDIL_CD(3)
+        VIDIL_CD(4)
+    }
+#undef VIDIL_CD
+    return 1;
 }
 
 int med_cache_fill_run(const void* qkv, void* cache, DType dt, int64_t n_rows, int T_seq, int D, int Tmax, int beams, cudaStream_t s) {

@@ -208,6 +208,7 @@ struct AttnArgs {
     int groups = 0, nq = 0;          // cross-attention: query groups and rows per group
     const int32_t* frame_of_group = nullptr;
     const void* cross_kv = nullptr;  // [depth][F][Nv][2D]
+    const CrossKvMap* kv_map = nullptr;  // decode: TMA view of cross_kv
     size_t cross_layer_elems = 0;
     int Nv = 0;
     void* cache = nullptr;           // [depth][R][Tmax][2D] or null
@@ -241,9 +242,12 @@ int run_stack(const vidil_med* m, const StackPlan& pl, const StackBufs& b, const
         if (layernorm_post_run(b.resid, ly.sln_w.f(), ly.sln_b.f(), b.xn, m->dt, rows, D, eps, s)) return 1;
         if (gemm_run(pl.cq[i], s)) return 1;
         const void* kv_l = reinterpret_cast<const uint8_t*>(a.cross_kv) + static_cast<size_t>(i) * a.cross_layer_elems * 2;
-        if (attention_x_run(b.qc, D, kv_l, reinterpret_cast<const uint8_t*>(kv_l) + static_cast<size_t>(D) * 2, 2 * D, a.frame_of_group,
-                            nullptr, b.attn, D, m->dt, a.groups, a.nq, a.Nv, H, false, 0.125f, s))
+        if (a.mode == MED_ATTN_DECODE && a.frame_of_group == nullptr) {
+            if (med_cross_attn_decode_run(a.kv_map, i, b.qc, kv_l, b.attn, m->dt, a.groups, a.nq, a.Nv, H, 0.125f, s)) return 1;
+        } else if (attention_x_run(b.qc, D, kv_l, reinterpret_cast<const uint8_t*>(kv_l) + static_cast<size_t>(D) * 2, 2 * D,
+                                   a.frame_of_group, nullptr, b.attn, D, m->dt, a.groups, a.nq, a.Nv, H, false, 0.125f, s)) {
             return 1;
+        }
         if (gemm_run(pl.co[i], s)) return 1;
         if (layernorm_post_run(b.resid, ly.cln_w.f(), ly.cln_b.f(), b.xn, m->dt, rows, D, eps, s)) return 1;
         if (gemm_run(pl.fc1[i], s)) return 1;
@@ -597,6 +601,9 @@ int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_
     if (cur_len < max_length) {
         StackPlan pl;
         if (plan_stack(med, pl, w.b, R)) return 1;
+        CrossKvMap kv_map;
+        if (med_cross_kv_map_prepare(kv_map, w.ckv, c.depth, F, n_img_tokens, c.num_heads)) return 1;
+        a.kv_map = &kv_map;
         a.mode = MED_ATTN_DECODE;
         a.T_seq = 1;
         a.nq = K;
