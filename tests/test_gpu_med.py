@@ -256,3 +256,23 @@ def test_med_errors_are_loud(cuda):
     with pytest.raises(RuntimeError):          # max_length beyond the 64-token limit of the search state
         m.generate(input_ids=torch.tensor([sp["prompt"]] * 2), max_length=100, num_beams=3, eos_token_id=sp["eos"],
                    encoder_hidden_states=enc.to(cuda))
+
+
+def test_itm_padding_columns_do_not_matter(cuda):
+    """blip_itm.py:46 pads every caption to 35 tokens; the [ENC]-row logits are the same whether the all-padding columns are
+    run (hidden requested) or dropped (cls only) — up to the different GEMM row count's tile rounding, i.e. exactly."""
+    name = "tiny"
+    m, sd = _itm(name, "bf16", cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(3, 7, c["encoder_width"], seed=9).to(cuda)
+    cap, mask = W.caption_ids(name, 3, 12, seed=4)
+    cap[:, 0] = sp["enc"]
+    pad_ids = torch.cat([cap, torch.zeros(3, 23, dtype=torch.long)], 1)
+    pad_mask = torch.cat([mask, torch.zeros(3, 23, dtype=torch.long)], 1)
+    hidden, _, full = m.run(pad_ids, pad_mask, enc, want_hidden=True, want_cls=True)       # all 35 columns
+    _, _, trimmed = m.run(pad_ids, pad_mask, enc, want_hidden=False, want_cls=True)        # padding columns dropped
+    assert hidden.shape[1] == 35
+    assert torch.equal(full, trimmed)
+    with torch.no_grad():
+        ref = med_oracle.itm_logits(sd, enc.cpu(), pad_ids, pad_mask, c["num_attention_heads"], c["num_hidden_layers"])
+    assert (trimmed.cpu() - ref).abs().max() < 8e-2

@@ -420,69 +420,88 @@ __global__ void med_cache_fill_kernel(const T* __restrict__ qkv, T* __restrict__
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int TK_THREADS = 256;
 constexpr int TK_MAX_NC = 8;
+constexpr int TK_CAP = 1024;  // candidate list capacity (shared memory)
 
 __device__ __forceinline__ bool cand_better(float v, int i, float v2, int i2) { return v > v2 || (v == v2 && i < i2); }
 
+// Best (value, index) of the block under cand_better; every thread gets the winner.  Two __syncthreads per call.
+__device__ __forceinline__ void block_argmax(float& v, int& i, float* s_v, int* s_i) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
+        const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
+        if (cand_better(v2, i2, v, i)) {
+            v = v2;
+            i = i2;
+        }
+    }
+    __syncthreads();  // the previous call's readers are done with s_v / s_i
+    if (lane == 0) {
+        s_v[w] = v;
+        s_i[w] = i;
+    }
+    __syncthreads();
+    v = s_v[0];
+    i = s_i[0];
+#pragma unroll
+    for (int k = 1; k < TK_THREADS / 32; ++k)
+        if (cand_better(s_v[k], s_i[k], v, i)) {
+            v = s_v[k];
+            i = s_i[k];
+        }
+}
+
+// Pass 1 streams the row once for the log-sum-exp and each thread's largest admissible logit; the nc-th largest of those
+// 256 thread maxima is a lower bound of the row's nc-th largest value, so pass 2 (the row is in L2 by then) only has to
+// collect the handful of elements at or above it, from which the block picks the nc best exactly — ties to the lowest token
+// id, like a stable descending sort.  Keeping a sorted top-nc list per thread instead costs ~10x more: with 120 elements per
+// thread a quarter of them trigger an insertion, and a warp diverges on almost every element.
 __global__ void __launch_bounds__(TK_THREADS)
     med_logits_topk_kernel(const float* __restrict__ logits, int64_t ld, int row_mul, const float* __restrict__ beam_scores, int V,
                            int nc, int ban_token, float* __restrict__ cand_score, int32_t* __restrict__ cand_tok) {
     __shared__ float s_red[TK_THREADS / 32];
     __shared__ float s_v[TK_THREADS / 32];
     __shared__ int s_i[TK_THREADS / 32];
-    __shared__ int s_owner[TK_THREADS / 32];
     __shared__ float s_m, s_l;
-    __shared__ int s_win;
+    __shared__ int s_cnt;
+    __shared__ float c_v[TK_CAP];
+    __shared__ int c_i[TK_CAP];
     const int list = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
     const float* row = logits + static_cast<int64_t>(list) * row_mul * ld;
-    float tv[TK_MAX_NC];
-    int ti[TK_MAX_NC];
-#pragma unroll
-    for (int c = 0; c < TK_MAX_NC; ++c) {
-        tv[c] = -INFINITY;
-        ti[c] = 0x7fffffff;
-    }
-    float m = -INFINITY, s = 0.f;
+    const float4* row4 = reinterpret_cast<const float4*>(row);
     const int v4 = V / 4;
-    constexpr int TU = 4;   // independent 16-byte loads in flight per thread
+    constexpr int TU = 4;  // independent 16-byte loads in flight per thread
+    float m = -INFINITY, s = 0.f, cm = -INFINITY;
+    if (t == 0) s_cnt = 0;
     for (int base = t; base < v4; base += TK_THREADS * TU) {
         float4 x4s[TU];
 #pragma unroll
         for (int u = 0; u < TU; ++u) {
             const int i4 = base + u * TK_THREADS;
-            x4s[u] = (i4 < v4) ? reinterpret_cast<const float4*>(row)[i4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            x4s[u] = (i4 < v4) ? row4[i4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
         }
 #pragma unroll
         for (int u = 0; u < TU; ++u) {
             const int i4 = base + u * TK_THREADS;
-            if (i4 >= v4) break;
-            const float xs[4] = {x4s[u].x, x4s[u].y, x4s[u].z, x4s[u].w};
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const float x = xs[e];
-                const int idx = 4 * i4 + e;
-                if (x > m) {
-                    s = s * __expf(m - x) + 1.0f;
-                    m = x;
-                } else {
-                    s += __expf(x - m);
+            if (i4 < v4) {
+                const float xs[4] = {x4s[u].x, x4s[u].y, x4s[u].z, x4s[u].w};
+                const float bm = fmaxf(fmaxf(xs[0], xs[1]), fmaxf(xs[2], xs[3]));
+                if (bm > m) {
+                    s *= __expf(m - bm);
+                    m = bm;
                 }
-                if (idx != ban_token && cand_better(x, idx, tv[TK_MAX_NC - 1], ti[TK_MAX_NC - 1])) {
-                    tv[TK_MAX_NC - 1] = x;
-                    ti[TK_MAX_NC - 1] = idx;
 #pragma unroll
-                    for (int c = TK_MAX_NC - 1; c > 0; --c) {
-                        if (cand_better(tv[c], ti[c], tv[c - 1], ti[c - 1])) {
-                            const float fv = tv[c]; tv[c] = tv[c - 1]; tv[c - 1] = fv;
-                            const int fi = ti[c]; ti[c] = ti[c - 1]; ti[c - 1] = fi;
-                        }
-                    }
+                for (int e = 0; e < 4; ++e) {
+                    s += __expf(xs[e] - m);
+                    if (4 * i4 + e != ban_token) cm = fmaxf(cm, xs[e]);
                 }
             }
         }
     }
-    // block max, then rescaled sum
-    float bm = warp_max(m);
-    if (lane == 0) s_red[w] = bm;
+    // block max, then rescaled sum -> log-sum-exp
+    const float wm = warp_max(m);
+    if (lane == 0) s_red[w] = wm;
     __syncthreads();
     if (t == 0) {
         float x = s_red[0];
@@ -491,55 +510,100 @@ __global__ void __launch_bounds__(TK_THREADS)
     }
     __syncthreads();
     const float gm = s_m;
-    float bs = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - gm));
+    const float ws = warp_sum(m == -INFINITY ? 0.f : s * __expf(m - gm));
     __syncthreads();
-    if (lane == 0) s_red[w] = bs;
+    if (lane == 0) s_red[w] = ws;
     __syncthreads();
     if (t == 0) {
         float x = 0.f;
         for (int i = 0; i < TK_THREADS / 32; ++i) x += s_red[i];
         s_l = logf(x);
     }
+    // threshold: the nc-th largest thread maximum (-inf when fewer than nc threads saw an admissible element)
+    float mine = cm, thr = -INFINITY;
+    for (int c = 0; c < nc; ++c) {
+        float v = mine;
+        int owner = t;
+        block_argmax(v, owner, s_v, s_i);
+        thr = v;
+        if (owner == t) mine = -INFINITY;
+    }
     __syncthreads();
     const float lse = s_l;
     const float add = beam_scores ? beam_scores[list] : 0.f;
-    // nc rounds of block arg-max over the heads of the per-thread lists
-    for (int c = 0; c < nc; ++c) {
-        float v = tv[0];
-        int i = ti[0];
-        int owner = t;
+    // pass 2: collect everything at or above the threshold
+    for (int base = t; base < v4; base += TK_THREADS * TU) {
+        float4 x4s[TU];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float v2 = __shfl_xor_sync(0xffffffffu, v, o);
-            const int i2 = __shfl_xor_sync(0xffffffffu, i, o);
-            const int o2 = __shfl_xor_sync(0xffffffffu, owner, o);
-            if (cand_better(v2, i2, v, i)) {
-                v = v2; i = i2; owner = o2;
+        for (int u = 0; u < TU; ++u) {
+            const int i4 = base + u * TK_THREADS;
+            x4s[u] = (i4 < v4) ? row4[i4] : make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        }
+#pragma unroll
+        for (int u = 0; u < TU; ++u) {
+            const int i4 = base + u * TK_THREADS;
+            if (i4 < v4) {
+                const float xs[4] = {x4s[u].x, x4s[u].y, x4s[u].z, x4s[u].w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int idx = 4 * i4 + e;
+                    if (xs[e] >= thr && idx != ban_token) {
+                        const int pos = atomicAdd(&s_cnt, 1);
+                        if (pos < TK_CAP) {
+                            c_v[pos] = xs[e];
+                            c_i[pos] = idx;
+                        }
+                    }
+                }
             }
         }
-        if (lane == 0) {
-            s_v[w] = v; s_i[w] = i; s_owner[w] = owner;
-        }
-        __syncthreads();
-        if (t == 0) {
-            int best = 0;
-            for (int k = 1; k < TK_THREADS / 32; ++k)
-                if (cand_better(s_v[k], s_i[k], s_v[best], s_i[best])) best = k;
-            s_win = s_owner[best];
-            cand_score[static_cast<int64_t>(list) * nc + c] = ((s_v[best] - gm) - lse) + add;  // log_softmax, then + beam score
-            cand_tok[static_cast<int64_t>(list) * nc + c] = s_i[best];
-        }
-        __syncthreads();
-        if (t == s_win) {
-#pragma unroll
-            for (int k = 0; k < TK_MAX_NC - 1; ++k) {
-                tv[k] = tv[k + 1];
-                ti[k] = ti[k + 1];
+    }
+    __syncthreads();
+    const int cnt = s_cnt;
+    if (cnt <= TK_CAP) {
+        for (int c = 0; c < nc; ++c) {
+            float v = -INFINITY;
+            int i = 0x7fffffff;
+            for (int e = t; e < cnt; e += TK_THREADS)
+                if (cand_better(c_v[e], c_i[e], v, i)) {
+                    v = c_v[e];
+                    i = c_i[e];
+                }
+            block_argmax(v, i, s_v, s_i);
+            if (t == 0) {
+                cand_score[static_cast<int64_t>(list) * nc + c] = ((v - gm) - lse) + add;  // log_softmax, then + beam score
+                cand_tok[static_cast<int64_t>(list) * nc + c] = i;
             }
-            tv[TK_MAX_NC - 1] = -INFINITY;
-            ti[TK_MAX_NC - 1] = 0x7fffffff;
+            for (int e = t; e < cnt; e += TK_THREADS)
+                if (c_i[e] == i) {
+                    c_v[e] = -INFINITY;
+                    c_i[e] = 0x7fffffff;
+                }
+            __syncthreads();
         }
-        __syncthreads();
+    } else {
+        // more than TK_CAP elements tie at or above the threshold: exact selection by nc ordered scans of the row
+        float pv = INFINITY;
+        int pi = -1;
+        for (int c = 0; c < nc; ++c) {
+            float v = -INFINITY;
+            int i = 0x7fffffff;
+            for (int idx = t; idx < V; idx += TK_THREADS) {
+                const float x = row[idx];
+                const bool after = x < pv || (x == pv && idx > pi);
+                if (after && idx != ban_token && cand_better(x, idx, v, i)) {
+                    v = x;
+                    i = idx;
+                }
+            }
+            block_argmax(v, i, s_v, s_i);
+            if (t == 0) {
+                cand_score[static_cast<int64_t>(list) * nc + c] = ((v - gm) - lse) + add;
+                cand_tok[static_cast<int64_t>(list) * nc + c] = i;
+            }
+            pv = v;
+            pi = i;
+        }
     }
 }
 

@@ -360,10 +360,10 @@ GenerateWs generate_ws(const vidil_med* m, void* base, int F, int Nv, int K, int
 }
 
 int check_beam_args(int F, int K, int V, int Lp, int max_length, int min_length, const void* prompt) {
-    if (F <= 0 || K < 1 || K > 4 || prompt == nullptr || Lp < 1 || max_length <= Lp || max_length > 64 || min_length < 0 || V < 2 * K ||
+    if (F <= 0 || K < 1 || K > 4 || prompt == nullptr || Lp < 1 || max_length <= Lp || max_length > 64 || min_length < 0 || V < 2 * K + 1 ||
         V % 4 != 0) {
         set_error("beam search: n_frames=%d num_beams=%d (1..4) prompt_len=%d max_length=%d (prompt_len < max_length <= 64) V=%d "
-                  "(multiple of 4, >= 2*num_beams)", F, K, Lp, max_length, V);
+                  "(multiple of 4, > 2*num_beams)", F, K, Lp, max_length, V);
         return 1;
     }
     return 0;

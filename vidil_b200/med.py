@@ -271,8 +271,14 @@ class BertModel(nn.Module):
             enc = enc.contiguous().float()
             F_, Nv = enc.shape[0], enc.shape[1]
             ids = _i32(input_ids, dev)
-            S, T = ids.shape
             mask = _i32(attention_mask, dev) if (attention_mask is not None and not causal) else None
+            if mask is not None and not want_hidden and not want_logits:
+                # Only token 0 is read (itm_head, blip_itm.py:56) and masked keys carry zero weight, so columns that are padding
+                # in EVERY sequence (tokenizer padding='max_length', :46) cannot influence the result: drop them.
+                keep = int((mask != 0).any(dim=0).nonzero().max().item()) + 1 if bool((mask != 0).any()) else 1
+                if keep < ids.shape[1]:
+                    ids, mask = ids[:, :keep].contiguous(), mask[:, :keep].contiguous()
+            S, T = ids.shape
             fos = _i32(frame_of_seq, dev) if frame_of_seq is not None else None
             hidden = torch.empty(S, T, c.hidden_size, dtype=torch.float32, device=dev) if want_hidden else None
             logits = torch.empty(S, T, c.vocab_size, dtype=torch.float32, device=dev) if want_logits else None
