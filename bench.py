@@ -607,12 +607,27 @@ def run_capfilt(args):
     launches = lib.launch_count() - before
     ms = [a / args.steps for a in acc]
     total = sum(ms)
+    cpu = None
+    if not args.no_cpu_baseline:
+        # the reference's text side on the host cores: oracle port of med.py + the restated beam search, 2 frames of image tokens
+        from oracle import med_oracle, weights as W
+        name = "base_l" if args.vit == "large" else "base_b"
+        torch.set_num_threads(os.cpu_count() or 1)
+        sd = W.med_state_dict(name, "decoder", seed=0)
+        n_tok = (args.image_size // 16) ** 2 + 1
+        enc = W.image_tokens(2, n_tok, W.MED_CONFIGS[name]["encoder_width"], seed=0)
+        t0 = time.perf_counter()
+        med_oracle.generate(sd, enc, W.MED_SPECIAL[name]["prompt"], 12, 12, num_beams=3, max_length=20, min_length=5)
+        dt = time.perf_counter() - t0
+        cpu = {"value": 2 / dt, "unit": "captions/s (beam search only, image tokens given)", "cores": os.cpu_count(), "kind": "port",
+               "sample": "oracle/med_oracle.generate on 2 frames of image tokens (cached decoder, beams 3, max_length 20)"}
     tokens = (args.image_size // 16) ** 2 + 1
     D, depth, _ = VIT[args.vit]
     print(json.dumps({"metric": "frames/sec through CapFilt (caption + filter)", "value": n_frames / (total / 1e3), "unit": "frames/s",
                       "ms_per_step": total, "steps": args.steps, "warmup": args.warmup, "gpu_launches": launches,
                       "stages_ms": {"captioner_vit": ms[0], "caption_beam_search": ms[1], "filterer_vit": ms[2], "itm_pairs": ms[3]},
                       "caption_frames_per_s": n_frames / ((ms[0] + ms[1]) / 1e3),
+                      "captions_per_s_beam_search_only": n_frames / (ms[1] / 1e3), "cpu_baseline": cpu,
                       "decode_rows": n_frames * 3, "itm_pairs": n_frames * Fv, "dtype": args.dtype, "data": "synthetic",
                       "config": {"workload": f"{V} synthetic videos x 8 frames @{args.image_size}, BLIP ViT-{args.vit[0].upper()}/16 + "
                                  f"med.py decoder (beam 3, max_length 20, min_length 5) + BLIP_ITM filter over {n_frames * Fv} "
