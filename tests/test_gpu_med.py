@@ -311,3 +311,38 @@ def test_generate_and_itm_on_vit_b_384_tokens(cuda):
     with torch.no_grad():
         ref = med_oracle.itm_logits(sdi, enc, cap, mask, H, depth)
     assert (cls.cpu() - ref).abs().max() < 8e-2
+
+
+@pytest.mark.parametrize("F,n_img,K,max_length,min_length", [(1, 3, 1, 6, 0), (2, 50, 2, 5, 5), (5, 300, 4, 9, 3), (3, 257, 3, 30, 10)])
+def test_generate_edge_shapes(cuda, F, n_img, K, max_length, min_length):
+    """One frame / greedy (1 beam) / a single step after the prompt (max_length = prompt + 1) / 4 beams / odd token counts (two
+    TMA boxes at 257 and 300) / the defaults of BLIP_Decoder.generate (max_length 30, min_length 10)."""
+    name = "tiny"
+    m, sd = _decoder(name, "fp16", cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(F, n_img, c["encoder_width"], seed=F + n_img)
+    prompt = torch.tensor([sp["prompt"]], dtype=torch.long).repeat(F, 1)
+    out, scores, lens = m.generate(input_ids=prompt, max_length=max_length, min_length=min_length, num_beams=K, eos_token_id=sp["eos"],
+                                   pad_token_id=sp["pad"], encoder_hidden_states=enc.to(cuda), return_scores=True)
+    ref_toks, ref_scores, _ = med_oracle.generate(sd, enc, sp["prompt"], c["num_attention_heads"], c["num_hidden_layers"], num_beams=K,
+                                                  max_length=max_length, min_length=min_length, eos=sp["eos"], pad=sp["pad"])
+    got = [out[b, :int(lens[b])].tolist() for b in range(F)]
+    assert all(g == r or s > rs - 0.02 for g, r, s, rs in zip(got, ref_toks, scores.cpu().numpy(), ref_scores))
+    assert sum(g == r for g, r in zip(got, ref_toks)) >= F - 1
+    assert all(len(g) <= max_length and g[:4] == sp["prompt"] for g in got)
+    assert out.shape == (F, max(len(g) for g in got))
+
+
+def test_decoder_forward_long_sequence_and_ragged_frames(cuda):
+    """Teacher-forced logits for 40-token sequences (the training max_length of blip.py:110) and a sequence->frame map."""
+    name = "tiny"
+    m, sd = _decoder(name, "fp16", cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(2, 9, c["encoder_width"], seed=21)
+    ids, _ = W.caption_ids(name, 5, 40, seed=8, min_words=38)
+    ids[:, 0] = sp["bos"]
+    frame_of = torch.tensor([1, 0, 0, 1, 1])
+    _, logits, _ = m.bert.run(ids, None, enc.to(cuda), frame_of_seq=frame_of, causal=True, want_hidden=False, want_logits=True)
+    with torch.no_grad():
+        ref, _ = med_oracle.decoder_logits(sd, "text_decoder.", ids, enc[frame_of], c["num_attention_heads"], c["num_hidden_layers"])
+    assert (logits.cpu() - ref).abs().max() < LOGIT_TOL["fp16"]
