@@ -452,6 +452,165 @@ __global__ void __launch_bounds__(ATT_THREADS)
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Decode-step cross-attention of the caption decoder on the same mma.sync pipeline, fed by TMA: one warp per (head, frame).
+// The frame's K and V tiles ([Nv, 64] each, Nv <= 256) land in 128B-swizzled shared memory through ONE bulk tensor load each,
+// issued before anything else; the NQ <= 4 beam queries are rows 0..NQ-1 of the 16-row A fragment (rows 8..15 are zero and
+// their accumulators are never read).  HBM-bound on the K/V stream: 3 CTAs per SM keep ~150 KB in flight and the ~200 MMAs per
+// CTA hide under the loads.
+// ---------------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(32)
+    cross_decode_mma_kernel(const __grid_constant__ CUtensorMap kv_map, const T* __restrict__ q, T* __restrict__ out, int row0, int Nv,
+                            int nq, int H, float scale_log2e) {
+    extern __shared__ uint8_t xsmem_raw[];
+    // the 128B swizzle pattern is a function of the address bits: tiles must start on a 1024-byte boundary
+    uint8_t* xsmem = xsmem_raw + ((1024u - (ptx::smem_u32(xsmem_raw) & 1023u)) & 1023u);
+    const int h = blockIdx.x, f = blockIdx.y;
+    const int D = H * HD;
+    const int lane = threadIdx.x;
+    const int rows_pad = (Nv + BKV - 1) / BKV * BKV;
+    uint8_t* sKp = xsmem;
+    uint8_t* sVp = xsmem + static_cast<size_t>(rows_pad) * 128;
+    uint64_t* bars = reinterpret_cast<uint64_t*>(sVp + static_cast<size_t>(rows_pad) * 128);
+    const uint32_t sK = ptx::smem_u32(sKp), sV = ptx::smem_u32(sVp);
+    if (lane == 0) {
+        ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[1], 1);
+        ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        const uint32_t bytes = static_cast<uint32_t>(Nv) * 128;
+        ptx::mbar_arrive_expect_tx(&bars[0], bytes);
+        ptx::tma_load_2d(&kv_map, &bars[0], sKp, h * HD, row0 + f * Nv);
+        ptx::mbar_arrive_expect_tx(&bars[1], bytes);
+        ptx::tma_load_2d(&kv_map, &bars[1], sVp, D + h * HD, row0 + f * Nv);
+    }
+    // rows Nv..rows_pad-1 are not written by the TMA boxes: zero them so that P = 0 times V stays 0
+    for (int i = Nv * 8 + lane; i < rows_pad * 8; i += 32) {
+        *reinterpret_cast<uint4*>(sKp + static_cast<size_t>(i) * 16) = make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sVp + static_cast<size_t>(i) * 16) = make_uint4(0, 0, 0, 0);
+    }
+    // Q fragments straight from global memory: row g = lane / 4 of the m16 tile, dims kk*16 + tq*2 (+8)
+    const int g = lane >> 2, tq = lane & 3;
+    uint32_t qf[4][4];
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        qf[kk][0] = qf[kk][1] = qf[kk][2] = qf[kk][3] = 0u;
+        if (g < nq) {
+            const T* qp = q + (static_cast<int64_t>(f) * nq + g) * D + h * HD + kk * 16 + tq * 2;
+            qf[kk][0] = *reinterpret_cast<const uint32_t*>(qp);
+            qf[kk][2] = *reinterpret_cast<const uint32_t*>(qp + 8);
+        }
+    }
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    __syncwarp();
+    ptx::mbar_wait(&bars[0], 0);
+    const int num_kb = rows_pad / BKV;
+    for (int kb = 0; kb < num_kb; ++kb) {
+        const uint32_t sKb = sK + kb * (BKV * 128);
+        float s[8][4];
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+            for (int kk2 = 0; kk2 < 2; ++kk2) {
+                uint32_t b0, b1, b2, b3;
+                ldsm_x4(sKb + tile_off(nt * 8 + (lane & 7), kk2 * 4 + (lane >> 3)), b0, b1, b2, b3);
+                mma16816<T>(s[nt], qf[2 * kk2], b0, b1);
+                mma16816<T>(s[nt], qf[2 * kk2 + 1], b2, b3);
+            }
+        }
+        const int key0 = kb * BKV + tq * 2;
+        float mx = m_run;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            const int key = key0 + nt * 8;
+            s[nt][0] = (key < Nv) ? s[nt][0] * scale_log2e : -INFINITY;
+            s[nt][1] = (key + 1 < Nv) ? s[nt][1] * scale_log2e : -INFINITY;
+            mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
+        }
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        const float corr = exp2f(m_run - mx);
+        m_run = mx;
+        float rs = 0.f;
+#pragma unroll
+        for (int nt = 0; nt < 8; ++nt) {
+            s[nt][0] = exp2f(s[nt][0] - mx);
+            s[nt][1] = exp2f(s[nt][1] - mx);
+            rs += s[nt][0] + s[nt][1];
+        }
+        l_run = l_run * corr + rs;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) {
+            o[nd][0] *= corr;
+            o[nd][1] *= corr;
+        }
+        if (kb == 0) ptx::mbar_wait(&bars[1], 0);
+        const uint32_t sVb = sV + kb * (BKV * 128);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            uint32_t pa[4];
+            pa[0] = pack2<T>(s[2 * j][0], s[2 * j][1]);
+            pa[1] = 0u;
+            pa[2] = pack2<T>(s[2 * j + 1][0], s[2 * j + 1][1]);
+            pa[3] = 0u;
+#pragma unroll
+            for (int nd2 = 0; nd2 < 4; ++nd2) {
+                uint32_t b0, b1, b2, b3;
+                const int r = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+                const int c = nd2 * 2 + (lane >> 4);
+                ldsm_x4_trans(sVb + tile_off(r, c), b0, b1, b2, b3);
+                mma16816<T>(o[2 * nd2], pa, b0, b1);
+                mma16816<T>(o[2 * nd2 + 1], pa, b2, b3);
+            }
+        }
+    }
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    if (g < nq) {
+        const float inv = 1.0f / l_run;
+        T* op = out + (static_cast<int64_t>(f) * nq + g) * D + h * HD + tq * 2;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) *reinterpret_cast<uint32_t*>(op + nd * 8) = pack2<T>(o[nd][0] * inv, o[nd][1] * inv);
+    }
+}
+
+}  // namespace
+
+int cross_decode_mma_run(const CUtensorMap& kv_map_sw128, int row0, const void* q, void* out, DType dt, int F, int nq, int Nv, int H,
+                         float scale, cudaStream_t stream) {
+    if (F <= 0) return 0;
+    if (nq < 1 || nq > 8 || Nv < 1 || Nv > 256 || F > 65535) {
+        set_error("decode cross-attention (mma): %d query rows (1..8), %d image tokens (1..256), %d frames", nq, Nv, F);
+        return 1;
+    }
+    const int rows_pad = (Nv + BKV - 1) / BKV * BKV;
+    const size_t smem = 2 * static_cast<size_t>(rows_pad) * 128 + 16 + 1024;
+    const float sl2 = scale * 1.4426950408889634f;
+    if (dt == DT_BF16) {
+        auto k = cross_decode_mma_kernel<__nv_bfloat16>;
+        VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k<<<dim3(H, F), 32, smem, stream>>>(kv_map_sw128, reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<__nv_bfloat16*>(out),
+                                           row0, Nv, nq, H, sl2);
+    } else {
+        auto k = cross_decode_mma_kernel<__half>;
+        VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+        k<<<dim3(H, F), 32, smem, stream>>>(kv_map_sw128, reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out), row0, Nv, nq,
+                                           H, sl2);
+    }
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+namespace {
 }  // namespace
 
 int attention_x_run(const void* q, int64_t q_stride, const void* k, const void* v, int64_t kv_stride, const int32_t* frame_of_group,

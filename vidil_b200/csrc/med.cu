@@ -865,6 +865,7 @@ int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, i
             fn = reinterpret_cast<EncodeTiledFn>(p);
     }
     m.valid = false;
+    m.valid_sw = false;
     m.F = F; m.Nv = Nv; m.H = H;
     m.n_box = (Nv + 255) / 256;
     m.box_rows = (Nv + m.n_box - 1) / m.n_box;
@@ -882,6 +883,16 @@ int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, i
         return 1;
     }
     m.valid = true;
+    if (Nv <= 256) {
+        const cuuint32_t box_sw[2] = {64, static_cast<cuuint32_t>(Nv)};
+        r = fn(&m.map_sw, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ckv), dims, strides, box_sw, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            set_error("cuTensorMapEncodeTiled (cross K/V, swizzled) failed with CUresult %d", static_cast<int>(r));
+            return 1;
+        }
+        m.valid_sw = true;
+    }
     return 0;
 }
 
@@ -893,6 +904,7 @@ int med_cross_attn_decode_run(const CrossKvMap* map, int layer, const void* q, c
         return 1;
     }
     const bool tma = map != nullptr && map->valid && map->F == F && map->Nv == Nv && map->H == H;
+    if (tma && map->valid_sw) return cross_decode_mma_run(map->map_sw, layer * F * Nv, q, out, dt, F, nq, Nv, H, scale, s);
 #define VIDIL_CD(NQ)                                                                                                      \
     case NQ:                                                                                                              \
         if (tma)                                                                                                          \
