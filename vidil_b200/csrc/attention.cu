@@ -460,6 +460,154 @@ __global__ void __launch_bounds__(ATT_THREADS)
 // their accumulators are never read).  HBM-bound on the K/V stream: 3 CTAs per SM keep ~150 KB in flight and the ~200 MMAs per
 // CTA hide under the loads.
 // ---------------------------------------------------------------------------------------------------------------------
+// One 64-key block of the decode cross-attention: S = Q K^T for the warp's (<= 8 valid) query rows, online softmax in the log2
+// domain, O += P V.  sKb / sVb: 128B-swizzled [64, 64] tiles; key_base: index of the block's first key within the frame.
+template <typename T>
+__device__ __forceinline__ void xdec_block(uint32_t sKb, uint32_t sVb, int key_base, int Nv, float scale_log2e, const uint32_t (&qf)[4][4],
+                                           float (&o)[8][4], float& m_run, float& l_run, int lane) {
+    const int tq = lane & 3;
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+#pragma unroll
+        for (int kk2 = 0; kk2 < 2; ++kk2) {
+            uint32_t b0, b1, b2, b3;
+            ldsm_x4(sKb + tile_off(nt * 8 + (lane & 7), kk2 * 4 + (lane >> 3)), b0, b1, b2, b3);
+            mma16816<T>(s[nt], qf[2 * kk2], b0, b1);
+            mma16816<T>(s[nt], qf[2 * kk2 + 1], b2, b3);
+        }
+    }
+    const int key0 = key_base + tq * 2;
+    float mx = m_run;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        const int key = key0 + nt * 8;
+        s[nt][0] = (key < Nv) ? s[nt][0] * scale_log2e : -INFINITY;
+        s[nt][1] = (key + 1 < Nv) ? s[nt][1] * scale_log2e : -INFINITY;
+        mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
+    }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    if (mx == -INFINITY) return;  // a block entirely past the frame's last key (chunk padding)
+    const float corr = exp2f(m_run - mx);
+    m_run = mx;
+    float rs = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = exp2f(s[nt][0] - mx);
+        s[nt][1] = exp2f(s[nt][1] - mx);
+        rs += s[nt][0] + s[nt][1];
+    }
+    l_run = l_run * corr + rs;
+#pragma unroll
+    for (int nd = 0; nd < 8; ++nd) {
+        o[nd][0] *= corr;
+        o[nd][1] *= corr;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        uint32_t pa[4];
+        pa[0] = pack2<T>(s[2 * j][0], s[2 * j][1]);
+        pa[1] = 0u;
+        pa[2] = pack2<T>(s[2 * j + 1][0], s[2 * j + 1][1]);
+        pa[3] = 0u;
+#pragma unroll
+        for (int nd2 = 0; nd2 < 4; ++nd2) {
+            uint32_t b0, b1, b2, b3;
+            const int r = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
+            const int c = nd2 * 2 + (lane >> 4);
+            ldsm_x4_trans(sVb + tile_off(r, c), b0, b1, b2, b3);
+            mma16816<T>(o[2 * nd2], pa, b0, b1);
+            mma16816<T>(o[2 * nd2 + 1], pa, b2, b3);
+        }
+    }
+}
+
+// Q fragments of the decode cross-attention straight from global memory: row g = lane / 4 of the m16 tile.
+template <typename T>
+__device__ __forceinline__ void xdec_load_q(const T* q, int f, int nq, int D, int h, int lane, uint32_t (&qf)[4][4]) {
+    const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+        qf[kk][0] = qf[kk][1] = qf[kk][2] = qf[kk][3] = 0u;
+        if (g < nq) {
+            const T* qp = q + (static_cast<int64_t>(f) * nq + g) * D + h * HD + kk * 16 + tq * 2;
+            qf[kk][0] = *reinterpret_cast<const uint32_t*>(qp);
+            qf[kk][2] = *reinterpret_cast<const uint32_t*>(qp + 8);
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void xdec_store(T* out, int f, int nq, int D, int h, int lane, const float (&o)[8][4], float l_run) {
+    const int g = lane >> 2, tq = lane & 3;
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+    if (g < nq) {
+        const float inv = 1.0f / l_run;
+        T* op = out + (static_cast<int64_t>(f) * nq + g) * D + h * HD + tq * 2;
+#pragma unroll
+        for (int nd = 0; nd < 8; ++nd) *reinterpret_cast<uint32_t*>(op + nd * 8) = pack2<T>(o[nd][0] * inv, o[nd][1] * inv);
+    }
+}
+
+// More than 256 image tokens per frame (ViT-B/16 @384: 577): the K/V stream goes through a two-stage ring of 128-row boxes, the
+// next chunk's two TMA loads in flight while the warp works on the current one.  Chunk padding past the frame's last key reads
+// the neighbouring frame's rows (or the tensor map's zero fill at the very end): masked in S, finite in V.
+constexpr int XCH = 128;
+
+template <typename T>
+__global__ void __launch_bounds__(32)
+    cross_decode_mma_chunked_kernel(const __grid_constant__ CUtensorMap kv_map, const T* __restrict__ q, T* __restrict__ out, int row0,
+                                    int Nv, int nq, int H, float scale_log2e) {
+    extern __shared__ uint8_t xsmem_raw[];
+    uint8_t* xsmem = xsmem_raw + ((1024u - (ptx::smem_u32(xsmem_raw) & 1023u)) & 1023u);
+    const int h = blockIdx.x, f = blockIdx.y;
+    const int D = H * HD;
+    const int lane = threadIdx.x;
+    constexpr uint32_t TILE = XCH * 128;                       // one K or V chunk
+    uint64_t* bars = reinterpret_cast<uint64_t*>(xsmem + 4 * TILE);
+    if (lane == 0) {
+        ptx::mbar_init(&bars[0], 1);
+        ptx::mbar_init(&bars[1], 1);
+        ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    const int n_chunks = (Nv + XCH - 1) / XCH;
+    auto issue = [&](int c) {
+        const int st = c & 1;
+        uint8_t* dst = xsmem + st * 2 * TILE;
+        ptx::mbar_arrive_expect_tx(&bars[st], 2 * TILE);
+        ptx::tma_load_2d(&kv_map, &bars[st], dst, h * HD, row0 + f * Nv + c * XCH);
+        ptx::tma_load_2d(&kv_map, &bars[st], dst + TILE, D + h * HD, row0 + f * Nv + c * XCH);
+    };
+    if (lane == 0) {
+        issue(0);
+        if (n_chunks > 1) issue(1);
+    }
+    uint32_t qf[4][4];
+    xdec_load_q<T>(q, f, nq, D, h, lane, qf);
+    float o[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+    float m_run = -INFINITY, l_run = 0.f;
+    for (int c = 0; c < n_chunks; ++c) {
+        const int st = c & 1;
+        ptx::mbar_wait(&bars[st], (c >> 1) & 1);
+        const uint32_t sK = ptx::smem_u32(xsmem + st * 2 * TILE), sV = sK + TILE;
+#pragma unroll
+        for (int kb = 0; kb < XCH / BKV; ++kb)
+            xdec_block<T>(sK + kb * (BKV * 128), sV + kb * (BKV * 128), c * XCH + kb * BKV, Nv, scale_log2e, qf, o, m_run, l_run, lane);
+        __syncwarp();
+        if (c + 2 < n_chunks) {
+            ptx::fence_proxy_async_smem();  // this warp's ldmatrix reads of the stage precede the async-proxy refill
+            if (lane == 0) issue(c + 2);
+        }
+    }
+    xdec_store<T>(out, f, nq, D, h, lane, o, l_run);
+}
+
 template <typename T>
 __global__ void __launch_bounds__(32)
     cross_decode_mma_kernel(const __grid_constant__ CUtensorMap kv_map, const T* __restrict__ q, T* __restrict__ out, int row0, int Nv,
@@ -493,118 +641,47 @@ __global__ void __launch_bounds__(32)
         *reinterpret_cast<uint4*>(sKp + static_cast<size_t>(i) * 16) = make_uint4(0, 0, 0, 0);
         *reinterpret_cast<uint4*>(sVp + static_cast<size_t>(i) * 16) = make_uint4(0, 0, 0, 0);
     }
-    // Q fragments straight from global memory: row g = lane / 4 of the m16 tile, dims kk*16 + tq*2 (+8)
-    const int g = lane >> 2, tq = lane & 3;
     uint32_t qf[4][4];
-#pragma unroll
-    for (int kk = 0; kk < 4; ++kk) {
-        qf[kk][0] = qf[kk][1] = qf[kk][2] = qf[kk][3] = 0u;
-        if (g < nq) {
-            const T* qp = q + (static_cast<int64_t>(f) * nq + g) * D + h * HD + kk * 16 + tq * 2;
-            qf[kk][0] = *reinterpret_cast<const uint32_t*>(qp);
-            qf[kk][2] = *reinterpret_cast<const uint32_t*>(qp + 8);
-        }
-    }
+    xdec_load_q<T>(q, f, nq, D, h, lane, qf);
     float o[8][4];
 #pragma unroll
     for (int i = 0; i < 8; ++i) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
     float m_run = -INFINITY, l_run = 0.f;
     __syncwarp();
     ptx::mbar_wait(&bars[0], 0);
+    ptx::mbar_wait(&bars[1], 0);
     const int num_kb = rows_pad / BKV;
-    for (int kb = 0; kb < num_kb; ++kb) {
-        const uint32_t sKb = sK + kb * (BKV * 128);
-        float s[8][4];
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-#pragma unroll
-            for (int kk2 = 0; kk2 < 2; ++kk2) {
-                uint32_t b0, b1, b2, b3;
-                ldsm_x4(sKb + tile_off(nt * 8 + (lane & 7), kk2 * 4 + (lane >> 3)), b0, b1, b2, b3);
-                mma16816<T>(s[nt], qf[2 * kk2], b0, b1);
-                mma16816<T>(s[nt], qf[2 * kk2 + 1], b2, b3);
-            }
-        }
-        const int key0 = kb * BKV + tq * 2;
-        float mx = m_run;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            const int key = key0 + nt * 8;
-            s[nt][0] = (key < Nv) ? s[nt][0] * scale_log2e : -INFINITY;
-            s[nt][1] = (key + 1 < Nv) ? s[nt][1] * scale_log2e : -INFINITY;
-            mx = fmaxf(mx, fmaxf(s[nt][0], s[nt][1]));
-        }
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-        const float corr = exp2f(m_run - mx);
-        m_run = mx;
-        float rs = 0.f;
-#pragma unroll
-        for (int nt = 0; nt < 8; ++nt) {
-            s[nt][0] = exp2f(s[nt][0] - mx);
-            s[nt][1] = exp2f(s[nt][1] - mx);
-            rs += s[nt][0] + s[nt][1];
-        }
-        l_run = l_run * corr + rs;
-#pragma unroll
-        for (int nd = 0; nd < 8; ++nd) {
-            o[nd][0] *= corr;
-            o[nd][1] *= corr;
-        }
-        if (kb == 0) ptx::mbar_wait(&bars[1], 0);
-        const uint32_t sVb = sV + kb * (BKV * 128);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            uint32_t pa[4];
-            pa[0] = pack2<T>(s[2 * j][0], s[2 * j][1]);
-            pa[1] = 0u;
-            pa[2] = pack2<T>(s[2 * j + 1][0], s[2 * j + 1][1]);
-            pa[3] = 0u;
-#pragma unroll
-            for (int nd2 = 0; nd2 < 4; ++nd2) {
-                uint32_t b0, b1, b2, b3;
-                const int r = j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8;
-                const int c = nd2 * 2 + (lane >> 4);
-                ldsm_x4_trans(sVb + tile_off(r, c), b0, b1, b2, b3);
-                mma16816<T>(o[2 * nd2], pa, b0, b1);
-                mma16816<T>(o[2 * nd2 + 1], pa, b2, b3);
-            }
-        }
-    }
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
-    l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-    if (g < nq) {
-        const float inv = 1.0f / l_run;
-        T* op = out + (static_cast<int64_t>(f) * nq + g) * D + h * HD + tq * 2;
-#pragma unroll
-        for (int nd = 0; nd < 8; ++nd) *reinterpret_cast<uint32_t*>(op + nd * 8) = pack2<T>(o[nd][0] * inv, o[nd][1] * inv);
-    }
+    for (int kb = 0; kb < num_kb; ++kb)
+        xdec_block<T>(sK + kb * (BKV * 128), sV + kb * (BKV * 128), kb * BKV, Nv, scale_log2e, qf, o, m_run, l_run, lane);
+    xdec_store<T>(out, f, nq, D, h, lane, o, l_run);
 }
 
 }  // namespace
 
+int cross_decode_mma_chunk_rows() { return XCH; }
+
 int cross_decode_mma_run(const CUtensorMap& kv_map_sw128, int row0, const void* q, void* out, DType dt, int F, int nq, int Nv, int H,
                          float scale, cudaStream_t stream) {
     if (F <= 0) return 0;
-    if (nq < 1 || nq > 8 || Nv < 1 || Nv > 256 || F > 65535) {
-        set_error("decode cross-attention (mma): %d query rows (1..8), %d image tokens (1..256), %d frames", nq, Nv, F);
+    if (nq < 1 || nq > 8 || Nv < 1 || F > 65535) {
+        set_error("decode cross-attention (mma): %d query rows (1..8), %d image tokens, %d frames (<= 65535)", nq, Nv, F);
         return 1;
     }
+    const bool chunked = Nv > 256;  // the map's box is [Nv, 64] up to 256 tokens, [XCH, 64] beyond
     const int rows_pad = (Nv + BKV - 1) / BKV * BKV;
-    const size_t smem = 2 * static_cast<size_t>(rows_pad) * 128 + 16 + 1024;
+    const size_t smem = (chunked ? 4 * static_cast<size_t>(XCH) * 128 : 2 * static_cast<size_t>(rows_pad) * 128) + 16 + 1024;
     const float sl2 = scale * 1.4426950408889634f;
-    if (dt == DT_BF16) {
-        auto k = cross_decode_mma_kernel<__nv_bfloat16>;
-        VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        k<<<dim3(H, F), 32, smem, stream>>>(kv_map_sw128, reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<__nv_bfloat16*>(out),
-                                           row0, Nv, nq, H, sl2);
-    } else {
-        auto k = cross_decode_mma_kernel<__half>;
-        VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-        k<<<dim3(H, F), 32, smem, stream>>>(kv_map_sw128, reinterpret_cast<const __half*>(q), reinterpret_cast<__half*>(out), row0, Nv, nq,
-                                           H, sl2);
-    }
+#define VIDIL_XDEC(T)                                                                                                          \
+    do {                                                                                                                       \
+        auto k = chunked ? cross_decode_mma_chunked_kernel<T> : cross_decode_mma_kernel<T>;                                    \
+        VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));           \
+        k<<<dim3(H, F), 32, smem, stream>>>(kv_map_sw128, reinterpret_cast<const T*>(q), reinterpret_cast<T*>(out), row0, Nv, nq, H, sl2); \
+    } while (0)
+    if (dt == DT_BF16)
+        VIDIL_XDEC(__nv_bfloat16);
+    else
+        VIDIL_XDEC(__half);
+#undef VIDIL_XDEC
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;

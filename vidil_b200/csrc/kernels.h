@@ -184,11 +184,11 @@ int med_self_attn_decode_run(const void* qkv, void* cache, const int32_t* anc, v
 // decode step: the nq beams of frame f (rows f*nq.. of q [F*nq, D]) attend to kv [F, Nv, 2D] -> out [F*nq, D].  With a prepared
 // CrossKvMap (one tensor map over the cross K/V of all layers, [depth*F*Nv, 2D]) the K/V tiles come in by TMA.
 struct CrossKvMap {
-    CUtensorMap map;       // no swizzle, [box_rows, 64] boxes: the SIMT kernel
-    CUtensorMap map_sw;    // 128B swizzle, one [Nv, 64] box: the mma.sync kernel (Nv <= 256)
-    bool valid = false, valid_sw = false;
-    int F = 0, Nv = 0, H = 0, box_rows = 0, n_box = 0;
+    CUtensorMap map;  // 128B swizzle, 64 columns wide: one [Nv, 64] box up to 256 tokens per frame, [128, 64] boxes beyond
+    bool valid = false;
+    int F = 0, Nv = 0, H = 0;
 };
+int cross_decode_mma_chunk_rows();
 int cross_decode_mma_run(const CUtensorMap& kv_map_sw128, int row0, const void* q, void* out, DType dt, int F, int nq, int Nv, int H,
                          float scale, cudaStream_t stream);
 int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, int Nv, int H);

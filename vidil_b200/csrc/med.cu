@@ -170,10 +170,11 @@ __global__ void __launch_bounds__(SA_WARPS * 32)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Decode-step cross-attention: the NQ beams of frame f (rows f*NQ .. f*NQ+NQ-1 of q [rows, D]) attend to the frame's Nv image
-// tokens, kv [F, Nv, 2D].  One CTA per (head, frame) streams the frame's K rows, then its V rows, exactly once with 16-byte
-// loads (8 lanes per 128-byte row, 4 rows in flight per thread): HBM-bound on reading kv — 2*Nv*128 bytes per CTA — which
-// no amount of query-side work can hide, so the tensor cores are left out here.
+// Decode-step cross-attention, register-load version: the NQ beams of frame f (rows f*NQ .. f*NQ+NQ-1 of q [rows, D]) attend to the
+// frame's Nv image tokens, kv [F, Nv, 2D].  One CTA per (head, frame) streams the frame's K rows, then its V rows, exactly once
+// with 16-byte loads (8 lanes per 128-byte row, 4 rows in flight per thread).  This is the path taken when no tensor map can be
+// encoded for the K/V buffer; the TMA-fed mma.sync kernels of attention.cu (cross_decode_mma_*) are the normal route: they keep
+// 50 KB instead of 8 KB per CTA in flight (194 -> 112 us per layer-step at 1024 frames x 197 tokens).
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int CD_THREADS = 128;
 
@@ -262,117 +263,6 @@ __global__ void __launch_bounds__(CD_THREADS)
         }
     }
     // lanes c + 8*{0..3} of a warp hold partial sums of the same dims
-#pragma unroll
-    for (int i = 0; i < NQ; ++i)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float x = acc[i][e];
-            x += __shfl_xor_sync(0xffffffffu, x, 8);
-            x += __shfl_xor_sync(0xffffffffu, x, 16);
-            acc[i][e] = x;
-        }
-    if (lane < 8) {
-#pragma unroll
-        for (int i = 0; i < NQ; ++i)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) red[(w * NQ + i) * 64 + c * 8 + e] = acc[i][e];
-    }
-    __syncthreads();
-    for (int i = t; i < NQ * 64; i += CD_THREADS) {
-        const int qi = i >> 6, d = i & 63;
-        const float x = red[(0 * NQ + qi) * 64 + d] + red[(1 * NQ + qi) * 64 + d] + red[(2 * NQ + qi) * 64 + d] + red[(3 * NQ + qi) * 64 + d];
-        out[(static_cast<int64_t>(f) * NQ + qi) * D + h * 64 + d] = from_f<T>(x);
-    }
-}
-
-// The same computation with the frame's K and V tiles brought into shared memory by TMA (two bulk tensor loads per box of
-// <= 256 rows, issued up front, one mbarrier for K and one for V): ~50 KB in flight per CTA instead of 8 KB of register loads,
-// which is what it takes to keep HBM busy (Little: 7.7 TB/s x ~0.8 us = 42 KB per SM).  kv_map views the cross K/V of ALL layers
-// as one [depth*F*Nv, 2D] matrix with a [box_rows, 64] box; row0 = layer * F * Nv.
-template <typename T, int NQ>
-__global__ void __launch_bounds__(CD_THREADS)
-    med_cross_attn_decode_tma_kernel(const __grid_constant__ CUtensorMap kv_map, const T* __restrict__ q, T* __restrict__ out,
-                                     int row0, int Nv, int box_rows, int n_box, int H, float scale) {
-    extern __shared__ __align__(128) uint8_t smem_raw[];
-    const int h = blockIdx.x, f = blockIdx.y;
-    const int D = H * 64;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int c = t & 7, kl = t >> 3;
-    const uint32_t tile_bytes = static_cast<uint32_t>(n_box) * box_rows * 128;
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw);                                  // 2 mbarriers in the first 128 bytes
-    uint8_t* sK = smem_raw + 128;
-    uint8_t* sV = sK + tile_bytes;
-    float* s_s = reinterpret_cast<float*>(sV + tile_bytes);                                  // [NQ][Nv]
-    float* red = s_s + static_cast<size_t>(NQ) * Nv;                                         // [4 warps][NQ][64]
-    if (t == 0) {
-        ptx::mbar_init(&bars[0], 1);
-        ptx::mbar_init(&bars[1], 1);
-        ptx::fence_mbar_init();
-    }
-    __syncthreads();
-    if (t == 0) {
-        const int r = row0 + f * Nv;
-        ptx::mbar_arrive_expect_tx(&bars[0], tile_bytes);
-        for (int b = 0; b < n_box; ++b) ptx::tma_load_2d(&kv_map, &bars[0], sK + static_cast<size_t>(b) * box_rows * 128, h * 64, r + b * box_rows);
-        ptx::mbar_arrive_expect_tx(&bars[1], tile_bytes);
-        for (int b = 0; b < n_box; ++b)
-            ptx::tma_load_2d(&kv_map, &bars[1], sV + static_cast<size_t>(b) * box_rows * 128, D + h * 64, r + b * box_rows);
-    }
-    float qv[NQ][8];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-        load8<T>(q + (static_cast<int64_t>(f) * NQ + i) * D + h * 64 + c * 8, qv[i]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) qv[i][e] *= scale;
-    }
-    ptx::mbar_wait(&bars[0], 0);
-    for (int jb = 0; jb < Nv; jb += 16) {      // warp-uniform trip count
-        const int j = jb + kl;
-        float k8[8];
-        load8<T>(reinterpret_cast<const T*>(sK + static_cast<size_t>(j < Nv ? j : Nv - 1) * 128) + c * 8, k8);
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            float d = 0.f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) d += qv[i][e] * k8[e];
-            d += __shfl_xor_sync(0xffffffffu, d, 1);
-            d += __shfl_xor_sync(0xffffffffu, d, 2);
-            d += __shfl_xor_sync(0xffffffffu, d, 4);
-            if (c == 0 && j < Nv) s_s[i * Nv + j] = d;
-        }
-    }
-    __syncthreads();
-    if (w < NQ) {
-        float* row = s_s + w * Nv;
-        float mx = -INFINITY;
-        for (int j = lane; j < Nv; j += 32) mx = fmaxf(mx, row[j]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < Nv; j += 32) {
-            const float e = __expf(row[j] - mx);
-            row[j] = e;
-            sum += e;
-        }
-        const float inv = 1.0f / warp_sum(sum);
-        for (int j = lane; j < Nv; j += 32) row[j] *= inv;
-    }
-    __syncthreads();
-    ptx::mbar_wait(&bars[1], 0);
-    float acc[NQ][8];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-    for (int j = kl; j < Nv; j += 16) {
-        float v8[8];
-        load8<T>(reinterpret_cast<const T*>(sV + static_cast<size_t>(j) * 128) + c * 8, v8);
-#pragma unroll
-        for (int i = 0; i < NQ; ++i) {
-            const float p = s_s[i * Nv + j];
-#pragma unroll
-            for (int e = 0; e < 8; ++e) acc[i][e] += p * v8[e];
-        }
-    }
 #pragma unroll
     for (int i = 0; i < NQ; ++i)
 #pragma unroll
@@ -840,19 +730,6 @@ int launch_cross_decode(const void* q, const void* kv, void* out, int F, int Nv,
     return 0;
 }
 
-template <typename T, int NQ>
-int launch_cross_decode_tma(const CrossKvMap& m, int layer, const void* q, void* out, float scale, cudaStream_t s) {
-    const size_t tile = static_cast<size_t>(m.n_box) * m.box_rows * 128;
-    const size_t smem = 128 + 2 * tile + (static_cast<size_t>(NQ) * m.Nv + 4 * NQ * 64) * sizeof(float);
-    auto k = med_cross_attn_decode_tma_kernel<T, NQ>;
-    VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k<<<dim3(m.H, m.F), CD_THREADS, smem, s>>>(m.map, reinterpret_cast<const T*>(q), reinterpret_cast<T*>(out), layer * m.F * m.Nv, m.Nv,
-                                               m.box_rows, m.n_box, m.H, scale);
-    VIDIL_CUDA_OK(cudaGetLastError());
-    count_launches(1);
-    return 0;
-}
-
 int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, int Nv, int H) {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -865,34 +742,20 @@ int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, i
             fn = reinterpret_cast<EncodeTiledFn>(p);
     }
     m.valid = false;
-    m.valid_sw = false;
     m.F = F; m.Nv = Nv; m.H = H;
-    m.n_box = (Nv + 255) / 256;
-    m.box_rows = (Nv + m.n_box - 1) / m.n_box;
     const int64_t rows = static_cast<int64_t>(depth) * F * Nv;
-    const size_t smem = 128 + 2 * static_cast<size_t>(m.n_box) * m.box_rows * 128 + (4 * static_cast<size_t>(Nv) + 4 * 4 * 64) * sizeof(float);
-    if (fn == nullptr || smem > 200 * 1024 || rows > 0x7fffffffLL) return 0;   // the register-load kernel serves these cases
+    if (fn == nullptr || rows > 0x7fffffffLL) return 0;   // the register-load kernel serves these cases
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(2 * H * 64), static_cast<cuuint64_t>(rows)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(2 * H * 64) * 2};
-    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(m.box_rows)};
+    const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(Nv <= 256 ? Nv : cross_decode_mma_chunk_rows())};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(&m.map, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ckv), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                    CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled (cross K/V) failed with CUresult %d", static_cast<int>(r));
         return 1;
     }
     m.valid = true;
-    if (Nv <= 256) {
-        const cuuint32_t box_sw[2] = {64, static_cast<cuuint32_t>(Nv)};
-        r = fn(&m.map_sw, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void*>(ckv), dims, strides, box_sw, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            set_error("cuTensorMapEncodeTiled (cross K/V, swizzled) failed with CUresult %d", static_cast<int>(r));
-            return 1;
-        }
-        m.valid_sw = true;
-    }
     return 0;
 }
 
@@ -903,14 +766,11 @@ int med_cross_attn_decode_run(const CrossKvMap* map, int layer, const void* q, c
         set_error("med decode cross-attention: %d beams (1..4), %d image tokens (<= 8192), %d frames (<= 65535)", nq, Nv, F);
         return 1;
     }
-    const bool tma = map != nullptr && map->valid && map->F == F && map->Nv == Nv && map->H == H;
-    if (tma && map->valid_sw) return cross_decode_mma_run(map->map_sw, layer * F * Nv, q, out, dt, F, nq, Nv, H, scale, s);
-#define VIDIL_CD(NQ)                                                                                                      \
-    case NQ:                                                                                                              \
-        if (tma)                                                                                                          \
-            return dt == DT_BF16 ? launch_cross_decode_tma<__nv_bfloat16, NQ>(*map, layer, q, out, scale, s)              \
-                                 : launch_cross_decode_tma<__half, NQ>(*map, layer, q, out, scale, s);                    \
-        return dt == DT_BF16 ? launch_cross_decode<__nv_bfloat16, NQ>(q, kv, out, F, Nv, H, scale, s)                     \
+    if (map != nullptr && map->valid && map->F == F && map->Nv == Nv && map->H == H)
+        return cross_decode_mma_run(map->map, layer * F * Nv, q, out, dt, F, nq, Nv, H, scale, s);
+#define VIDIL_CD(NQ)                                                                                     \
+    case NQ:                                                                                             \
+        return dt == DT_BF16 ? launch_cross_decode<__nv_bfloat16, NQ>(q, kv, out, F, Nv, H, scale, s)    \
                              : launch_cross_decode<__half, NQ>(q, kv, out, F, Nv, H, scale, s);
     switch (nq) {
         VIDIL_CD(1)
