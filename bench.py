@@ -576,19 +576,17 @@ def run_capfilt(args):
         itoks = torch.cat([itm.visual_encoder(frames[i:i + chunk]) for i in range(0, n_frames, chunk)])
         if timed:
             ev[3].record()
-        pair_ids = cap_ids.repeat_interleave(Fv, 0)                                       # caption c of video v x its 8 frames
-        pair_mask = mask.repeat_interleave(Fv, 0)
-        vid = torch.arange(n_frames, device=dev) // Fv
-        frame_of = (vid.repeat_interleave(Fv) * Fv + torch.arange(Fv, device=dev).repeat(n_frames)).int()
+        # frame-major pairs: frame (v, j) against the Fv captions of video v -> one cross-attention query group per frame
+        pair_ids = cap_ids.view(V, 1, Fv, T_itm).expand(V, Fv, Fv, T_itm).reshape(-1, T_itm)
+        pair_mask = mask.view(V, 1, Fv, T_itm).expand(V, Fv, Fv, T_itm).reshape(-1, T_itm)
         logits = []
-        pc = args.pair_chunk
-        for i in range(0, pair_ids.shape[0], pc):                # whole videos per call: only their frames' K/V are projected
+        pc = max(Fv * Fv, args.pair_chunk - args.pair_chunk % (Fv * Fv))             # whole videos per call
+        for i in range(0, pair_ids.shape[0], pc):
             j = min(i + pc, pair_ids.shape[0])
-            f0, f1 = (i // Fv // Fv) * Fv, ((j - 1) // Fv // Fv + 1) * Fv
-            _, _, cls = itm.text_encoder.run(pair_ids[i:j], pair_mask[i:j], itoks[f0:f1], frame_of_seq=frame_of[i:j] - f0,
-                                             want_hidden=False, want_cls=True)
+            _, _, cls = itm.text_encoder.run(pair_ids[i:j], pair_mask[i:j], itoks[i // Fv:j // Fv], want_hidden=False, want_cls=True,
+                                             seqs_per_frame=Fv)
             logits.append(cls)
-        prob = torch.softmax(torch.cat(logits), dim=1)[:, 1].view(n_frames, Fv).max(dim=1).values   # max_filter, :117-118
+        prob = torch.softmax(torch.cat(logits), dim=1)[:, 1].view(V, Fv, Fv).max(dim=1).values.reshape(-1)   # max over frames, :118
         keep = (prob > 0.5).cpu()
         if timed:
             ev[4].record()

@@ -185,6 +185,9 @@ int32_t vidil_med_check_loaded(const vidil_med* med);
 
 /* Whole-sequence forward.  image_embeds fp32 [n_frames, n_img_tokens, E]; input_ids int32 [n_seq, seq_len];
  * frame_of_seq int32 [n_seq] (NULL: sequence i reads frame i, n_seq == n_frames); all device pointers.
+ * seqs_per_frame > 0 (frame_of_seq must be NULL, n_seq == n_frames * seqs_per_frame): sequences are ordered frame-major, sequence i
+ * reads frame i / seqs_per_frame, and the cross-attention handles all sequences of a frame in one query group (the captions of a
+ * video against one of its frames, run_video_CapFilt.py:107-126).
  *   causal = 1: decoder (BertLMHeadModel.forward is_decoder=True, all-ones attention mask, med.py:871-893)
  *   causal = 0: encoder with the padding mask attention_mask int32 [n_seq, seq_len] (blip_itm.py:49-54)
  * Outputs, each optional (NULL): out_hidden fp32 [n_seq, seq_len, D] (last_hidden_state), out_logits fp32
@@ -192,9 +195,9 @@ int32_t vidil_med_check_loaded(const vidil_med* med);
 size_t  vidil_med_forward_workspace_bytes(const vidil_med* med, int32_t n_seq, int32_t seq_len, int32_t n_frames,
                                           int32_t n_img_tokens);
 int32_t vidil_med_forward(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens,
-                          const int32_t* input_ids, const int32_t* attention_mask, const int32_t* frame_of_seq, int32_t n_seq,
-                          int32_t seq_len, int32_t causal, float* out_hidden, float* out_logits, float* out_cls, void* workspace,
-                          size_t workspace_bytes, void* stream);
+                          const int32_t* input_ids, const int32_t* attention_mask, const int32_t* frame_of_seq,
+                          int32_t seqs_per_frame, int32_t n_seq, int32_t seq_len, int32_t causal, float* out_hidden, float* out_logits,
+                          float* out_cls, void* workspace, size_t workspace_bytes, void* stream);
 
 /* Beam-search captioning, BLIP_Decoder.generate(sample=False) after the ViT (blip.py:130-167): the prompt (HOST pointer,
  * prompt_len ids, id 0 already replaced by bos as blip.py:136-137 does) is decoded once per frame, then

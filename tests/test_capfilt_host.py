@@ -54,8 +54,9 @@ class FakeFilterer:
         l1 = torch.tensor([_logit(_h(c) % 30000, float(images[i].mean())) for i, c in enumerate(captions)])
         return torch.stack([torch.zeros_like(l1), l1], dim=1)
 
-    def forward_ids(self, images, ids, mask, frame_of_seq=None):            # the batched call of vidil_b200.capfilt
-        l1 = torch.tensor([_logit(int(ids[p, 1]), float(images[int(frame_of_seq[p])].mean())) for p in range(ids.shape[0])])
+    def forward_ids(self, images, ids, mask, frame_of_seq=None, seqs_per_frame=0):   # the batched call of vidil_b200.capfilt
+        frame = (lambda p: int(frame_of_seq[p])) if frame_of_seq is not None else (lambda p: p // seqs_per_frame)
+        l1 = torch.tensor([_logit(int(ids[p, 1]), float(images[frame(p)].mean())) for p in range(ids.shape[0])])
         return torch.stack([torch.zeros_like(l1), l1], dim=1)
 
 

@@ -184,6 +184,10 @@ def test_itm_pairs_share_frames(cuda):
     with torch.no_grad():
         ref = med_oracle.itm_logits(sd, enc.cpu()[frame_of], pair_ids, pair_mask, c["num_attention_heads"], c["num_hidden_layers"])
     assert (all_pairs.cpu() - ref).abs().max() < 8e-2
+    # frame-major pairs with seqs_per_frame: the captions of a frame share one cross-attention query group (what
+    # vidil_b200.capfilt.filter_captions sends); same numbers, re-ordered
+    _, _, grouped = m.run(cap.repeat(n_frames, 1), mask.repeat(n_frames, 1), enc, want_hidden=False, want_cls=True, seqs_per_frame=n_caps)
+    assert torch.equal(grouped.view(n_frames, n_caps, 2).transpose(0, 1).reshape(-1, 2), all_pairs)
 
 
 # ---- generation ----------------------------------------------------------------------------------------------------------

@@ -157,12 +157,12 @@ class BLIP_ITM(nn.Module):
         self.text_encoder.attach_cls_head(self.itm_head)
 
     @torch.no_grad()
-    def forward_ids(self, image, input_ids, attention_mask, frame_of_seq=None):
-        """ITM logits [n_seq, 2] for tokenised captions; with frame_of_seq every (caption, frame) pair of a video goes through
-        one native call instead of one call per caption."""
+    def forward_ids(self, image, input_ids, attention_mask, frame_of_seq=None, seqs_per_frame=0):
+        """ITM logits [n_seq, 2] for tokenised captions; with frame_of_seq (or frame-major pairs and seqs_per_frame) every
+        (caption, frame) pair of a video goes through one native call instead of one call per caption."""
         image_embeds = self.visual_encoder(image)                                              # blip_itm.py:43
         _, _, cls = self.text_encoder.run(input_ids, attention_mask, image_embeds, frame_of_seq=frame_of_seq, causal=False,
-                                          want_hidden=False, want_cls=True)
+                                          want_hidden=False, want_cls=True, seqs_per_frame=seqs_per_frame)
         return cls
 
     @torch.no_grad()

@@ -54,10 +54,11 @@ def filter_captions(filterer, images, texts, threshold, mode='max_filter'):
     if tok is None:
         raise RuntimeError("filter_captions needs filterer.tokenizer (bert-base-uncased is not on disk: pass tokenizer= to BLIP_ITM)")
     text = tok(list(texts), padding='max_length', truncation=True, max_length=35, return_tensors="pt")    # blip_itm.py:46-47
-    ids = text.input_ids.repeat_interleave(n_frames, 0)
-    mask = text.attention_mask.repeat_interleave(n_frames, 0)
-    frame_of = torch.arange(n_frames).repeat(len(texts))
-    itm_score = _itm_prob(filterer.forward_ids(images, ids, mask, frame_of_seq=frame_of)).reshape(len(texts), n_frames)
+    # pairs in frame-major order (frame j, caption i) -> row j * len(texts) + i: the captions of a frame form one query group
+    ids = text.input_ids.repeat(n_frames, 1)
+    mask = text.attention_mask.repeat(n_frames, 1)
+    logits = filterer.forward_ids(images, ids, mask, seqs_per_frame=len(texts))
+    itm_score = _itm_prob(logits).reshape(n_frames, len(texts)).T                          # [caption, frame]
     filtered_captions = []
     for i, t in enumerate(texts):
         if _reduce_prob(itm_score[i], mode) > threshold:

@@ -84,13 +84,13 @@ __device__ __forceinline__ uint32_t tile_off(int row, int chunk) {
     return static_cast<uint32_t>(row * 128 + ((chunk ^ (row & 7)) << 4));
 }
 
-// Copy a [64 x 64] tile (rows row0..row0+63 of a strided matrix, zero beyond `nrows`) into shared memory.
-template <typename T>
+// Copy a [ROWS x 64] tile (rows row0..row0+ROWS-1 of a strided matrix, zero beyond `nrows`) into shared memory.
+template <typename T, int THREADS = ATT_THREADS, int ROWS = BKV>
 __device__ __forceinline__ void load_tile_async(uint32_t smem_tile, const T* g, int64_t row_stride, int row0,
                                                 int nrows) {
 #pragma unroll
-    for (int i = 0; i < (BKV * 8) / ATT_THREADS; ++i) {
-        const int idx = threadIdx.x + i * ATT_THREADS;
+    for (int i = 0; i < (ROWS * 8) / THREADS; ++i) {
+        const int idx = threadIdx.x + i * THREADS;
         const int r = idx >> 3, c = idx & 7;
         const int gr = row0 + r;
         const bool ok = gr < nrows;
@@ -278,14 +278,16 @@ __global__ void __launch_bounds__(ATT_THREADS)
 // Masked keys get -10000 added to the scaled score like the reference (med.py:667); warps whose 16 query rows lie beyond
 // nq (decode: 3 beams per frame) only help with the loads.
 // ---------------------------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(ATT_THREADS)
+template <typename T, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32)
     attention_x_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ k, const T* __restrict__ v,
                        int64_t kv_stride, const int32_t* __restrict__ frame_of_group, const int32_t* __restrict__ key_mask,
                        T* __restrict__ out, int64_t out_stride, int nq, int nk, int causal, float scale_log2e) {
-    __shared__ __align__(128) uint8_t smem[BQ * HD * 2 + 2 * 2 * BKV * HD * 2];
+    // Q tile (16 rows per warp) | K/V stage 0 | K/V stage 1 (only when there is more than one key block)
+    extern __shared__ __align__(128) uint8_t smem[];
+    constexpr int XBQ = NWARPS * 16, XT = NWARPS * 32;
     const uint32_t sQ = ptx::smem_u32(smem);
-    const uint32_t sKV = sQ + BQ * HD * 2;
+    const uint32_t sKV = sQ + XBQ * HD * 2;
     constexpr float MASKV = -10000.0f * 1.4426950408889634f;
 
     const int qblk = blockIdx.x, h = blockIdx.y, g = blockIdx.z;
@@ -295,13 +297,13 @@ __global__ void __launch_bounds__(ATT_THREADS)
     const T* k_base = k + static_cast<int64_t>(f) * nk * kv_stride + h * HD;
     const T* v_base = v + static_cast<int64_t>(f) * nk * kv_stride + h * HD;
     const int32_t* mrow = key_mask ? key_mask + static_cast<int64_t>(g) * nk : nullptr;
-    const int q0 = qblk * BQ;
+    const int q0 = qblk * XBQ;
     const int num_kb = (nk + BKV - 1) / BKV;
     const bool active = q0 + warp * 16 < nq;
 
-    load_tile_async<T>(sQ, q_base, q_stride, q0, nq);
-    load_tile_async<T>(sKV, k_base, kv_stride, 0, nk);
-    load_tile_async<T>(sKV + 8192, v_base, kv_stride, 0, nk);
+    load_tile_async<T, XT, XBQ>(sQ, q_base, q_stride, q0, nq);
+    load_tile_async<T, XT>(sKV, k_base, kv_stride, 0, nk);
+    load_tile_async<T, XT>(sKV + 8192, v_base, kv_stride, 0, nk);
     cp_async_commit();
 
     uint32_t qf[4][4];
@@ -316,8 +318,8 @@ __global__ void __launch_bounds__(ATT_THREADS)
         const int stage = kb & 1;
         if (kb + 1 < num_kb) {
             const uint32_t nxt = sKV + (stage ^ 1) * 16384;
-            load_tile_async<T>(nxt, k_base, kv_stride, (kb + 1) * BKV, nk);
-            load_tile_async<T>(nxt + 8192, v_base, kv_stride, (kb + 1) * BKV, nk);
+            load_tile_async<T, XT>(nxt, k_base, kv_stride, (kb + 1) * BKV, nk);
+            load_tile_async<T, XT>(nxt + 8192, v_base, kv_stride, (kb + 1) * BKV, nk);
             cp_async_commit();
             cp_async_wait<1>();
         } else {
@@ -703,24 +705,29 @@ int attention_x_run(const void* q, int64_t q_stride, const void* k, const void* 
         set_error("attention: operands must be 16-byte aligned with row strides that are multiples of 8 elements");
         return 1;
     }
-    const dim3 grid((nq + BQ - 1) / BQ, H, groups);
     const float sl2 = scale * 1.4426950408889634f;
-    if (dt == DT_BF16)
-        attention_x_kernel<__nv_bfloat16><<<grid, ATT_THREADS, 0, stream>>>(
-            reinterpret_cast<const __nv_bfloat16*>(q), q_stride, reinterpret_cast<const __nv_bfloat16*>(k),
-            reinterpret_cast<const __nv_bfloat16*>(v), kv_stride, frame_of_group, key_mask, reinterpret_cast<__nv_bfloat16*>(out),
-            out_stride, nq, nk, causal ? 1 : 0, sl2);
-    else
-        attention_x_kernel<__half><<<grid, ATT_THREADS, 0, stream>>>(
-            reinterpret_cast<const __half*>(q), q_stride, reinterpret_cast<const __half*>(k), reinterpret_cast<const __half*>(v),
-            kv_stride, frame_of_group, key_mask, reinterpret_cast<__half*>(out), out_stride, nq, nk, causal ? 1 : 0, sl2);
+    const int stages = nk > BKV ? 2 : 1;
+    // short query groups (text self-attention, <= 32 tokens) run with 2 warps per CTA: less shared memory and fewer registers per
+    // CTA, so twice as many of these latency-bound CTAs are resident
+#define VIDIL_XATT(T, NW)                                                                                                        \
+    do {                                                                                                                         \
+        const size_t smem = static_cast<size_t>(NW) * 16 * HD * 2 + static_cast<size_t>(stages) * 2 * BKV * HD * 2;               \
+        auto kern = attention_x_kernel<T, NW>;                                                                                   \
+        const dim3 grid((nq + NW * 16 - 1) / (NW * 16), H, groups);                                                               \
+        kern<<<grid, NW * 32, smem, stream>>>(reinterpret_cast<const T*>(q), q_stride, reinterpret_cast<const T*>(k),             \
+                                             reinterpret_cast<const T*>(v), kv_stride, frame_of_group, key_mask,                \
+                                             reinterpret_cast<T*>(out), out_stride, nq, nk, causal ? 1 : 0, sl2);                 \
+    } while (0)
+    if (dt == DT_BF16) {
+        if (nq <= 32) VIDIL_XATT(__nv_bfloat16, 2); else VIDIL_XATT(__nv_bfloat16, 4);
+    } else {
+        if (nq <= 32) VIDIL_XATT(__half, 2); else VIDIL_XATT(__half, 4);
+    }
+#undef VIDIL_XATT
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;
 }
-
-namespace {
-}  // namespace
 
 int attention_run(const void* qkv, void* out, DType dt, int B, int N, int H, float scale, cudaStream_t stream) {
     if (B <= 0 || N <= 0 || H <= 0) return 0;

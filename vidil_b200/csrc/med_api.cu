@@ -472,8 +472,9 @@ size_t vidil_med_forward_workspace_bytes(const vidil_med* med, int32_t n_seq, in
 }
 
 int32_t vidil_med_forward(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens, const int32_t* input_ids,
-                          const int32_t* attention_mask, const int32_t* frame_of_seq, int32_t n_seq, int32_t seq_len, int32_t causal,
-                          float* out_hidden, float* out_logits, float* out_cls, void* workspace, size_t workspace_bytes, void* stream) {
+                          const int32_t* attention_mask, const int32_t* frame_of_seq, int32_t seqs_per_frame, int32_t n_seq, int32_t seq_len,
+                          int32_t causal, float* out_hidden, float* out_logits, float* out_cls, void* workspace, size_t workspace_bytes,
+                          void* stream) {
     if (med == nullptr || image_embeds == nullptr || input_ids == nullptr || workspace == nullptr) {
         set_error("vidil_med_forward: null argument");
         return 1;
@@ -484,8 +485,13 @@ int32_t vidil_med_forward(vidil_med* med, const float* image_embeds, int32_t n_f
                   c.max_positions, n_frames, n_img_tokens);
         return 1;
     }
-    if (frame_of_seq == nullptr && n_seq != n_frames) {
-        set_error("vidil_med_forward: %d sequences for %d frames need frame_of_seq", n_seq, n_frames);
+    if (seqs_per_frame > 0 && (frame_of_seq != nullptr || n_seq != n_frames * seqs_per_frame)) {
+        set_error("vidil_med_forward: seqs_per_frame=%d needs frame_of_seq == NULL and n_seq == n_frames * seqs_per_frame (%d != %d * %d)",
+                  seqs_per_frame, n_seq, n_frames, seqs_per_frame);
+        return 1;
+    }
+    if (seqs_per_frame <= 0 && frame_of_seq == nullptr && n_seq != n_frames) {
+        set_error("vidil_med_forward: %d sequences for %d frames need frame_of_seq or seqs_per_frame", n_seq, n_frames);
         return 1;
     }
     if ((out_logits != nullptr && !c.lm_head) || (out_cls != nullptr && c.cls_out <= 0)) {
@@ -511,8 +517,8 @@ int32_t vidil_med_forward(vidil_med* med, const float* image_embeds, int32_t n_f
     AttnArgs a;
     a.mode = causal ? MED_ATTN_CAUSAL : MED_ATTN_FULL;
     a.T_seq = seq_len;
-    a.groups = n_seq;
-    a.nq = seq_len;
+    a.groups = seqs_per_frame > 0 ? n_frames : n_seq;          // cross-attention query groups
+    a.nq = seqs_per_frame > 0 ? seqs_per_frame * seq_len : seq_len;
     a.frame_of_group = frame_of_seq;
     a.cross_kv = w.ckv;
     a.cross_layer_elems = static_cast<size_t>(n_frames) * n_img_tokens * 2 * D;

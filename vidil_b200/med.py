@@ -259,8 +259,10 @@ class BertModel(nn.Module):
     # -- whole-sequence forward ------------------------------------------------------------------------------------------
     @torch.no_grad()
     def run(self, input_ids, attention_mask, encoder_hidden_states, frame_of_seq=None, causal=False, want_hidden=True,
-            want_logits=False, want_cls=False):
-        """One vidil_med_forward call; returns (hidden | None, logits | None, cls | None)."""
+            want_logits=False, want_cls=False, seqs_per_frame=0):
+        """One vidil_med_forward call; returns (hidden | None, logits | None, cls | None).  frame_of_seq [n_seq]: the frame each
+        sequence attends to; or seqs_per_frame > 0: sequences come frame-major (sequence i reads frame i // seqs_per_frame) and
+        the cross-attention batches a frame's sequences into one query group."""
         enc = encoder_hidden_states
         if not enc.is_cuda:
             raise RuntimeError("vidil_b200: encoder_hidden_states must be on a CUDA device (no CPU path exists)")
@@ -286,7 +288,7 @@ class BertModel(nn.Module):
             need = n.lib.vidil_med_forward_workspace_bytes(n.handle, S, T, F_, Nv)
             ws = n.workspace(need, dev)
             ptr = lambda t: t.data_ptr() if t is not None else None  # noqa: E731
-            st = n.lib.vidil_med_forward(n.handle, enc.data_ptr(), F_, Nv, ids.data_ptr(), ptr(mask), ptr(fos), S, T,
+            st = n.lib.vidil_med_forward(n.handle, enc.data_ptr(), F_, Nv, ids.data_ptr(), ptr(mask), ptr(fos), int(seqs_per_frame), S, T,
                                          1 if causal else 0, ptr(hidden), ptr(logits), ptr(cls), ws.data_ptr(), ws.numel(),
                                          torch.cuda.current_stream().cuda_stream)
             _lib.check(st, "vidil_med_forward")
