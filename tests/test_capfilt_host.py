@@ -150,6 +150,20 @@ def test_capfilt_matches_reference_control_flow(extra, mode, threshold):
 
 
 @pytest.mark.skipif(not rs.reference_available(), reason="reference tree not mounted")
+@pytest.mark.parametrize("extra", CONFIGS[:3])
+@pytest.mark.parametrize("video_batch", [3, 16])
+def test_capfilt_video_batches_equal_reference(extra, video_batch):
+    """Several videos per ViT pass / beam search / ITM call: every item ends up exactly as the reference leaves it."""
+    ref_capfilt, _ = _reference_capfilt()
+    cfg = _config(extra)
+    ref_data, data = _data(), _data()
+    ref_capfilt(ref_data, cfg, "cpu")
+    capfilt.CapFilt(data, cfg, "cpu", captioner=FakeCaptioner(), filterer=FakeFilterer(), frame_loader=fake_loader,
+                    sentence_splitter=splitter, frame_processor=fake_processor, video_batch=video_batch)
+    assert data == ref_data
+
+
+@pytest.mark.skipif(not rs.reference_available(), reason="reference tree not mounted")
 def test_filter_captions_matches_reference():
     _, ref_filter = _reference_capfilt()
     images = torch.randn(5, 3, 4, 4) * 0.3

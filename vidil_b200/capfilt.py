@@ -88,9 +88,48 @@ def dedup_exact(captions):
 
 
 @torch.no_grad()
-def CapFilt(data, config, device, captioner=None, filterer=None, frame_loader=None, sentence_splitter=None, frame_processor=None):
+def filter_captions_batched(filterer, images_list, texts_list, threshold, mode='max_filter'):
+    """filter_captions for several videos in ONE native call: video v's captions texts_list[v] are scored against its own frames
+    images_list[v] only (ragged: any number of captions per video).  Returns one filtered list per video, each identical to
+    filter_captions(filterer, images_list[v], texts_list[v], threshold, mode)."""
+    tok = filterer.tokenizer
+    if tok is None:
+        raise RuntimeError("filter_captions needs filterer.tokenizer (bert-base-uncased is not on disk: pass tokenizer= to BLIP_ITM)")
+    flat_texts, seq_text, seq_frame, spans = [], [], [], []
+    frame0 = 0
+    for images, texts in zip(images_list, texts_list):
+        n_frames = images.size()[0]
+        spans.append((len(seq_text), len(texts), n_frames))
+        for t in texts:                                           # caption-major inside a video, like filter_captions' loop
+            seq_text += [len(flat_texts)] * n_frames
+            seq_frame += list(range(frame0, frame0 + n_frames))
+            flat_texts.append(t)
+        frame0 += n_frames
+    if not flat_texts:
+        return [[] for _ in texts_list]
+    text = tok(flat_texts, padding='max_length', truncation=True, max_length=35, return_tensors="pt")
+    sel = torch.tensor(seq_text, dtype=torch.long)
+    logits = filterer.forward_ids(torch.cat(list(images_list), dim=0), text.input_ids[sel], text.attention_mask[sel],
+                                  frame_of_seq=torch.tensor(seq_frame, dtype=torch.int32))
+    itm_score = _itm_prob(logits)
+    out = []
+    for (start, n_texts, n_frames), texts in zip(spans, texts_list):
+        kept = []
+        for i, t in enumerate(texts):
+            if _reduce_prob(itm_score[start + i * n_frames:start + (i + 1) * n_frames], mode) > threshold:
+                kept.append(t)
+        out.append(kept)
+    return out
+
+
+@torch.no_grad()
+def CapFilt(data, config, device, captioner=None, filterer=None, frame_loader=None, sentence_splitter=None, frame_processor=None,
+            video_batch=1):
     """run_video_CapFilt.py:139-204; mutates the items of `data` exactly as the reference does ('unfiltered_text', 'text').
-    frame_processor(frames_u8 [n,H,W,3] on device, image_size) -> float [n,3,S,S]; default: the native process_frames."""
+    frame_processor(frames_u8 [n,H,W,3] on device, image_size) -> float [n,3,S,S]; default: the native process_frames.
+    video_batch > 1: that many videos share one ViT pass, one beam search and one ITM call (the reference does one video at a time
+    with 4-8 frames, which leaves a B200 idle); every item ends up exactly as with video_batch=1, because a frame's caption and a
+    (caption, frame) score do not depend on what else is in the batch."""
     from .blip import blip_decoder, blip_itm
     if config.get("caption") and captioner is None:
         captioner = blip_decoder(pretrained=config["caption_model_ckpt"], image_size=config["image_size"], vit=config["vit"])
@@ -106,49 +145,69 @@ def CapFilt(data, config, device, captioner=None, filterer=None, frame_loader=No
     if do_split and sentence_splitter is None:
         sentence_splitter = _default_sentence_splitter()
 
-    for item in data:
-        video_path = item['video_path']
-        try:
-            raw_sample_frms = frame_loader(video_path, config["frm_sampling_strategy"], config["num_frm_CapFilt"])
-            frames_u8 = torch.as_tensor(np.asarray(raw_sample_frms)).to(device)
-            processed_frms = frame_processor(frames_u8, config["image_size"])         # = stack(process_frame(f) ...), :161
-        except Exception:  # noqa: BLE001 - the reference skips anything that fails to load (:162)
-            print(f'skip video that cannot be loaded: {video_path}')
+    data = list(data)
+    for c0 in range(0, len(data), max(1, video_batch)):
+        loaded = []                                              # (item, processed_frms)
+        for item in data[c0:c0 + max(1, video_batch)]:
+            video_path = item['video_path']
+            try:
+                raw_sample_frms = frame_loader(video_path, config["frm_sampling_strategy"], config["num_frm_CapFilt"])
+                frames_u8 = torch.as_tensor(np.asarray(raw_sample_frms)).to(device)
+                loaded.append((item, frame_processor(frames_u8, config["image_size"])))   # = stack(process_frame(f) ...), :161
+            except Exception:  # noqa: BLE001 - the reference skips anything that fails to load (:162)
+                print(f'skip video that cannot be loaded: {video_path}')
+        if not loaded:
             continue
 
-        if do_split:
-            original_caption_sentences = []
-            for original_cap in item['text']:
-                original_caption = original_cap.replace('\n', '. ')
-                for sent in sentence_splitter(original_caption):
-                    if len(sent) > 3:
-                        original_caption_sentences.append(sent.strip())
-        else:
-            original_caption_sentences = [cap.replace('\n', '. ').strip() for cap in item['text']]
+        # captioning (:172-194), one beam search for all frames of the chunk
+        per_item_generated = [[] for _ in loaded]
+        if config["caption"]:
+            counts = [frms.size()[0] for _, frms in loaded]
+            flat = caption_frames(captioner, torch.cat([frms for _, frms in loaded], dim=0), mode=config["generation_mode"])
+            pos = 0
+            for k, n in enumerate(counts):
+                per_item_generated[k] = dedup_exact(flat[pos:pos + n])                     # :184-188
+                pos += n
 
-        generated_captions_final = []
-        if not config["caption"]:
-            candidate_captions = original_caption_sentences
-            item['unfiltered_text'] = candidate_captions
-        else:
-            generated_captions = caption_frames(captioner, processed_frms, mode=config["generation_mode"])
-            generated_captions_final = dedup_exact(generated_captions)
-            if config['keep_original_caption']:
+        to_filter = []
+        for k, (item, _) in enumerate(loaded):
+            if do_split:
+                original_caption_sentences = []
+                for original_cap in item['text']:
+                    original_caption = original_cap.replace('\n', '. ')
+                    for sent in sentence_splitter(original_caption):
+                        if len(sent) > 3:
+                            original_caption_sentences.append(sent.strip())
+            else:
+                original_caption_sentences = [cap.replace('\n', '. ').strip() for cap in item['text']]
+            generated_captions_final = per_item_generated[k]
+            if not config["caption"]:
+                candidate_captions = original_caption_sentences
+                item['unfiltered_text'] = candidate_captions
+            elif config['keep_original_caption']:
                 candidate_captions = original_caption_sentences + generated_captions_final
                 item['unfiltered_text'] = candidate_captions
             else:
                 item['text'] = []
                 candidate_captions = generated_captions_final
                 item['unfiltered_text'] = candidate_captions
-        if config["filter"]:
-            if config["filter_generated_only"]:
-                item['text'] += filter_captions(filterer, processed_frms, generated_captions_final, config["threshold"],
-                                                config['filter_mode'])
+            if config["filter"]:
+                to_filter.append(generated_captions_final if config["filter_generated_only"] else candidate_captions)
             else:
-                item['text'] = filter_captions(filterer, processed_frms, candidate_captions, config["threshold"],
+                item['text'] = candidate_captions
+
+        # filtering (:196-203), one ITM call for every (caption, frame) pair of the chunk
+        if config["filter"]:
+            if len(loaded) == 1:
+                kept = [filter_captions(filterer, loaded[0][1], to_filter[0], config["threshold"], config['filter_mode'])]
+            else:
+                kept = filter_captions_batched(filterer, [frms for _, frms in loaded], to_filter, config["threshold"],
                                                config['filter_mode'])
-        else:
-            item['text'] = candidate_captions
+            for (item, _), texts in zip(loaded, kept):
+                if config["filter_generated_only"]:
+                    item['text'] += texts
+                else:
+                    item['text'] = texts
 
 
 def collect_rank_outputs(items):
