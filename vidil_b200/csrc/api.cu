@@ -2,6 +2,7 @@
 // operator-level entry points used by the parity tests.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <atomic>
@@ -28,6 +29,15 @@ void set_error(const char* fmt, ...) {
 const char* get_error() { return g_error.c_str(); }
 void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 int64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+// PDL is off unless VIDIL_PDL=1, or a caller that measured a gain turns it on for its scope (the caption decoder's chain of
+// ~2400 short kernels; on the ViT path, whose kernels run 50-300 us each under the power cap, it costs 1 %).
+static const int g_pdl_env = [] {
+    const char* e = getenv("VIDIL_PDL");
+    return e == nullptr ? -1 : (e[0] == '0' ? 0 : 1);
+}();
+static thread_local int g_pdl_scope = 0;
+bool pdl_enabled() { return g_pdl_env >= 0 ? g_pdl_env == 1 : g_pdl_scope > 0; }
+void pdl_scope(int delta) { g_pdl_scope += delta; }
 
 namespace {
 

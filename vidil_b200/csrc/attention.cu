@@ -283,6 +283,8 @@ __global__ void __launch_bounds__(NWARPS * 32)
     attention_x_kernel(const T* __restrict__ q, int64_t q_stride, const T* __restrict__ k, const T* __restrict__ v,
                        int64_t kv_stride, const int32_t* __restrict__ frame_of_group, const int32_t* __restrict__ key_mask,
                        T* __restrict__ out, int64_t out_stride, int nq, int nk, int causal, float scale_log2e) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     // Q tile (16 rows per warp) | K/V stage 0 | K/V stage 1 (only when there is more than one key block)
     extern __shared__ __align__(128) uint8_t smem[];
     constexpr int XBQ = NWARPS * 16, XT = NWARPS * 32;
@@ -563,6 +565,8 @@ template <typename T>
 __global__ void __launch_bounds__(32)
     cross_decode_mma_chunked_kernel(const __grid_constant__ CUtensorMap kv_map, const T* __restrict__ q, T* __restrict__ out, int row0,
                                     int Nv, int nq, int H, float scale_log2e) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     extern __shared__ uint8_t xsmem_raw[];
     uint8_t* xsmem = xsmem_raw + ((1024u - (ptx::smem_u32(xsmem_raw) & 1023u)) & 1023u);
     const int h = blockIdx.x, f = blockIdx.y;
@@ -614,6 +618,8 @@ template <typename T>
 __global__ void __launch_bounds__(32)
     cross_decode_mma_kernel(const __grid_constant__ CUtensorMap kv_map, const T* __restrict__ q, T* __restrict__ out, int row0, int Nv,
                             int nq, int H, float scale_log2e) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     extern __shared__ uint8_t xsmem_raw[];
     // the 128B swizzle pattern is a function of the address bits: tiles must start on a 1024-byte boundary
     uint8_t* xsmem = xsmem_raw + ((1024u - (ptx::smem_u32(xsmem_raw) & 1023u)) & 1023u);
@@ -677,7 +683,8 @@ int cross_decode_mma_run(const CUtensorMap& kv_map_sw128, int row0, const void* 
     do {                                                                                                                       \
         auto k = chunked ? cross_decode_mma_chunked_kernel<T> : cross_decode_mma_kernel<T>;                                    \
         VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));           \
-        k<<<dim3(H, F), 32, smem, stream>>>(kv_map_sw128, reinterpret_cast<const T*>(q), reinterpret_cast<T*>(out), row0, Nv, nq, H, sl2); \
+        VIDIL_CUDA_OK(launch_pdl(k, dim3(H, F), dim3(32), smem, stream, kv_map_sw128, reinterpret_cast<const T*>(q),         \
+                                 reinterpret_cast<T*>(out), row0, Nv, nq, H, sl2));                                           \
     } while (0)
     if (dt == DT_BF16)
         VIDIL_XDEC(__nv_bfloat16);
@@ -714,9 +721,9 @@ int attention_x_run(const void* q, int64_t q_stride, const void* k, const void* 
         const size_t smem = static_cast<size_t>(NW) * 16 * HD * 2 + static_cast<size_t>(stages) * 2 * BKV * HD * 2;               \
         auto kern = attention_x_kernel<T, NW>;                                                                                   \
         const dim3 grid((nq + NW * 16 - 1) / (NW * 16), H, groups);                                                               \
-        kern<<<grid, NW * 32, smem, stream>>>(reinterpret_cast<const T*>(q), q_stride, reinterpret_cast<const T*>(k),             \
-                                             reinterpret_cast<const T*>(v), kv_stride, frame_of_group, key_mask,                \
-                                             reinterpret_cast<T*>(out), out_stride, nq, nk, causal ? 1 : 0, sl2);                 \
+        VIDIL_CUDA_OK(launch_pdl(kern, grid, dim3(NW * 32), smem, stream, reinterpret_cast<const T*>(q), q_stride,                \
+                                 reinterpret_cast<const T*>(k), reinterpret_cast<const T*>(v), kv_stride, frame_of_group, key_mask, \
+                                 reinterpret_cast<T*>(out), out_stride, nq, nk, causal ? 1 : 0, sl2));                            \
     } while (0)
     if (dt == DT_BF16) {
         if (nq <= 32) VIDIL_XATT(__nv_bfloat16, 2); else VIDIL_XATT(__nv_bfloat16, 4);

@@ -170,6 +170,9 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     __syncthreads();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // PDL: set-up done; let the next kernel start its own, then wait for the predecessor's qkv before any global access
+    ptx::griddep_launch();
+    ptx::griddep_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -416,8 +419,8 @@ int launch_tc(const AttentionMaps& m, int B, int N, int H, float scale_log2e, cu
     int grid = gemm_num_sms();
     if (grid > n_items) grid = n_items;
     if (grid < 1) return 1;
-    kern<<<grid, ATC_THREADS, ATC_SMEM, stream>>>(m.q, m.kv, m.out, n_items, N, H, scale_log2e, g_trace, m.causal ? 1 : 0);
-    VIDIL_CUDA_OK(cudaGetLastError());
+    VIDIL_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(ATC_THREADS), ATC_SMEM, stream, m.q, m.kv, m.out, n_items, N, H, scale_log2e, g_trace,
+                             m.causal ? 1 : 0));
     count_launches(1);
     return 0;
 }

@@ -158,6 +158,9 @@ __global__ void __launch_bounds__(ATL_THREADS, 1)
     __syncthreads();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // PDL: set-up done; let the next kernel start its own, then wait for the predecessor's qkv before any global access
+    ptx::griddep_launch();
+    ptx::griddep_wait();
 
     if (warp == 0) {
         if (lane == 0) {
@@ -663,10 +666,9 @@ int launch_long(const AttentionMaps& m, float scale, cudaStream_t stream) {
     int grid = gemm_num_sms();
     if (grid > n_items) grid = n_items;
     if (grid < 1) return 1;
-    kern<<<grid, ATL_THREADS, lay.total, stream>>>(m.q, m.kv, m.out, n_items, m.N, m.H, m.KB, m.nkb, m.n_qt, m.n_tail,
-                                                    scale * 1.4426950408889634f, reinterpret_cast<const T*>(m.qkv),
-                                                    reinterpret_cast<T*>(m.out_ptr));
-    VIDIL_CUDA_OK(cudaGetLastError());
+    VIDIL_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(ATL_THREADS), lay.total, stream, m.q, m.kv, m.out, n_items, m.N, m.H, m.KB, m.nkb,
+                             m.n_qt, m.n_tail, scale * 1.4426950408889634f, reinterpret_cast<const T*>(m.qkv),
+                             reinterpret_cast<T*>(m.out_ptr)));
     count_launches(1);
     const int row_first = m.n_qt * QT;
     if (m.n_tail == 0 && row_first < m.N) {

@@ -250,6 +250,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         __syncthreads();
     ptx::tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_ptr_smem;
+    // PDL: barriers, TMEM and descriptors are set up; the next kernel may start its own set-up on SMs this grid has left, and this
+    // grid may now wait for its predecessors' results (every global read and write of the kernel lies below this line).
+    ptx::griddep_launch();
+    ptx::griddep_wait();
 
     // Static persistent schedule, identical in every role: cluster c takes tiles c, c+G, c+2G, ...
     // N is the fast index so concurrently running clusters share a few A row-bands and all of W in L2.
@@ -573,13 +577,15 @@ int launch(const GemmProblem& p, cudaStream_t stream) {
     cfg.blockDim = dim3(NUM_THREADS);
     cfg.dynamicSmemBytes = C::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = CG;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     VIDIL_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, p.map_a, p.map_w, p.map_out, p.M, p.N, p.K, e));
     count_launches(1);
     return 0;

@@ -29,6 +29,27 @@ const char* get_error();
 void count_launches(int n);
 int64_t launch_count();
 
+// Whether kernels are launched with programmatic stream serialization (PDL); VIDIL_PDL=0 in the environment switches it off.
+bool pdl_enabled();
+void pdl_scope(int delta);  // +1 / -1 around a region whose launches should use PDL (unless VIDIL_PDL forces it either way)
+
+// <<<grid, block, smem, stream>>> with the PDL attribute: the kernel may begin before its predecessor in the stream has finished
+// and must call ptx::griddep_wait() before it touches global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 #define VIDIL_CUDA_OK(expr)                                                                  \
     do {                                                                                     \
         cudaError_t _e = (expr);                                                             \

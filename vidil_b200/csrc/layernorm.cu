@@ -41,6 +41,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
     layernorm_kernel(const float* __restrict__ in, int64_t in_row_stride, const float* __restrict__ gamma,
                      const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps) {
     constexpr int D = VPL * 128;
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -85,6 +87,8 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
     layernorm_post_kernel(float* __restrict__ resid, const T* __restrict__ in16, const float* __restrict__ gamma,
                           const float* __restrict__ beta, T* __restrict__ out16, int rows, float eps) {
     constexpr int D = VPL * 128;
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (row >= rows) return;
@@ -137,11 +141,11 @@ int launch_ln_post(float* resid, const void* in16, const float* g, const float* 
     const T* i16 = reinterpret_cast<const T*>(in16);
     T* o = reinterpret_cast<T*>(out16);
     switch (D) {
-        case 768: layernorm_post_kernel<T, 6, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
-        case 1024: layernorm_post_kernel<T, 8, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
-        case 512: layernorm_post_kernel<T, 4, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
-        case 256: layernorm_post_kernel<T, 2, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
-        case 128: layernorm_post_kernel<T, 1, IN16><<<grid, LN_WARPS * 32, 0, s>>>(resid, i16, g, b, o, rows, eps); break;
+        case 768: VIDIL_CUDA_OK(launch_pdl(layernorm_post_kernel<T, 6, IN16>, dim3(grid), dim3(LN_WARPS * 32), 0, s, resid, i16, g, b, o, rows, eps)); break;
+        case 1024: VIDIL_CUDA_OK(launch_pdl(layernorm_post_kernel<T, 8, IN16>, dim3(grid), dim3(LN_WARPS * 32), 0, s, resid, i16, g, b, o, rows, eps)); break;
+        case 512: VIDIL_CUDA_OK(launch_pdl(layernorm_post_kernel<T, 4, IN16>, dim3(grid), dim3(LN_WARPS * 32), 0, s, resid, i16, g, b, o, rows, eps)); break;
+        case 256: VIDIL_CUDA_OK(launch_pdl(layernorm_post_kernel<T, 2, IN16>, dim3(grid), dim3(LN_WARPS * 32), 0, s, resid, i16, g, b, o, rows, eps)); break;
+        case 128: VIDIL_CUDA_OK(launch_pdl(layernorm_post_kernel<T, 1, IN16>, dim3(grid), dim3(LN_WARPS * 32), 0, s, resid, i16, g, b, o, rows, eps)); break;
         default: set_error("layernorm: unsupported width %d (supported: 128, 256, 512, 768, 1024)", D); return 1;
     }
     VIDIL_CUDA_OK(cudaGetLastError());
@@ -155,12 +159,12 @@ int launch_ln(const float* in, int64_t stride, const float* g, const float* b, v
     const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
     OutT* o = reinterpret_cast<OutT*>(out);
     switch (D) {
-        case 768: layernorm_kernel<OutT, 6><<<grid, LN_WARPS * 32, 0, s>>>(in, stride, g, b, o, rows, eps); break;
-        case 1024: layernorm_kernel<OutT, 8><<<grid, LN_WARPS * 32, 0, s>>>(in, stride, g, b, o, rows, eps); break;
-        case 1280: layernorm_kernel<OutT, 10><<<grid, LN_WARPS * 32, 0, s>>>(in, stride, g, b, o, rows, eps); break;
-        case 512: layernorm_kernel<OutT, 4><<<grid, LN_WARPS * 32, 0, s>>>(in, stride, g, b, o, rows, eps); break;
-        case 256: layernorm_kernel<OutT, 2><<<grid, LN_WARPS * 32, 0, s>>>(in, stride, g, b, o, rows, eps); break;
-        case 128: layernorm_kernel<OutT, 1><<<grid, LN_WARPS * 32, 0, s>>>(in, stride, g, b, o, rows, eps); break;
+        case 768: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 6>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
+        case 1024: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 8>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
+        case 1280: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 10>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
+        case 512: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 4>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
+        case 256: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
+        case 128: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 1>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
         default: set_error("layernorm: unsupported width %d (supported: 128, 256, 512, 768, 1024, 1280)", D); return 1;
     }
     VIDIL_CUDA_OK(cudaGetLastError());

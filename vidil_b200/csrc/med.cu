@@ -62,6 +62,8 @@ __device__ __forceinline__ float warp_max(float x) {
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void med_embed_kernel(const int32_t* __restrict__ ids, const float* __restrict__ word, const float* __restrict__ pos,
                                  float* __restrict__ resid, int64_t rows, int T, int pos0, int ids_mod, int D, int vocab, int max_pos) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int d4 = D / 4;
     const int64_t total = rows * d4;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -93,6 +95,8 @@ template <typename T>
 __global__ void __launch_bounds__(SA_WARPS * 32)
     med_self_attn_decode_kernel(const T* __restrict__ qkv, T* __restrict__ cache, const int32_t* __restrict__ anc, T* __restrict__ out,
                                 int rows, int H, int pos, int Tmax, float scale) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     __shared__ float s_sc[SA_WARPS][SA_MAX_KEYS];
     __shared__ int s_src[SA_WARPS][SA_MAX_KEYS];
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -291,6 +295,8 @@ __global__ void __launch_bounds__(CD_THREADS)
 template <typename T>
 __global__ void med_cache_fill_kernel(const T* __restrict__ qkv, T* __restrict__ cache, int64_t n_rows, int T_seq, int D, int Tmax,
                                       int beams) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int chunks = 2 * D / 8;
     const int64_t total = n_rows * chunks;
     for (int64_t i = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; i < total;
@@ -350,6 +356,8 @@ __device__ __forceinline__ void block_argmax(float& v, int& i, float* s_v, int* 
 __global__ void __launch_bounds__(TK_THREADS)
     med_logits_topk_kernel(const float* __restrict__ logits, int64_t ld, int row_mul, const float* __restrict__ beam_scores, int V,
                            int nc, int ban_token, float* __restrict__ cand_score, int32_t* __restrict__ cand_tok) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     __shared__ float s_red[TK_THREADS / 32];
     __shared__ float s_v[TK_THREADS / 32];
     __shared__ int s_i[TK_THREADS / 32];
@@ -535,6 +543,8 @@ __device__ void hyp_add(const BeamState& st, int b, const int32_t* toks, int len
 
 __global__ void med_beam_step_kernel(BeamState st, const float* __restrict__ cand_score, const int32_t* __restrict__ cand_tok,
                                      int lists_per_frame, int nc, int V, int cur_len, int parity) {
+    ptx::griddep_launch();
+    ptx::griddep_wait();
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= st.frames) return;
     const int K = st.beams, Tm = st.t_max;
@@ -691,8 +701,8 @@ inline int grid_for(int64_t n, int block) {
 int med_embed_run(const int32_t* ids, const float* word, const float* pos, float* resid, int64_t rows, int T, int pos0, int ids_mod,
                   int D, int vocab, int max_pos, cudaStream_t s) {
     if (rows <= 0) return 0;
-    med_embed_kernel<<<grid_for(rows * (D / 4), 256), 256, 0, s>>>(ids, word, pos, resid, rows, T, pos0, ids_mod, D, vocab, max_pos);
-    VIDIL_CUDA_OK(cudaGetLastError());
+    VIDIL_CUDA_OK(launch_pdl(med_embed_kernel, dim3(grid_for(rows * (D / 4), 256)), dim3(256), 0, s, ids, word, pos, resid, rows, T, pos0,
+                             ids_mod, D, vocab, max_pos));
     count_launches(1);
     return 0;
 }
@@ -706,14 +716,13 @@ int med_self_attn_decode_run(const void* qkv, void* cache, const int32_t* anc, v
     }
     const int grid = (rows * H + SA_WARPS - 1) / SA_WARPS;
     if (dt == DT_BF16)
-        med_self_attn_decode_kernel<__nv_bfloat16><<<grid, SA_WARPS * 32, 0, s>>>(
-            reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(cache), anc,
-            reinterpret_cast<__nv_bfloat16*>(out), rows, H, pos, Tmax, scale);
+        VIDIL_CUDA_OK(launch_pdl(med_self_attn_decode_kernel<__nv_bfloat16>, dim3(grid), dim3(SA_WARPS * 32), 0, s,
+                                 reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(cache), anc,
+                                 reinterpret_cast<__nv_bfloat16*>(out), rows, H, pos, Tmax, scale));
     else
-        med_self_attn_decode_kernel<__half><<<grid, SA_WARPS * 32, 0, s>>>(reinterpret_cast<const __half*>(qkv),
-                                                                          reinterpret_cast<__half*>(cache), anc,
-                                                                          reinterpret_cast<__half*>(out), rows, H, pos, Tmax, scale);
-    VIDIL_CUDA_OK(cudaGetLastError());
+        VIDIL_CUDA_OK(launch_pdl(med_self_attn_decode_kernel<__half>, dim3(grid), dim3(SA_WARPS * 32), 0, s,
+                                 reinterpret_cast<const __half*>(qkv), reinterpret_cast<__half*>(cache), anc, reinterpret_cast<__half*>(out),
+                                 rows, H, pos, Tmax, scale));
     count_launches(1);
     return 0;
 }
@@ -801,8 +810,8 @@ int med_logits_topk_run(const float* logits, int64_t ld, int row_mul, const floa
         set_error("med top-k: nc=%d (1..%d), V=%d and ld=%lld must be multiples of 4", nc, TK_MAX_NC, V, (long long)ld);
         return 1;
     }
-    med_logits_topk_kernel<<<n_lists, TK_THREADS, 0, s>>>(logits, ld, row_mul, beam_scores, V, nc, ban_token, cand_score, cand_tok);
-    VIDIL_CUDA_OK(cudaGetLastError());
+    VIDIL_CUDA_OK(launch_pdl(med_logits_topk_kernel, dim3(n_lists), dim3(TK_THREADS), 0, s, logits, ld, row_mul, beam_scores, V, nc, ban_token,
+                             cand_score, cand_tok));
     count_launches(1);
     return 0;
 }
@@ -821,8 +830,8 @@ int med_beam_step_run(const BeamState& st, const float* cand_score, const int32_
         set_error("beam step: num_beams=%d (at most 4) with %d candidates per list (must be 2*num_beams)", st.beams, nc);
         return 1;
     }
-    med_beam_step_kernel<<<(st.frames + 63) / 64, 64, 0, s>>>(st, cand_score, cand_tok, lists_per_frame, nc, V, cur_len, parity);
-    VIDIL_CUDA_OK(cudaGetLastError());
+    VIDIL_CUDA_OK(launch_pdl(med_beam_step_kernel, dim3((st.frames + 63) / 64), dim3(64), 0, s, st, cand_score, cand_tok, lists_per_frame, nc, V,
+                             cur_len, parity));
     count_launches(1);
     return 0;
 }

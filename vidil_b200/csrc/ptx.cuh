@@ -55,6 +55,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ----------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start
+// while its predecessor in the stream is still running; griddep_wait() blocks until every prerequisite grid has completed and
+// its memory is visible, griddep_launch() lets the NEXT kernel of the stream start its own prologue.  Both are no-ops for a
+// kernel launched without the attribute.  Rule used throughout: nothing that reads or writes global memory precedes the wait.
+// ----------------------------------------------------------------------------------------
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// ----------------------------------------------------------------------------------------
 // mbarrier
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
