@@ -350,3 +350,20 @@ def test_decoder_forward_long_sequence_and_ragged_frames(cuda):
     with torch.no_grad():
         ref, _ = med_oracle.decoder_logits(sd, "text_decoder.", ids, enc[frame_of], c["num_attention_heads"], c["num_hidden_layers"])
     assert (logits.cpu() - ref).abs().max() < LOGIT_TOL["fp16"]
+
+
+def test_generate_chunks_large_batches(cuda, monkeypatch):
+    """A batch whose cross-attention K/V would not fit the workspace budget is decoded in chunks, with identical captions."""
+    name = "tiny"
+    m, _ = _decoder(name, "bf16", cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    enc = W.image_tokens(11, 40, c["encoder_width"], seed=13).to(cuda)
+    kw = dict(input_ids=torch.tensor([sp["prompt"]], dtype=torch.long).repeat(11, 1), max_length=10, min_length=5, num_beams=3,
+              eos_token_id=sp["eos"], pad_token_id=sp["pad"], encoder_hidden_states=enc, return_scores=True)
+    full = m.generate(**kw)
+    need3 = m.bert._native.lib.vidil_med_generate_workspace_bytes(m.bert._native.handle, 3, 40, 3, 10, 4)
+    monkeypatch.setenv("VIDIL_MED_WORKSPACE_GB", str((need3 + 4096) / (1 << 30)))   # room for 3 frames at a time
+    before = _lib.launch_count()
+    chunked = m.generate(**kw)
+    assert all(torch.equal(a, b) for a, b in zip(full, chunked))
+    assert _lib.launch_count() - before > 3 * 100                    # four chunks' worth of kernels

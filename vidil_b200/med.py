@@ -15,6 +15,7 @@ Inference only, CUDA only — there is no CPU implementation and no fallback.
 from __future__ import annotations
 
 import ctypes
+import os
 from types import SimpleNamespace
 
 import torch
@@ -370,13 +371,21 @@ class BertLMHeadModel(nn.Module):
             toks = torch.empty(B, max_length, dtype=torch.int32, device=dev)
             lens = torch.empty(B, dtype=torch.int32, device=dev)
             scores = torch.empty(B, dtype=torch.float32, device=dev)
-            need = n.lib.vidil_med_generate_workspace_bytes(n.handle, B, Nv, num_beams, max_length, Lp)
-            ws = n.workspace(need, dev)
-            st = n.lib.vidil_med_generate(n.handle, enc.data_ptr(), B, Nv, prompt.data_ptr(), Lp, num_beams, max_length,
-                                          min_length, eos_token_id, pad_token_id, float(length_penalty), toks.data_ptr(),
-                                          lens.data_ptr(), scores.data_ptr(), ws.data_ptr(), ws.numel(),
-                                          torch.cuda.current_stream().cuda_stream)
-            _lib.check(st, "vidil_med_generate")
+            # the workspace holds the cross-attention K/V of every frame for every layer (12 x frames x tokens x 3 KB): bound it,
+            # and run the frames in chunks when a batch would need more (captions do not depend on the batch they are in)
+            budget = int(float(os.environ.get("VIDIL_MED_WORKSPACE_GB", "32")) * (1 << 30))
+            chunk = B
+            while chunk > 1 and n.lib.vidil_med_generate_workspace_bytes(n.handle, chunk, Nv, num_beams, max_length, Lp) > budget:
+                chunk = (chunk + 1) // 2
+            for b0 in range(0, B, chunk):
+                nb = min(chunk, B - b0)
+                need = n.lib.vidil_med_generate_workspace_bytes(n.handle, nb, Nv, num_beams, max_length, Lp)
+                ws = n.workspace(need, dev)
+                st = n.lib.vidil_med_generate(n.handle, enc[b0:b0 + nb].data_ptr(), nb, Nv, prompt.data_ptr(), Lp, num_beams, max_length,
+                                              min_length, eos_token_id, pad_token_id, float(length_penalty), toks[b0:b0 + nb].data_ptr(),
+                                              lens[b0:b0 + nb].data_ptr(), scores[b0:b0 + nb].data_ptr(), ws.data_ptr(), ws.numel(),
+                                              torch.cuda.current_stream().cuda_stream)
+                _lib.check(st, "vidil_med_generate")
             width = int(lens.max().item())          # finalize: sent_max_len = min(max(sent_lengths) + 1, max_length)
             out = toks[:, :width].long()
         return (out, scores, lens) if return_scores else out
