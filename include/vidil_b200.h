@@ -206,7 +206,9 @@ int32_t vidil_med_forward(vidil_med* med, const float* image_embeds, int32_t n_f
  * image tokens are projected once per frame.  Search rules: transformers v4.15 beam_search / BeamSearchScorer with
  * early_stopping False, repetition_penalty 1.0.  Outputs (device): out_tokens int32 [n_frames, max_length] = best
  * hypothesis incl. the prompt, followed by eos when it fits, padded with pad; out_lengths int32 [n_frames];
- * out_scores fp32 [n_frames] (sum of log-probs / len^length_penalty).  num_beams <= 4, max_length <= 64. */
+ * out_scores fp32 [n_frames] (sum of log-probs / len^length_penalty).  num_beams <= 4, max_length <= 64.
+ * Like transformers' loop the search stops as soon as every frame is done: from min_length on the call synchronises `stream`
+ * every other step to read one counter; the outputs are enqueued on `stream` as everywhere else. */
 size_t  vidil_med_generate_workspace_bytes(const vidil_med* med, int32_t n_frames, int32_t n_img_tokens, int32_t num_beams,
                                            int32_t max_length, int32_t prompt_len);
 int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens,

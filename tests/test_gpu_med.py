@@ -367,3 +367,31 @@ def test_generate_chunks_large_batches(cuda, monkeypatch):
     chunked = m.generate(**kw)
     assert all(torch.equal(a, b) for a, b in zip(full, chunked))
     assert _lib.launch_count() - before > 3 * 100                    # four chunks' worth of kernels
+
+
+def test_generate_stops_early_when_all_frames_are_done(cuda):
+    """A decoder whose LM bias makes [SEP] overwhelmingly likely finishes every frame right after min_length: the search stops
+    issuing decode steps (far fewer kernels than a full-length run) and still returns what the oracle's loop returns."""
+    name = "tiny"
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    sd = W.med_state_dict(name, "decoder", seed=0)
+    sd["text_decoder.cls.predictions.bias"] = sd["text_decoder.cls.predictions.bias"].clone()
+    sd["text_decoder.cls.predictions.bias"][sp["eos"]] += 12.0
+    m = BertLMHeadModel(_cfg(name), compute_dtype="fp16")
+    m.load_state_dict({k[len("text_decoder."):]: v for k, v in sd.items()}, strict=False)
+    m = m.to(cuda).eval()
+    enc = W.image_tokens(5, 6, c["encoder_width"], seed=17)
+    kw = dict(input_ids=torch.tensor([sp["prompt"]], dtype=torch.long).repeat(5, 1), min_length=6, num_beams=3, eos_token_id=sp["eos"],
+              pad_token_id=sp["pad"], encoder_hidden_states=enc.to(cuda), return_scores=True)
+    m.generate(max_length=40, **kw)                                            # packs the weights
+    before = _lib.launch_count()
+    out, scores, lens = m.generate(max_length=40, **kw)
+    launches = _lib.launch_count() - before
+    ref_toks, ref_scores, trace = med_oracle.generate(sd, enc, sp["prompt"], c["num_attention_heads"], c["num_hidden_layers"],
+                                                      num_beams=3, max_length=40, min_length=6, eos=sp["eos"], pad=sp["pad"])
+    assert len(trace) < 10 and all(trace[-1]["done"])                          # the oracle's loop broke early too
+    got = [out[b, :int(lens[b])].tolist() for b in range(5)]
+    assert got == ref_toks and all(g[-1] == sp["eos"] and len(g) <= 9 for g in got)
+    assert np.allclose(scores.cpu().numpy(), np.asarray(ref_scores, dtype=np.float32), atol=2e-2)
+    per_step = 2 * 17 + 8                                                       # kernels of one tiny decode step (2 layers)
+    assert launches < 12 * per_step, f"{launches} kernels: the search did not stop early (a 36-step run takes > {30 * per_step})"

@@ -194,6 +194,7 @@ struct BeamState {
     int32_t* hyp_tok = nullptr;    // [frames][beams+1][t_max]
     double* worst = nullptr;       // [frames]
     int32_t* done = nullptr;       // [frames]
+    int32_t* n_done = nullptr;     // [1] number of frames whose search has finished (the host polls it to stop early)
 };
 // resid[r,:] = word[ids[ids_mod ? r % ids_mod : r],:] + pos[pos0 + r % T,:]
 int med_embed_run(const int32_t* ids, const float* word, const float* pos, float* resid, int64_t rows, int T, int pos0, int ids_mod,

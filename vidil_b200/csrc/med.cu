@@ -621,7 +621,10 @@ __global__ void med_beam_step_kernel(BeamState st, const float* __restrict__ can
     // BeamHypotheses.is_done(best_sum_logprobs = max of the step's candidates, cur_len), early_stopping False
     if (st.hyp_n[b] >= K) {
         const double cur = static_cast<double>(top_s[0]) / pow(static_cast<double>(cur_len), static_cast<double>(st.length_penalty));
-        if (st.worst[b] >= cur) st.done[b] = 1;
+        if (st.worst[b] >= cur) {
+            st.done[b] = 1;
+            atomicAdd(st.n_done, 1);
+        }
     }
 }
 
@@ -666,6 +669,7 @@ __global__ void med_beam_init_kernel(BeamState st, const int32_t* __restrict__ p
             st.seq[(p * R + r) * Tm + i] = i < prompt_len ? prompt[i] : st.pad;
             st.anc[(p * R + r) * Tm + i] = b * K;
         }
+    if (r == 0) *st.n_done = 0;
     st.beam_scores[r] = (r % K == 0) ? 0.f : -1e9f;
     st.cur_tok[r] = prompt[prompt_len - 1];
     if (r % K == 0) {

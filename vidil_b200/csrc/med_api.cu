@@ -337,6 +337,7 @@ void carve_beam(Carver& cv, int F, int K, int Tm, BeamWs& w) {
     w.st.hyp_tok = cv.take<int32_t>(static_cast<size_t>(F) * (K + 1) * Tm);
     w.st.worst = cv.take<double>(F);
     w.st.done = cv.take<int32_t>(F);
+    w.st.n_done = cv.take<int32_t>(1);
     w.cand_score = cv.take<float>(R * 2 * K);
     w.cand_tok = cv.take<int32_t>(R * 2 * K);
     w.prompt = cv.take<int32_t>(Tm);
@@ -634,6 +635,18 @@ int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_
                 return 1;
             if (med_beam_step_run(st, w.beam.cand_score, w.beam.cand_tok, K, nc, V, cur_len, parity, s)) return 1;
             parity ^= 1;
+            // `if beam_scorer.is_done: break` of transformers' beam_search: every other step from min_length on (no frame can finish
+            // earlier) the host reads the count of finished frames; the remaining steps would only pad.  This synchronises the
+            // stream — once per ~8 ms of queued work.
+            if (cur_len >= min_length && cur_len + 1 < max_length && ((cur_len - min_length) & 1) == 0) {
+                int32_t n_done = 0;
+                VIDIL_CUDA_OK(cudaMemcpyAsync(&n_done, st.n_done, sizeof(n_done), cudaMemcpyDeviceToHost, s));
+                VIDIL_CUDA_OK(cudaStreamSynchronize(s));
+                if (n_done >= F) {
+                    ++cur_len;
+                    break;
+                }
+            }
         }
     }
     return med_beam_finalize_run(st, cur_len, parity, max_length, out_tokens, out_lengths, out_scores, s);
