@@ -531,13 +531,23 @@ def run_capfilt(args):
     """BASELINE.json configs[2]: `--videos` synthetic videos x 8 frames through the CapFilt models of run_video_CapFilt.py —
     captioner = BLIP ViT + med.py decoder with beam search (beams 3, max_length 20, min_length 5, :102), filterer = BLIP_ITM
     (its own ViT + the multimodal text encoder + itm_head) over every (caption, frame) pair of a video (:108-120).  One step =
-    all videos once; frames start on the device.  Not the driver's line."""
+    all videos once; frames start on the device.  Under torchrun the videos are sharded over the ranks with the reference's
+    slice formula (run_video_CapFilt.py:239-241) and the kept captions are merged by one all-gather of JSON rows (BASELINE.json
+    configs[4], CapFilt half).  Not the driver's line."""
     import torch
+    import torch.distributed as dist
 
+    from vidil_b200 import distributed as vdist
     from vidil_b200.blip import BLIP_Decoder, BLIP_ITM
-    dev = torch.device("cuda", 0)
+    rank, world, local = dist_env(args)
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        vdist.init_distributed_mode("nccl")
     torch.manual_seed(0)
-    V, Fv = args.videos, 8
+    Fv = 8
+    v_start, v_end = vdist.shard_bounds(args.videos, world, rank)
+    V = v_end - v_start
     n_frames = V * Fv
     cap = BLIP_Decoder(image_size=args.image_size, vit=args.vit, compute_dtype=args.dtype)
     _randomise(cap)
@@ -595,16 +605,36 @@ def run_capfilt(args):
     for _ in range(args.warmup):
         step(False)
     torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
     before = lib.launch_count()
     acc = [0.0] * 4
     for _ in range(args.steps):
-        step(True)
+        out, keep = step(True)
         torch.cuda.synchronize()
         for i in range(4):
             acc[i] += ev[i].elapsed_time(ev[i + 1])
     launches = lib.launch_count() - before
     ms = [a / args.steps for a in acc]
     total = sum(ms)
+    # the rows a rank contributes: video -> kept captions (token ids here: there is no vocabulary to decode with), then the one
+    # collective of the path
+    t0 = time.perf_counter()
+    rows = {f"video{v_start + v}": [out[v * Fv + i].tolist() for i in range(Fv) if bool(keep[v * Fv + i])] for v in range(V)}
+    merged = vdist.gather_and_write(rows, None, device=dev)
+    gather_ms = (time.perf_counter() - t0) * 1e3
+    if world > 1:
+        t = torch.tensor([total, gather_ms] + ms, dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total, gather_ms, ms = float(t[0]), float(t[1]), [float(x) for x in t[2:]]
+        cnt = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(cnt)
+        launches = int(cnt.item())
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    n_frames_all = args.videos * Fv
     cpu = None
     if not args.no_cpu_baseline:
         # the reference's text side on the host cores: oracle port of med.py + the restated beam search, 2 frames of image tokens
@@ -621,15 +651,19 @@ def run_capfilt(args):
                "sample": "oracle/med_oracle.generate on 2 frames of image tokens (cached decoder, beams 3, max_length 20)"}
     tokens = (args.image_size // 16) ** 2 + 1
     D, depth, _ = VIT[args.vit]
-    print(json.dumps({"metric": "frames/sec through CapFilt (caption + filter)", "value": n_frames / (total / 1e3), "unit": "frames/s",
-                      "ms_per_step": total, "steps": args.steps, "warmup": args.warmup, "gpu_launches": launches,
+    print(json.dumps({"metric": "frames/sec through CapFilt (caption + filter)", "value": n_frames_all / (total / 1e3), "unit": "frames/s",
+                      "n_gpus": world, "ms_per_step": total, "steps": args.steps, "warmup": args.warmup, "gpu_launches": launches,
+                      "scaling": "strong", "gather": {"ms": gather_ms, "rows": len(merged), "collective": "all_gather of length-prefixed JSON rows"},
                       "stages_ms": {"captioner_vit": ms[0], "caption_beam_search": ms[1], "filterer_vit": ms[2], "itm_pairs": ms[3]},
-                      "caption_frames_per_s": n_frames / ((ms[0] + ms[1]) / 1e3),
-                      "captions_per_s_beam_search_only": n_frames / (ms[1] / 1e3), "cpu_baseline": cpu,
-                      "decode_rows": n_frames * 3, "itm_pairs": n_frames * Fv, "dtype": args.dtype, "data": "synthetic",
-                      "config": {"workload": f"{V} synthetic videos x 8 frames @{args.image_size}, BLIP ViT-{args.vit[0].upper()}/16 + "
+                      "caption_frames_per_s": n_frames_all / ((ms[0] + ms[1]) / 1e3),
+                      "captions_per_s_beam_search_only": n_frames_all / (ms[1] / 1e3), "cpu_baseline": cpu,
+                      "decode_rows_per_rank": n_frames * 3, "itm_pairs_per_rank": n_frames * Fv, "dtype": args.dtype, "data": "synthetic",
+                      "config": {"workload": f"{args.videos} synthetic videos x 8 frames @{args.image_size}, BLIP ViT-{args.vit[0].upper()}/16 + "
                                  f"med.py decoder (beam 3, max_length 20, min_length 5) + BLIP_ITM filter over {n_frames * Fv} "
-                                 f"(caption, frame) pairs x 35 tokens; {tokens} image tokens per frame"}}), flush=True)
+                                 f"(caption, frame) pairs x 35 tokens per rank; {tokens} image tokens per frame; videos sharded over "
+                                 f"{world} rank(s)"}}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
 
 
 def main():
