@@ -105,3 +105,41 @@ def test_generate_runs_cached_and_uncached_identically():
     assert toks == toks2
     assert np.allclose(scores, scores2, atol=1e-5)
     assert all(t[:4] == sp["prompt"] for t in toks)
+
+
+def test_beam_search_single_beam_is_greedy_and_scores_are_consistent():
+    """Independent checks of the restated search: with one beam it is greedy decoding (arg-max of the admissible log-probs each
+    step, stop at eos), and for any beam count the returned score is the sum of the returned tokens' log-probs divided by the
+    hypothesis length (eos excluded from the length, included in the sum), recomputed here from the logits tables."""
+    V, eos, prompt, max_length, min_length = 40, 3, [7, 8], 12, 4
+    rng = np.random.default_rng(5)
+    for K in (1, 2, 3):
+        S = max_length - len(prompt)
+        L = [rng.standard_normal((2 * K, V)).astype(np.float32) * 3 for _ in range(S)]
+        for l in L:
+            l[:, eos] += 1.5
+        # tables that depend on the step only (rows identical across beams), so that a sequence's log-prob is path-independent
+        L = [np.tile(l[:1], (2 * K, 1)) for l in L]
+        it = iter(L)
+        toks, scores, _ = med_oracle.beam_search_from_logits(lambda ids, bi: next(it), 2, prompt, K, max_length, min_length, eos, 0)
+        lp = [torch.log_softmax(torch.from_numpy(l[0]), -1).numpy() for l in L]
+        for t, s in zip(toks, scores):
+            gen = t[len(prompt):]
+            total = sum(float(lp[i][tok]) for i, tok in enumerate(gen))
+            if t[-1] == eos:
+                assert abs(s - total / (len(t) - 1)) < 1e-5
+            else:
+                assert len(t) == max_length and abs(s - total / len(t)) < 1e-5
+            assert eos not in t[:min_length]                                  # MinLengthLogitsProcessor
+        if K == 1:
+            greedy = list(prompt)
+            for i in range(S):
+                row = lp[i].copy()
+                if len(greedy) < min_length:
+                    row[eos] = -np.inf
+                nxt = int(np.argmax(row))
+                if nxt == eos:
+                    break
+                greedy.append(nxt)
+            expect = greedy + ([eos] if len(greedy) < max_length else [])
+            assert toks[0] == expect and toks[1] == expect
