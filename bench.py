@@ -12,6 +12,7 @@ One step = one 256-frame batch through vidil_vit_forward.  Prints ONE JSON line 
             and step k-1's D2H overlapping step k's forward
   roofline  the tcgen05 GEMM kernel: algorithmic FLOPs / its event-timed device time inside the timed steps
   cpu_baseline  the oracle port of models/vit.py timed on this box's host cores (rank 0, N=1 only)
+  reference_ops_on_gpu  the same restatement run by PyTorch eager on the GPU (TF32 and bf16 autocast): the honest second baseline
 Other workloads (not the driver's line): --workload clip | sim | text | tokenize | capfilt.
 """
 from __future__ import annotations
@@ -340,9 +341,43 @@ def run_vit(args):
         line["cpu_baseline"] = {"value": fps_cpu, "unit": "frames/s", "cores": cores, "kind": "port",
                                 "sample": f"8-frame batches x {done} (1 warm-up) of the same workload through "
                                           f"oracle/vit_oracle.py (fp32 restatement of models/vit.py), {cores} torch threads"}
+        # the reference's own op sequence (the fp32 restatement of models/vit.py: Conv2d, nn.Linear, materialised
+        # softmax attention, nn.GELU, nn.LayerNorm) run by PyTorch eager on this same GPU — not a product path, a second baseline
+        line["reference_ops_on_gpu"] = torch_eager_on_gpu(args.vit, args.image_size, args.batch, dev)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def torch_eager_on_gpu(vit, image_size, batch, dev, iters=5):
+    """frames/s of oracle/vit_oracle.vit_forward on CUDA tensors: fp32 with TF32 matmuls (cudnn.benchmark / allow_tf32 as the
+    reference sets them, run_video_CapFilt.py:234) and under bf16 autocast.  Bounded: 2 warm-up + `iters` timed batches each."""
+    import torch
+
+    from oracle import vit_oracle, weights as W
+    _, _, heads = VIT[vit]
+    sd = {k: v.to(dev) for k, v in W.vit_state_dict(vit, image_size, seed=0).items()}
+    x = torch.randn(batch, 3, image_size, image_size, device=dev)
+    out = {"what": "oracle/vit_oracle.py (same ATen ops as models/vit.py) on this GPU through PyTorch eager, batch %d" % batch}
+    old = torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = True
+    try:
+        for key, ctx in (("fp32_tf32_frames_per_s", torch.autocast("cuda", enabled=False)),
+                         ("bf16_autocast_frames_per_s", torch.autocast("cuda", dtype=torch.bfloat16))):
+            with torch.no_grad(), ctx:
+                for _ in range(2):
+                    vit_oracle.vit_forward(sd, x, heads)
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    vit_oracle.vit_forward(sd, x, heads)
+                e1.record()
+                torch.cuda.synchronize()
+            out[key] = batch * iters / (e0.elapsed_time(e1) / 1e3)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+    return out
 
 
 def run_sim(args):
