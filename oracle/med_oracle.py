@@ -79,10 +79,10 @@ def self_mask(attention_mask: torch.Tensor, T: int, past_len: int, causal: bool)
     """get_extended_attention_mask, med.py:609-668: additive 0 / -10000 mask [B,1,T,past+T]."""
     am = attention_mask.to(torch.float32)
     if causal:
-        ids = torch.arange(T)
+        ids = torch.arange(T, device=am.device)
         cm = (ids[None, :] <= ids[:, None]).to(torch.float32)                                  # :636
         if past_len:
-            cm = torch.cat([torch.ones(T, past_len), cm], dim=-1)                              # :641-649
+            cm = torch.cat([torch.ones(T, past_len, device=am.device), cm], dim=-1)            # :641-649
         ext = cm[None, None] * am[:, None, None, :]                                            # :651
     else:
         ext = am[:, None, None, :]                                                             # :653
@@ -95,7 +95,7 @@ def bert_forward(sd: dict, pre: str, input_ids, attention_mask, enc, H: int, dep
     B, T = input_ids.shape
     past_len = 0 if past is None else past[0][0].shape[2]
     if attention_mask is None:
-        attention_mask = torch.ones(B, past_len + T)
+        attention_mask = torch.ones(B, past_len + T, device=input_ids.device)
     x = embeddings(sd, pre, input_ids, past_len, eps)
     m = self_mask(attention_mask, T, past_len, causal)
     presents = []
@@ -155,8 +155,16 @@ class _BeamHyps:
 
 
 def topk_candidates(scores: np.ndarray, k: int):
-    """torch.topk(largest, sorted) over the flattened [beams*V] row; equal scores are taken lowest index first."""
-    order = np.argsort(-scores, kind="stable")[:k]
+    """torch.topk(largest, sorted) over the flattened [beams*V] row; equal scores are taken lowest index first (what a stable
+    descending sort gives).  A partition finds the k-th value first so that the 90k-entry row is not fully sorted every step."""
+    if scores.size <= 8 * k:
+        order = np.argsort(-scores, kind="stable")[:k]
+        return scores[order], order
+    thr = np.partition(scores, scores.size - k)[scores.size - k]          # the k-th largest value
+    above = np.flatnonzero(scores > thr)
+    equal = np.flatnonzero(scores == thr)
+    cand = np.concatenate([above, equal[:k - above.size]])                # ties at the threshold: lowest indices
+    order = cand[np.argsort(-scores[cand], kind="stable")]
     return scores[order], order
 
 
@@ -230,23 +238,24 @@ def beam_search_from_logits(step_logits, batch: int, prompt: list, num_beams: in
 @torch.no_grad()
 def generate(sd: dict, image_embeds: torch.Tensor, prompt: list, H: int, depth: int, pre: str = "text_decoder.",
              num_beams: int = 3, max_length: int = 20, min_length: int = 5, eos: int = 102, pad: int = 0,
-             length_penalty: float = 1.0):
+             length_penalty: float = 1.0, device=None):
     """BLIP_Decoder.generate(sample=False), blip.py:127-167, from the image tokens on: repeat_interleave the image
     tokens over the beams (:130), run the cached decoder (prepare_inputs_for_generation / _reorder_cache, med.py:929-955)."""
     B = image_embeds.shape[0]
+    dev = image_embeds.device if device is None else device   # `device`: where sd / image_embeds live (bench.py's eager-GPU baseline)
     enc = image_embeds.repeat_interleave(num_beams, dim=0)
     state = {"past": None}
 
     def step(ids, beam_idx):
         past = state["past"]
         if past is None:
-            inp = torch.from_numpy(ids)
+            inp = torch.from_numpy(ids).to(dev)
         else:
-            idx = torch.from_numpy(beam_idx)
+            idx = torch.from_numpy(beam_idx).to(dev)
             past = [(k.index_select(0, idx), v.index_select(0, idx)) for k, v in past]
-            inp = torch.from_numpy(ids[:, -1:])
+            inp = torch.from_numpy(ids[:, -1:]).to(dev)
         logits, presents = decoder_logits(sd, pre, inp, enc, H, depth, past)
         state["past"] = presents
-        return logits[:, -1, :].numpy()
+        return logits[:, -1, :].float().cpu().numpy()
 
     return beam_search_from_logits(step, B, prompt, num_beams, max_length, min_length, eos, pad, length_penalty)
