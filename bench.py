@@ -652,6 +652,28 @@ def run_capfilt(args):
     launches = lib.launch_count() - before
     ms = [a / args.steps for a in acc]
     total = sum(ms)
+    # per-class device time of ONE more beam search with an event pair around every kernel (not part of the timed steps): the
+    # decode-step cross-attention is the dominant kernel and a pure K/V stream, so its roofline is HBM
+    native = cap.text_decoder.bert._ensure_packed()
+    native.set_profiling(True)
+    toks = torch.cat([cap.visual_encoder(frames[i:i + chunk]) for i in range(0, n_frames, chunk)])
+    ids = torch.tensor([cap._prompt_ids], dtype=torch.long).repeat(n_frames, 1)
+    ids[:, 0] = cap.bos_token_id
+    cap.text_decoder.generate(input_ids=ids[:, :-1], max_length=20, min_length=5, num_beams=3, eos_token_id=cap.sep_token_id,
+                              pad_token_id=cap.pad_token_id, encoder_hidden_states=toks)
+    prof = native.read_profile()
+    native.set_profiling(False)
+    del toks
+    peaks = measured_peaks()
+    xa = prof["attention"]
+    roofline = {"bound": "hbm", "kernel": "cross_decode_mma_kernel + the prompt's attention_x_kernel (cross-attention onto the image "
+                "tokens, one launch per layer and step)", "achieved": xa["bytes"] / (xa["ms"] / 1e3) / 1e9 if xa["ms"] else None,
+                "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": xa["bytes"] / (xa["ms"] / 1e3) / 1e9 / peaks["hbm_gbs"] if xa["ms"] else None,
+                "traffic": 624.4e6 if (args.vit == "large" and args.image_size == 224 and n_frames == 1024) else None,
+                "algorithmic_bytes_per_launch": xa["bytes"] / max(xa["launches"], 1), "launches": xa["launches"],
+                "peak_source": peaks["source"], "share_of_beam_search": xa["ms"] / max(sum(v["ms"] for v in prof.values()), 1e-9)}
+    classes = {k: {"ms": v["ms"], "launches": v["launches"], "tflops": v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] else 0.0,
+                   "gbs": v["bytes"] / (v["ms"] / 1e3) / 1e9 if v["ms"] else 0.0} for k, v in prof.items()}
     # the rows a rank contributes: video -> kept captions (token ids here: there is no vocabulary to decode with), then the one
     # collective of the path
     t0 = time.perf_counter()
@@ -692,6 +714,7 @@ def run_capfilt(args):
                       "stages_ms": {"captioner_vit": ms[0], "caption_beam_search": ms[1], "filterer_vit": ms[2], "itm_pairs": ms[3]},
                       "caption_frames_per_s": n_frames_all / ((ms[0] + ms[1]) / 1e3),
                       "captions_per_s_beam_search_only": n_frames_all / (ms[1] / 1e3), "cpu_baseline": cpu,
+                      "roofline": roofline, "beam_search_kernel_classes": classes,
                       "decode_rows_per_rank": n_frames * 3, "itm_pairs_per_rank": n_frames * Fv, "dtype": args.dtype, "data": "synthetic",
                       "config": {"workload": f"{args.videos} synthetic videos x 8 frames @{args.image_size}, BLIP ViT-{args.vit[0].upper()}/16 + "
                                  f"med.py decoder (beam 3, max_length 20, min_length 5) + BLIP_ITM filter over {n_frames * Fv} "

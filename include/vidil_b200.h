@@ -248,6 +248,11 @@ typedef struct vidil_kernel_stats {
 } vidil_kernel_stats;
 int32_t vidil_encoder_set_profiling(vidil_encoder* enc, int32_t enable);
 int32_t vidil_encoder_read_profile(vidil_encoder* enc, vidil_kernel_stats* out);
+/* The same for a text-stack handle.  Classes there: GEMM = every projection incl. the cross K/V and the vocabulary GEMM;
+ * ATTENTION = the cross-attention onto the image tokens (bytes = each query group's K and V tiles once + its q and out rows);
+ * LAYERNORM = the post-LayerNorm kernel; OTHER = text self-attention, vocabulary log-softmax/top-k. */
+int32_t vidil_med_set_profiling(vidil_med* med, int32_t enable);
+int32_t vidil_med_read_profile(vidil_med* med, vidil_kernel_stats* out);
 
 /* ---- similarity + top-k ----------------------------------------------------------------------- */
 /* img fp32 [F,D], bank fp32 [T,D] (device, D multiple of 64) -> out_scores fp32 [F,k], out_idx int32 [F,k]:

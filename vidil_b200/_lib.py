@@ -89,6 +89,8 @@ SIGNATURES = {
     "vidil_med_destroy": (None, [c_void_p]),
     "vidil_med_load": (c_int32, [c_void_p, c_char_p, c_void_p, c_int64, c_void_p]),
     "vidil_med_check_loaded": (c_int32, [c_void_p]),
+    "vidil_med_set_profiling": (c_int32, [c_void_p, c_int32]),
+    "vidil_med_read_profile": (c_int32, [c_void_p, POINTER(KernelStats)]),
     "vidil_med_forward_workspace_bytes": (c_size_t, [c_void_p, c_int32, c_int32, c_int32, c_int32]),
     "vidil_med_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32,
                                     c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -81,9 +81,26 @@ struct StackPlan {
 
 }  // namespace
 
+// Event-pair records of the launches enqueued while profiling is on (read back by vidil_med_read_profile).
+struct MedProfRec {
+    cudaEvent_t a, b;
+    int cls;
+    double flops, bytes;
+};
+
 struct vidil_med {
     vidil_med_cfg cfg;
     DType dt = DT_BF16;
+    bool profiling = false;
+    std::vector<MedProfRec> prof;
+    std::vector<cudaEvent_t> free_events;
+    ~vidil_med() {
+        for (auto& r : prof) {
+            cudaEventDestroy(r.a);
+            cudaEventDestroy(r.b);
+        }
+        for (auto ev : free_events) cudaEventDestroy(ev);
+    }
     MBuf word, pos, eln_w, eln_b;
     std::vector<std::unique_ptr<MedLayer>> layers;
     MBuf hd_w, hd_b, hln_w, hln_b, dec_w, dec_b, cls_w, cls_b;
@@ -172,6 +189,37 @@ GemmProblem make_gemm(const vidil_med* m, int epi, int M, int N, int K, const vo
     return g;
 }
 
+int med_event(vidil_med* m, cudaEvent_t* ev) {
+    if (!m->free_events.empty()) {
+        *ev = m->free_events.back();
+        m->free_events.pop_back();
+        return 0;
+    }
+    VIDIL_CUDA_OK(cudaEventCreate(ev));
+    return 0;
+}
+
+// Runs one launcher; with profiling on, brackets it with an event pair on the same stream (class: VIDIL_KCLASS_*; here
+// ATTENTION = cross-attention onto the image tokens, OTHER = self-attention, vocabulary scan, beam bookkeeping, embedding).
+template <typename Fn>
+int med_timed(const vidil_med* cm, cudaStream_t s, int cls, double flops, double bytes, Fn&& fn) {
+    vidil_med* m = const_cast<vidil_med*>(cm);
+    if (!m->profiling) return fn();
+    MedProfRec r{nullptr, nullptr, cls, flops, bytes};
+    if (med_event(m, &r.a) || med_event(m, &r.b)) return 1;
+    VIDIL_CUDA_OK(cudaEventRecord(r.a, s));
+    const int rc = fn();
+    VIDIL_CUDA_OK(cudaEventRecord(r.b, s));
+    m->prof.push_back(r);
+    return rc;
+}
+
+int gemm_timed(const vidil_med* m, cudaStream_t s, const GemmProblem& g) {
+    const double out = (g.epi == EPI_RESID) ? 8.0 : (g.epi == EPI_STORE_F32) ? 4.0 : 2.0;
+    return med_timed(m, s, VIDIL_KCLASS_GEMM, 2.0 * g.M * g.N * g.K, 2.0 * g.M * g.K + 2.0 * g.N * g.K + out * g.M * g.N,
+                     [&] { return gemm_run(g, s); });
+}
+
 void carve_stack(Carver& cv, const vidil_med* m, size_t rows, StackBufs& b) {
     const size_t D = m->cfg.hidden;
     b.resid = cv.take<float>(rows * D);
@@ -233,35 +281,45 @@ int run_stack(const vidil_med* m, const StackPlan& pl, const StackBufs& b, const
     const vidil_med_cfg& c = m->cfg;
     const int D = c.hidden, H = c.num_heads, rows = pl.rows;
     const float eps = c.ln_eps;
-    if (layernorm_post_run(b.resid, m->eln_w.f(), m->eln_b.f(), b.xn, m->dt, rows, D, eps, s)) return 1;
+    if (med_timed(m, s, VIDIL_KCLASS_LAYERNORM, 0.0, 10.0 * rows * D, [&] { return layernorm_post_run(b.resid, m->eln_w.f(), m->eln_b.f(), b.xn, m->dt, rows, D, eps, s); })) return 1;
     for (int i = 0; i < c.depth; ++i) {
         const MedLayer& ly = *m->layers[i];
-        if (gemm_run(pl.sqkv[i], s)) return 1;
+        if (gemm_timed(m, s, pl.sqkv[i])) return 1;
         uint8_t* cache_l = a.cache ? reinterpret_cast<uint8_t*>(a.cache) + static_cast<size_t>(i) * a.cache_layer_elems * 2 : nullptr;
         const uint8_t* qkv8 = reinterpret_cast<const uint8_t*>(b.qkv);
         if (a.mode == MED_ATTN_DECODE) {
-            if (med_self_attn_decode_run(b.qkv, cache_l, a.anc, b.attn, m->dt, rows, H, a.pos, a.Tmax, 0.125f, s)) return 1;
+            if (med_timed(m, s, VIDIL_KCLASS_OTHER, 0.0, 0.0, [&] {
+                    return med_self_attn_decode_run(b.qkv, cache_l, a.anc, b.attn, m->dt, rows, H, a.pos, a.Tmax, 0.125f, s);
+                }))
+                return 1;
         } else {
-            if (attention_x_run(b.qkv, 3 * D, qkv8 + static_cast<size_t>(D) * 2, qkv8 + static_cast<size_t>(2 * D) * 2, 3 * D, nullptr,
-                                a.mask, b.attn, D, m->dt, rows / a.T_seq, a.T_seq, a.T_seq, H, a.mode == MED_ATTN_CAUSAL, 0.125f, s))
+            if (med_timed(m, s, VIDIL_KCLASS_OTHER, 4.0 * rows * a.T_seq * D, 0.0, [&] {
+                    return attention_x_run(b.qkv, 3 * D, qkv8 + static_cast<size_t>(D) * 2, qkv8 + static_cast<size_t>(2 * D) * 2, 3 * D,
+                                           nullptr, a.mask, b.attn, D, m->dt, rows / a.T_seq, a.T_seq, a.T_seq, H,
+                                           a.mode == MED_ATTN_CAUSAL, 0.125f, s);
+                }))
                 return 1;
             if (cache_l && med_cache_fill_run(b.qkv, cache_l, m->dt, rows, a.T_seq, D, a.Tmax, a.beams, s)) return 1;
         }
-        if (gemm_run(pl.so[i], s)) return 1;
-        if (layernorm_post_run(b.resid, ly.sln_w.f(), ly.sln_b.f(), b.xn, m->dt, rows, D, eps, s)) return 1;
-        if (gemm_run(pl.cq[i], s)) return 1;
+        if (gemm_timed(m, s, pl.so[i])) return 1;
+        if (med_timed(m, s, VIDIL_KCLASS_LAYERNORM, 0.0, 10.0 * rows * D, [&] { return layernorm_post_run(b.resid, ly.sln_w.f(), ly.sln_b.f(), b.xn, m->dt, rows, D, eps, s); })) return 1;
+        if (gemm_timed(m, s, pl.cq[i])) return 1;
         const void* kv_l = reinterpret_cast<const uint8_t*>(a.cross_kv) + static_cast<size_t>(i) * a.cross_layer_elems * 2;
-        if (a.mode == MED_ATTN_DECODE && a.frame_of_group == nullptr) {
-            if (med_cross_attn_decode_run(a.kv_map, i, b.qc, kv_l, b.attn, m->dt, a.groups, a.nq, a.Nv, H, 0.125f, s)) return 1;
-        } else if (attention_x_run(b.qc, D, kv_l, reinterpret_cast<const uint8_t*>(kv_l) + static_cast<size_t>(D) * 2, 2 * D,
-                                   a.frame_of_group, nullptr, b.attn, D, m->dt, a.groups, a.nq, a.Nv, H, false, 0.125f, s)) {
+        // algorithmic bytes of the cross-attention: each group's K and V tiles once (2 * Nv * 64 * 2 B per head) + q and out rows
+        const double x_bytes = static_cast<double>(a.groups) * H * (2.0 * a.Nv * 128 + 2.0 * a.nq * 128);
+        const double x_flops = 4.0 * a.groups * a.nq * static_cast<double>(a.Nv) * D;
+        if (med_timed(m, s, VIDIL_KCLASS_ATTENTION, x_flops, x_bytes, [&] {
+                if (a.mode == MED_ATTN_DECODE && a.frame_of_group == nullptr)
+                    return med_cross_attn_decode_run(a.kv_map, i, b.qc, kv_l, b.attn, m->dt, a.groups, a.nq, a.Nv, H, 0.125f, s);
+                return attention_x_run(b.qc, D, kv_l, reinterpret_cast<const uint8_t*>(kv_l) + static_cast<size_t>(D) * 2, 2 * D,
+                                       a.frame_of_group, nullptr, b.attn, D, m->dt, a.groups, a.nq, a.Nv, H, false, 0.125f, s);
+            }))
             return 1;
-        }
-        if (gemm_run(pl.co[i], s)) return 1;
-        if (layernorm_post_run(b.resid, ly.cln_w.f(), ly.cln_b.f(), b.xn, m->dt, rows, D, eps, s)) return 1;
-        if (gemm_run(pl.fc1[i], s)) return 1;
-        if (gemm_run(pl.fc2[i], s)) return 1;
-        if (layernorm_post_run(b.resid, ly.fln_w.f(), ly.fln_b.f(), b.xn, m->dt, rows, D, eps, s)) return 1;
+        if (gemm_timed(m, s, pl.co[i])) return 1;
+        if (med_timed(m, s, VIDIL_KCLASS_LAYERNORM, 0.0, 10.0 * rows * D, [&] { return layernorm_post_run(b.resid, ly.cln_w.f(), ly.cln_b.f(), b.xn, m->dt, rows, D, eps, s); })) return 1;
+        if (gemm_timed(m, s, pl.fc1[i])) return 1;
+        if (gemm_timed(m, s, pl.fc2[i])) return 1;
+        if (med_timed(m, s, VIDIL_KCLASS_LAYERNORM, 0.0, 10.0 * rows * D, [&] { return layernorm_post_run(b.resid, ly.fln_w.f(), ly.fln_b.f(), b.xn, m->dt, rows, D, eps, s); })) return 1;
     }
     return 0;
 }
@@ -276,7 +334,7 @@ int run_cross_kv(const vidil_med* m, const float* image_embeds, int F, int Nv, v
         const MedLayer& ly = *m->layers[i];
         void* out = reinterpret_cast<uint8_t*>(ckv) + static_cast<size_t>(i) * Mi * 2 * D * 2;
         GemmProblem g = make_gemm(m, EPI_STORE, static_cast<int>(Mi), 2 * D, E, img16, E, ly.ckv_w, &ly.ckv_b, out, 2 * D);
-        if (gemm_prepare(g) || gemm_run(g, s)) return 1;
+        if (gemm_prepare(g) || gemm_timed(m, s, g)) return 1;
     }
     return 0;
 }
@@ -286,10 +344,10 @@ int run_lm_head(const vidil_med* m, const void* A, int64_t lda, int M, void* hea
     const vidil_med_cfg& c = m->cfg;
     const int D = c.hidden, V = c.vocab_size;
     GemmProblem t = make_gemm(m, EPI_GELU, M, D, D, A, lda, m->hd_w, &m->hd_b, head_t, D);
-    if (gemm_prepare(t) || gemm_run(t, s)) return 1;
+    if (gemm_prepare(t) || gemm_timed(m, s, t)) return 1;
     if (layernorm16_run(head_t, m->hln_w.f(), m->hln_b.f(), head_ln, m->dt, M, D, c.ln_eps, s)) return 1;
     GemmProblem d = make_gemm(m, EPI_STORE_F32, M, V, D, head_ln, D, m->dec_w, &m->dec_b, logits, V);
-    if (gemm_prepare(d) || gemm_run(d, s)) return 1;
+    if (gemm_prepare(d) || gemm_timed(m, s, d)) return 1;
     return 0;
 }
 
@@ -476,6 +534,36 @@ int32_t vidil_med_check_loaded(const vidil_med* med) {
     return 0;
 }
 
+int32_t vidil_med_set_profiling(vidil_med* med, int32_t enable) {
+    if (med == nullptr) {
+        set_error("null handle");
+        return 1;
+    }
+    med->profiling = enable != 0;
+    return 0;
+}
+
+int32_t vidil_med_read_profile(vidil_med* med, vidil_kernel_stats* out) {
+    if (med == nullptr || out == nullptr) {
+        set_error("vidil_med_read_profile: null argument");
+        return 1;
+    }
+    memset(out, 0, sizeof(*out));
+    for (auto& r : med->prof) {
+        VIDIL_CUDA_OK(cudaEventSynchronize(r.b));
+        float ms = 0.f;
+        VIDIL_CUDA_OK(cudaEventElapsedTime(&ms, r.a, r.b));
+        out->ms[r.cls] += ms;
+        out->flops[r.cls] += r.flops;
+        out->bytes[r.cls] += r.bytes;
+        out->launches[r.cls] += 1;
+        med->free_events.push_back(r.a);
+        med->free_events.push_back(r.b);
+    }
+    med->prof.clear();
+    return 0;
+}
+
 size_t vidil_med_forward_workspace_bytes(const vidil_med* med, int32_t n_seq, int32_t seq_len, int32_t n_frames, int32_t n_img_tokens) {
     if (med == nullptr || n_seq <= 0 || seq_len <= 0 || n_frames <= 0 || n_img_tokens <= 0) return 0;
     return forward_ws(med, nullptr, n_seq, seq_len, n_frames, n_img_tokens).total;
@@ -630,8 +718,10 @@ int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_
             if (med_embed_run(st.cur_tok, med->word.f(), med->pos.f(), w.b.resid, R, 1, cur_len - 1, 0, D, V, c.max_positions, s)) return 1;
             if (run_stack(med, pl, w.b, a, s)) return 1;
             if (run_lm_head(med, w.b.xn, D, R, w.head_t, w.head_ln, w.logits, s)) return 1;
-            if (med_logits_topk_run(w.logits, V, 1, st.beam_scores, R, V, nc, cur_len < min_length ? eos_token : -1, w.beam.cand_score,
-                                    w.beam.cand_tok, s))
+            if (med_timed(med, s, VIDIL_KCLASS_OTHER, 0.0, 4.0 * R * V, [&] {
+                    return med_logits_topk_run(w.logits, V, 1, st.beam_scores, R, V, nc, cur_len < min_length ? eos_token : -1,
+                                               w.beam.cand_score, w.beam.cand_tok, s);
+                }))
                 return 1;
             if (med_beam_step_run(st, w.beam.cand_score, w.beam.cand_tok, K, nc, V, cur_len, parity, s)) return 1;
             parity ^= 1;

@@ -157,6 +157,16 @@ class NativeMed:
         st = self.lib.vidil_med_load(self.handle, name.encode(), t.data_ptr(), t.numel(), torch.cuda.current_stream().cuda_stream)
         _lib.check(st, f"vidil_med_load({name})")
 
+    def set_profiling(self, enable: bool) -> None:
+        _lib.check(self.lib.vidil_med_set_profiling(self.handle, int(enable)), "vidil_med_set_profiling")
+
+    def read_profile(self) -> dict:
+        """{class: {ms, flops, bytes, launches}} of the kernels enqueued since the last read (synchronises)."""
+        st = _lib.KernelStats()
+        _lib.check(self.lib.vidil_med_read_profile(self.handle, ctypes.byref(st)), "vidil_med_read_profile")
+        return {name: dict(ms=st.ms[i], flops=st.flops[i], bytes=st.bytes[i], launches=int(st.launches[i]))
+                for i, name in enumerate(_lib.KCLASSES)}
+
     def workspace(self, need: int, device) -> torch.Tensor:
         if self._ws is None or self._ws.numel() < need or self._ws.device != device:
             buf = torch.empty(need + 1024, dtype=torch.uint8, device=device)
