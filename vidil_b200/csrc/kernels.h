@@ -214,8 +214,8 @@ int cross_decode_mma_chunk_rows();
 int cross_decode_mma_run(const CUtensorMap& kv_map_sw128, int row0, const void* q, void* out, DType dt, int F, int nq, int Nv, int H,
                          float scale, cudaStream_t stream);
 int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, int Nv, int H);
-int med_cross_attn_decode_run(const CrossKvMap* map, int layer, const void* q, const void* kv, void* out, DType dt, int F, int nq,
-                              int Nv, int H, float scale, cudaStream_t s);
+int med_cross_attn_decode_run(const CrossKvMap* map, int layer, const void* q, void* out, DType dt, int F, int nq, int Nv, int H,
+                              float scale, cudaStream_t s);
 // K/V of whole sequences, qkv [n_seq*T_seq, 3D] -> cache slots (seq*beams, t)
 int med_cache_fill_run(const void* qkv, void* cache, DType dt, int64_t n_rows, int T_seq, int D, int Tmax, int beams, cudaStream_t s);
 // list l scans logits row l*row_mul: log_softmax, ban_token excluded (-1: none), + beam_scores[l] -> nc best (score, token)

@@ -173,123 +173,6 @@ __global__ void __launch_bounds__(SA_WARPS * 32)
     }
 }
 
-// ---------------------------------------------------------------------------------------------------------------------
-// Decode-step cross-attention, register-load version: the NQ beams of frame f (rows f*NQ .. f*NQ+NQ-1 of q [rows, D]) attend to the
-// frame's Nv image tokens, kv [F, Nv, 2D].  One CTA per (head, frame) streams the frame's K rows, then its V rows, exactly once
-// with 16-byte loads (8 lanes per 128-byte row, 4 rows in flight per thread).  This is the path taken when no tensor map can be
-// encoded for the K/V buffer; the TMA-fed mma.sync kernels of attention.cu (cross_decode_mma_*) are the normal route: they keep
-// 50 KB instead of 8 KB per CTA in flight (194 -> 112 us per layer-step at 1024 frames x 197 tokens).
-// ---------------------------------------------------------------------------------------------------------------------
-constexpr int CD_THREADS = 128;
-
-template <typename T, int NQ>
-__global__ void __launch_bounds__(CD_THREADS)
-    med_cross_attn_decode_kernel(const T* __restrict__ q, const T* __restrict__ kv, T* __restrict__ out, int Nv, int H, float scale) {
-    extern __shared__ float smem[];
-    float* s_s = smem;                                   // [NQ][Nv]
-    float* red = smem + static_cast<size_t>(NQ) * Nv;    // [4 warps][NQ][64]
-    const int h = blockIdx.x, f = blockIdx.y;
-    const int D = H * 64;
-    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-    const int c = t & 7, kl = t >> 3;                    // 16-byte chunk of the row, key lane 0..15
-    float qv[NQ][8];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i) {
-        load8<T>(q + (static_cast<int64_t>(f) * NQ + i) * D + h * 64 + c * 8, qv[i]);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) qv[i][e] *= scale;
-    }
-    const T* kbase = kv + static_cast<int64_t>(f) * Nv * (2 * D) + h * 64 + c * 8;
-    constexpr int U = 4;
-    for (int jb = 0; jb < Nv; jb += 16 * U) {   // warp-uniform trip count: the shuffles below need every lane
-        const int j0 = jb + kl;
-        float k8[U][8];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int j = j0 + 16 * u;
-            load8<T>(kbase + static_cast<int64_t>(j < Nv ? j : Nv - 1) * (2 * D), k8[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int j = j0 + 16 * u;
-#pragma unroll
-            for (int i = 0; i < NQ; ++i) {
-                float d = 0.f;
-#pragma unroll
-                for (int e = 0; e < 8; ++e) d += qv[i][e] * k8[u][e];
-                d += __shfl_xor_sync(0xffffffffu, d, 1);
-                d += __shfl_xor_sync(0xffffffffu, d, 2);
-                d += __shfl_xor_sync(0xffffffffu, d, 4);
-                if (c == 0 && j < Nv) s_s[i * Nv + j] = d;
-            }
-        }
-    }
-    __syncthreads();
-    if (w < NQ) {
-        float* row = s_s + w * Nv;
-        float mx = -INFINITY;
-        for (int j = lane; j < Nv; j += 32) mx = fmaxf(mx, row[j]);
-        mx = warp_max(mx);
-        float sum = 0.f;
-        for (int j = lane; j < Nv; j += 32) {
-            const float e = __expf(row[j] - mx);
-            row[j] = e;
-            sum += e;
-        }
-        const float inv = 1.0f / warp_sum(sum);
-        for (int j = lane; j < Nv; j += 32) row[j] *= inv;
-    }
-    __syncthreads();
-    float acc[NQ][8];
-#pragma unroll
-    for (int i = 0; i < NQ; ++i)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) acc[i][e] = 0.f;
-    const T* vbase = kbase + D;
-    for (int j0 = kl; j0 < Nv; j0 += 16 * U) {
-        float v8[U][8];
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int j = j0 + 16 * u;
-            if (j < Nv) load8<T>(vbase + static_cast<int64_t>(j) * (2 * D), v8[u]);
-        }
-#pragma unroll
-        for (int u = 0; u < U; ++u) {
-            const int j = j0 + 16 * u;
-            if (j < Nv) {
-#pragma unroll
-                for (int i = 0; i < NQ; ++i) {
-                    const float p = s_s[i * Nv + j];
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) acc[i][e] += p * v8[u][e];
-                }
-            }
-        }
-    }
-    // lanes c + 8*{0..3} of a warp hold partial sums of the same dims
-#pragma unroll
-    for (int i = 0; i < NQ; ++i)
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float x = acc[i][e];
-            x += __shfl_xor_sync(0xffffffffu, x, 8);
-            x += __shfl_xor_sync(0xffffffffu, x, 16);
-            acc[i][e] = x;
-        }
-    if (lane < 8) {
-#pragma unroll
-        for (int i = 0; i < NQ; ++i)
-#pragma unroll
-            for (int e = 0; e < 8; ++e) red[(w * NQ + i) * 64 + c * 8 + e] = acc[i][e];
-    }
-    __syncthreads();
-    for (int i = t; i < NQ * 64; i += CD_THREADS) {
-        const int qi = i >> 6, d = i & 63;
-        const float x = red[(0 * NQ + qi) * 64 + d] + red[(1 * NQ + qi) * 64 + d] + red[(2 * NQ + qi) * 64 + d] + red[(3 * NQ + qi) * 64 + d];
-        out[(static_cast<int64_t>(f) * NQ + qi) * D + h * 64 + d] = from_f<T>(x);
-    }
-}
-
 // K/V of whole sequences (the prompt) -> cache slots (seq * beams, t): the decode steps of every beam of a frame start from
 // the same prompt prefix.  qkv [n_seq*T, 3D]; one thread per 16 bytes.
 template <typename T>
@@ -731,18 +614,6 @@ int med_self_attn_decode_run(const void* qkv, void* cache, const int32_t* anc, v
     return 0;
 }
 
-template <typename T, int NQ>
-int launch_cross_decode(const void* q, const void* kv, void* out, int F, int Nv, int H, float scale, cudaStream_t s) {
-    const size_t smem = (static_cast<size_t>(NQ) * Nv + 4 * NQ * 64) * sizeof(float);
-    auto k = med_cross_attn_decode_kernel<T, NQ>;
-    if (smem > 48 * 1024) VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    k<<<dim3(H, F), CD_THREADS, smem, s>>>(reinterpret_cast<const T*>(q), reinterpret_cast<const T*>(kv), reinterpret_cast<T*>(out), Nv, H,
-                                           scale);
-    VIDIL_CUDA_OK(cudaGetLastError());
-    count_launches(1);
-    return 0;
-}
-
 int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, int Nv, int H) {
     typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                       const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -757,7 +628,11 @@ int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, i
     m.valid = false;
     m.F = F; m.Nv = Nv; m.H = H;
     const int64_t rows = static_cast<int64_t>(depth) * F * Nv;
-    if (fn == nullptr || rows > 0x7fffffffLL) return 0;   // the register-load kernel serves these cases
+    if (fn == nullptr || rows > 0x7fffffffLL) {
+        set_error("decode cross-attention: cuTensorMapEncodeTiled unavailable or %lld K/V rows exceed the tensor-map coordinate range",
+                  static_cast<long long>(rows));
+        return 1;
+    }
     const cuuint64_t dims[2] = {static_cast<cuuint64_t>(2 * H * 64), static_cast<cuuint64_t>(rows)};
     const cuuint64_t strides[1] = {static_cast<cuuint64_t>(2 * H * 64) * 2};
     const cuuint32_t box[2] = {64, static_cast<cuuint32_t>(Nv <= 256 ? Nv : cross_decode_mma_chunk_rows())};
@@ -772,27 +647,18 @@ int med_cross_kv_map_prepare(CrossKvMap& m, const void* ckv, int depth, int F, i
     return 0;
 }
 
-int med_cross_attn_decode_run(const CrossKvMap* map, int layer, const void* q, const void* kv, void* out, DType dt, int F, int nq,
-                              int Nv, int H, float scale, cudaStream_t s) {
+int med_cross_attn_decode_run(const CrossKvMap* map, int layer, const void* q, void* out, DType dt, int F, int nq, int Nv, int H,
+                              float scale, cudaStream_t s) {
     if (F <= 0) return 0;
-    if (nq < 1 || nq > 4 || Nv > 8192 || F > 65535) {
-        set_error("med decode cross-attention: %d beams (1..4), %d image tokens (<= 8192), %d frames (<= 65535)", nq, Nv, F);
+    if (nq < 1 || nq > 4 || F > 65535) {
+        set_error("med decode cross-attention: %d beams (1..4), %d frames (<= 65535)", nq, F);
         return 1;
     }
-    if (map != nullptr && map->valid && map->F == F && map->Nv == Nv && map->H == H)
-        return cross_decode_mma_run(map->map, layer * F * Nv, q, out, dt, F, nq, Nv, H, scale, s);
-#define VIDIL_CD(NQ)                                                                                     \
-    case NQ:                                                                                             \
-        return dt == DT_BF16 ? launch_cross_decode<__nv_bfloat16, NQ>(q, kv, out, F, Nv, H, scale, s)    \
-                             : launch_cross_decode<__half, NQ>(q, kv, out, F, Nv, H, scale, s);
-    switch (nq) {
-        VIDIL_CD(1)
-        VIDIL_CD(2)
-        VIDIL_CD(3)
-        VIDIL_CD(4)
+    if (map == nullptr || !map->valid || map->F != F || map->Nv != Nv || map->H != H) {
+        set_error("med decode cross-attention: no tensor map prepared for %d frames x %d image tokens x %d heads", F, Nv, H);
+        return 1;
     }
-#undef VIDIL_CD
-    return 1;
+    return cross_decode_mma_run(map->map, layer * F * Nv, q, out, dt, F, nq, Nv, H, scale, s);
 }
 
 int med_cache_fill_run(const void* qkv, void* cache, DType dt, int64_t n_rows, int T_seq, int D, int Tmax, int beams, cudaStream_t s) {

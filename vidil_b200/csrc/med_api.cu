@@ -310,7 +310,7 @@ int run_stack(const vidil_med* m, const StackPlan& pl, const StackBufs& b, const
         const double x_flops = 4.0 * a.groups * a.nq * static_cast<double>(a.Nv) * D;
         if (med_timed(m, s, VIDIL_KCLASS_ATTENTION, x_flops, x_bytes, [&] {
                 if (a.mode == MED_ATTN_DECODE && a.frame_of_group == nullptr)
-                    return med_cross_attn_decode_run(a.kv_map, i, b.qc, kv_l, b.attn, m->dt, a.groups, a.nq, a.Nv, H, 0.125f, s);
+                    return med_cross_attn_decode_run(a.kv_map, i, b.qc, b.attn, m->dt, a.groups, a.nq, a.Nv, H, 0.125f, s);
                 return attention_x_run(b.qc, D, kv_l, reinterpret_cast<const uint8_t*>(kv_l) + static_cast<size_t>(D) * 2, 2 * D,
                                        a.frame_of_group, nullptr, b.attn, D, m->dt, a.groups, a.nq, a.Nv, H, false, 0.125f, s);
             }))
