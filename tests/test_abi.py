@@ -75,3 +75,40 @@ def test_bad_configurations_are_rejected_with_a_message():
         cfg = _lib.EncoderCfg(**base)
         assert lib.vidil_encoder_create(ctypes.byref(cfg), ctypes.byref(h)) != 0
         assert _lib.last_error()
+
+
+def _med_cfg(**kw):
+    base = dict(vocab_size=30524, max_positions=512, hidden=768, depth=12, num_heads=12, mlp_dim=3072, encoder_width=1024,
+                ln_eps=1e-12, lm_head=1, cls_out=0, dtype=0, cta_group=0)
+    base.update(kw)
+    return _lib.MedCfg(**base)
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
+def test_text_stack_entry_points_fail_loudly_without_a_gpu():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    cfg = _med_cfg()
+    assert lib.vidil_med_create(ctypes.byref(cfg), ctypes.byref(h)) != 0 and not h
+    assert len(_lib.last_error()) > 0
+    assert lib.vidil_med_generate(None, None, 1, 1, None, 4, 3, 20, 5, 102, 0, 1.0, None, None, None, None, 0, None) != 0
+    assert lib.vidil_med_forward(None, None, 1, 1, None, None, None, 0, 1, 8, 1, None, None, None, None, 0, None) != 0
+    buf = (ctypes.c_float * 64)()
+    prompt = (ctypes.c_int32 * 4)(1, 2, 3, 4)
+    # argument checks come first and name the offending values
+    assert lib.vidil_op_beam_search(buf, 3, 1, 9, 8, ctypes.cast(prompt, ctypes.c_void_p), 4, 7, 0, 1, 0, 1.0, buf, buf, buf, buf, 64,
+                                    None) != 0
+    assert "num_beams" in _lib.last_error()
+    # workspace queries are pure arithmetic and work without a device
+    assert lib.vidil_op_beam_search_workspace_bytes(1024, 3, 20) > 1024 * 3 * 20 * 4
+    assert lib.vidil_med_generate_workspace_bytes(None, 8, 197, 3, 20, 4) == 0
+
+
+def test_text_stack_bad_configurations_are_rejected_with_a_message():
+    lib = _lib.load()
+    h = ctypes.c_void_p()
+    for kw in [dict(vocab_size=30523), dict(hidden=700), dict(num_heads=8), dict(encoder_width=1000), dict(mlp_dim=3000), dict(dtype=5),
+               dict(cls_out=-1), dict(depth=0), dict(cta_group=4)]:
+        cfg = _med_cfg(**kw)
+        assert lib.vidil_med_create(ctypes.byref(cfg), ctypes.byref(h)) != 0, kw
+        assert _lib.last_error(), kw
