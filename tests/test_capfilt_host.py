@@ -211,3 +211,18 @@ def test_capfilt_run_world2_equals_single_process(tmp_path):
         assert got == ref and list(got) == list(ref)
         assert open(tmp_path / "two" / name).read() == json.dumps(ref, indent=4)
     assert "video3" not in single[1] and len(single[1]) == 6
+
+
+def test_filter_captions_batched_is_ragged_safe():
+    """Any number of captions (zero included) and frames per video: the one-call version equals per-video filter_captions."""
+    rng = np.random.default_rng(3)
+    f = FakeFilterer()
+    for trial in range(20):
+        n_videos = int(rng.integers(1, 6))
+        images = [torch.from_numpy(rng.standard_normal((int(rng.integers(1, 6)), 3, 4, 4)).astype(np.float32)) * 0.4
+                  for _ in range(n_videos)]
+        texts = [[f"{WORDS[int(rng.integers(0, len(WORDS)))]} v{v} c{c}" for c in range(int(rng.integers(0, 5)))] for v in range(n_videos)]
+        for mode, thr in (("max_filter", 0.5), ("avg_filter", 0.45)):
+            got = capfilt.filter_captions_batched(f, images, texts, thr, mode)
+            assert got == [capfilt.filter_captions(f, im, tx, thr, mode) for im, tx in zip(images, texts)]
+    assert capfilt.filter_captions_batched(f, [torch.zeros(2, 3, 4, 4)], [[]], 0.5) == [[]]
