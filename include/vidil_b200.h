@@ -116,7 +116,10 @@ int32_t vidil_clip_forward_host(vidil_encoder* enc, const float* frames_host, in
  * slot's result is in out_host.  Submitting batch k+1 to the other slot before waiting for batch k overlaps its
  * H2D with batch k's forward and batch k's D2H with batch k+1's forward.  The handle decides which forward runs
  * (vit: tokens, clip: image_embeds).  dev_scratch: vidil_encoder_host_pipeline_scratch_bytes(enc, batch) bytes,
- * the same pointer for both slots.  The caller must not touch a slot's host buffers between submit and wait. */
+ * the same pointer for both slots.  The slot offsets inside dev_scratch are fixed by the batch of the call that first
+ * binds a (pointer, size) pair: later calls with a smaller batch (the ragged last batch of a stream) reuse them; a
+ * call with a different scratch or a larger batch first waits for everything in flight, then re-binds.  The caller
+ * must not touch a slot's host buffers between submit and wait, nor free dev_scratch before both slots are waited. */
 size_t  vidil_encoder_host_pipeline_scratch_bytes(const vidil_encoder* enc, int32_t batch);
 int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_host,
                                   int32_t slot, void* dev_scratch, size_t dev_scratch_bytes, void* stream);

@@ -172,6 +172,45 @@ def test_vit_identity_cache_for_the_caption_filter_loop(cuda):
     _check(c.cpu(), vit_oracle.vit_forward(W.vit_state_dict("tiny", 32, seed=3), y.cpu(), 2), "fp16")
 
 
+def test_vit_identity_cache_survives_free_and_reallocate(cuda):
+    """Half-precision (or non-contiguous) frames are converted before the kernels see them.  The cache key is the ORIGINAL
+    tensor's address + version, so the original must be what the cache pins: if only the converted copy were kept alive, the
+    caching allocator would hand the freed address (version 0 again) to the next video's frames and the cache would return
+    the previous video's tokens.  Each 'video' below is a fresh fp16 tensor allocated right after the last one was freed."""
+    m, sd = _build("tiny", 32, "fp16", cuda)
+    m.cache_identical_inputs = True
+    seen_ptrs = set()
+    for video in range(6):
+        x32 = W.frames(4, 32, seed=100 + video)
+        x = x32.to(cuda).half()                     # fresh allocation of the same size class every iteration
+        seen_ptrs.add(x.data_ptr())
+        got = m(x)
+        _check(got.cpu(), vit_oracle.vit_forward(sd, x.float().cpu(), 2), "fp16")
+        assert m(x) is got                          # the per-caption re-encode of the same frames still hits
+        del x, got
+    # non-contiguous frames: same rule
+    base = W.frames(8, 32, seed=7).to(cuda)
+    for video in range(3):
+        x = (base + video)[::2]
+        _check(m(x).cpu(), vit_oracle.vit_forward(sd, x.cpu().contiguous(), 2), "fp16")
+        del x
+
+
+def test_vit_host_stream_ragged_and_growing_batches(cuda):
+    """A dataset stream ends with a smaller batch: its slot offsets must be those of the full batches (the other slot is
+    still in flight).  A larger batch later re-binds the pipeline after draining it.  Results stay bit-identical to the
+    device-resident call in every case."""
+    m, _ = _build("tiny", 32, "bf16", cuda)
+    sizes = [6, 6, 6, 2, 1, 6, 9, 3, 9]
+    batches = [W.frames(b, 32, seed=40 + i).pin_memory() for i, b in enumerate(sizes)]
+    want = [m(b.to(cuda)).cpu() for b in batches]
+    for _ in range(3):                              # repeated, so in-flight overlap has several chances to bite
+        got = [o.clone() for o in m.encode_host_stream(iter(batches))]
+        assert [tuple(g.shape) for g in got] == [tuple(w.shape) for w in want]
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+
+
 def test_native_library_is_the_path(cuda):
     m, _ = _build("tiny", 32, "bf16", cuda)
     x = W.frames(2, 32, seed=0).to(cuda)

@@ -126,3 +126,21 @@ def test_real_vg_ontology_sizes():
     got = vt.load_ontology("vg", root="/root/reference")
     assert len(got["scenes"]) == 365
     assert 19000 < len(got["objects"]) < 20000 and 7000 < len(got["verbs"]) < 7500
+
+
+def test_clip_model_rejects_unsupported_text_tower_instead_of_falling_back():
+    """North-star: no library / CPU fallback — a text tower outside the native kernels' shapes is an error."""
+    import pytest
+    from transformers import CLIPConfig, CLIPModel
+
+    from vidil_b200.clip import VidilCLIPModel
+    cfg = CLIPConfig(text_config=dict(hidden_size=96, intermediate_size=192, num_hidden_layers=1, num_attention_heads=2,
+                                      max_position_embeddings=16, vocab_size=64),
+                     vision_config=dict(hidden_size=128, intermediate_size=256, num_hidden_layers=1, num_attention_heads=2,
+                                        image_size=28, patch_size=14), projection_dim=64)
+    hf = CLIPModel(cfg).eval()
+    with pytest.raises(RuntimeError, match="unsupported CLIP text tower"):
+        VidilCLIPModel(hf)
+    m = VidilCLIPModel(hf, native_text=False)       # image tower only is allowed; asking it for text is an error
+    with pytest.raises(RuntimeError, match="no fallback text path"):
+        m(input_ids=__import__("torch").zeros(1, 4, dtype=__import__("torch").long))

@@ -21,6 +21,20 @@ __global__ void __launch_bounds__(512, 1) k(int iters, long long* cycles, float*
         } else if (MODE == 2) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) x[i] = fmaf(x[i], 0.999f, 0.001f);
+        } else if (MODE == 4) {  // packed half exponentials: two results per MUFU instruction?
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                uint32_t u = __float_as_uint(x[i]);
+                asm volatile("ex2.approx.f16x2 %0, %0;" : "+r"(u));
+                x[i] = __uint_as_float(u);
+            }
+        } else if (MODE == 5) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                uint32_t u = __float_as_uint(x[i]);
+                asm volatile("ex2.approx.ftz.bf16x2 %0, %0;" : "+r"(u));
+                x[i] = __uint_as_float(u);
+            }
         } else {  // mixed: per pair 1 FFMA2 + 2 MUFU + 1 FADD2 (the softmax inner loop)
 #pragma unroll
             for (int i = 0; i < 16; i += 2) {
@@ -45,13 +59,15 @@ int main() {
     long long* cyc; float* sink;
     cudaMalloc(&cyc, 148 * 8); cudaMalloc(&sink, 148 * 512 * 4);
     const int iters = 4000;
-    const char* names[4] = {"MUFU.EX2", "FFMA2", "FFMA", "softmax-mix"};
-    for (int mode = 0; mode < 4; ++mode) for (int threads : {128, 256, 512}) {
+    const char* names[6] = {"MUFU.EX2", "FFMA2", "FFMA", "softmax-mix", "EX2.f16x2", "EX2.bf16x2"};
+    for (int mode = 0; mode < 6; ++mode) for (int threads : {128, 256, 512}) {
         switch (mode) {
             case 0: k<0><<<148, threads>>>(iters, cyc, sink); break;
             case 1: k<1><<<148, threads>>>(iters, cyc, sink); break;
             case 2: k<2><<<148, threads>>>(iters, cyc, sink); break;
-            default: k<3><<<148, threads>>>(iters, cyc, sink); break;
+            case 3: k<3><<<148, threads>>>(iters, cyc, sink); break;
+            case 4: k<4><<<148, threads>>>(iters, cyc, sink); break;
+            default: k<5><<<148, threads>>>(iters, cyc, sink); break;
         }
         cudaDeviceSynchronize();
         long long h; cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);

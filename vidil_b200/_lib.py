@@ -136,8 +136,7 @@ def load() -> ctypes.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_build.LIB_PATH):
-        _build.build()
+    _build.build()  # returns at once when build.stamp matches the sources; rebuilds a stale library (file-locked, atomic)
     lib = ctypes.CDLL(_build.LIB_PATH)
     for name, (res, args) in SIGNATURES.items():
         fn = getattr(lib, name)  # AttributeError here means the .so is stale: rebuild with --force

@@ -58,31 +58,49 @@ def is_current() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile (if sources changed) and return the path of the shared library."""
+    """Compile (if sources changed) and return the path of the shared library.
+
+    Safe under torchrun: every rank may call this at import.  The whole build runs under an exclusive file lock, objects
+    go to a private temporary directory and the finished library is moved into place with os.replace, so no process can
+    ever dlopen a half-written .so or link half-written objects; ranks that lose the race find the stamp current."""
     if not force and is_current():
         return LIB_PATH
+    import fcntl
+    import tempfile
     os.makedirs(OUT_DIR, exist_ok=True)
-    nvcc = _nvcc()
-    extra = ["-Xptxas", "-v"] if verbose else []
+    with open(os.path.join(OUT_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and is_current():  # another process built it while this one waited for the lock
+                return LIB_PATH
+            nvcc = _nvcc()
+            extra = ["-Xptxas", "-v"] if verbose else []
+            with tempfile.TemporaryDirectory(dir=OUT_DIR, prefix=".build-") as tmp:
 
-    def compile_one(src: str) -> str:
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
-        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(SRC_DIR, src), "-o", obj]
-        r = subprocess.run(cmd, capture_output=True, text=True)
-        if r.returncode != 0:
-            raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
-        if verbose:
-            sys.stderr.write(f"== {src}\n{r.stderr}\n")
-        return obj
+                def compile_one(src: str) -> str:
+                    obj = os.path.join(tmp, src.replace(".cu", ".o"))
+                    cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", os.path.join(SRC_DIR, src), "-o", obj]
+                    r = subprocess.run(cmd, capture_output=True, text=True)
+                    if r.returncode != 0:
+                        raise RuntimeError(f"nvcc failed on {src}:\n{r.stdout}\n{r.stderr}")
+                    if verbose:
+                        sys.stderr.write(f"== {src}\n{r.stderr}\n")
+                    return obj
 
-    with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
-        objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB_PATH, *objs]
-    r = subprocess.run(cmd, capture_output=True, text=True)
-    if r.returncode != 0:
-        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(os.path.join(OUT_DIR, "build.stamp"), "w") as f:
-        f.write(_source_digest())
+                with concurrent.futures.ThreadPoolExecutor(max_workers=min(len(SOURCES), os.cpu_count() or 1)) as ex:
+                    objs = list(ex.map(compile_one, SOURCES))
+                tmp_lib = os.path.join(tmp, "libvidil_b200.so")
+                cmd = [nvcc, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", tmp_lib, *objs]
+                r = subprocess.run(cmd, capture_output=True, text=True)
+                if r.returncode != 0:
+                    raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+                os.replace(tmp_lib, LIB_PATH)
+            tmp_stamp = os.path.join(OUT_DIR, f".build.stamp.{os.getpid()}")
+            with open(tmp_stamp, "w") as f:
+                f.write(_source_digest())
+            os.replace(tmp_stamp, os.path.join(OUT_DIR, "build.stamp"))
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return LIB_PATH
 
 

@@ -397,23 +397,25 @@ class VidilCLIPModel(nn.Module):
 
     def __init__(self, hf_model, compute_dtype="bf16", native_text=True):
         super().__init__()
-        self.hf = hf_model
         self.vision = CLIPVisionB200.from_hf(hf_model, compute_dtype=compute_dtype)
         tc = hf_model.config.text_config
-        # the native text tower covers CLIP's shapes (head_dim 64, <= 208 positions); anything else stays on transformers
-        self.text = (CLIPTextB200.from_hf(hf_model, compute_dtype=compute_dtype)
-                     if native_text and tc.hidden_size == 64 * tc.num_attention_heads and tc.hidden_size % 128 == 0
-                     and tc.max_position_embeddings <= 208 else None)
+        # No library fallback on the product path: a text tower outside the native kernels' shapes (head_dim 64,
+        # width a multiple of 128, <= 208 positions — every OpenAI CLIP checkpoint) is an error, not a detour
+        # through transformers' eager code.
+        if native_text and not (tc.hidden_size == 64 * tc.num_attention_heads and tc.hidden_size % 128 == 0
+                                and tc.max_position_embeddings <= 208):
+            raise RuntimeError(f"vidil_b200: unsupported CLIP text tower (hidden {tc.hidden_size}, heads "
+                               f"{tc.num_attention_heads}, positions {tc.max_position_embeddings}); the native "
+                               "text encoder needs head_dim 64, hidden % 128 == 0 and <= 208 positions")
+        self.text = CLIPTextB200.from_hf(hf_model, compute_dtype=compute_dtype) if native_text else None
 
     @torch.no_grad()
     def forward(self, input_ids=None, pixel_values=None, attention_mask=None, **_unused):
         image_embeds = self.vision(pixel_values) if pixel_values is not None else None
         text_embeds = None
         if input_ids is not None:
-            if self.text is not None:
-                text_embeds = self.text(input_ids, attention_mask)
-            else:
-                t = self.hf.text_model(input_ids=input_ids, attention_mask=attention_mask).pooler_output
-                t = self.hf.text_projection(t)
-                text_embeds = t / t.norm(p=2, dim=-1, keepdim=True)
+            if self.text is None:
+                raise RuntimeError("vidil_b200: this VidilCLIPModel was built with native_text=False (image tower only); "
+                                   "there is no fallback text path")
+            text_embeds = self.text(input_ids, attention_mask)
         return SimpleNamespace(image_embeds=image_embeds, text_embeds=text_embeds)

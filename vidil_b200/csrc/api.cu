@@ -111,9 +111,16 @@ struct vidil_encoder {
     // host-buffer pipeline (vidil_encoder_host_submit / _wait): copy engines run on their own streams
     cudaStream_t copy_in = nullptr, copy_out = nullptr;
     cudaEvent_t ev_in[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_out[2] = {nullptr, nullptr};
+    cudaEvent_t ev_bind = nullptr;
+    // geometry of the two-slot pipeline, fixed when a scratch buffer is bound: slot offsets must not move while the other slot
+    // is in flight, so they are derived from the capacity batch, never from the batch of the current call
+    void* pipe_scratch = nullptr;
+    size_t pipe_bytes = 0;
+    int pipe_cap = 0;
     ~vidil_encoder() {
         if (copy_in) cudaStreamDestroy(copy_in);
         if (copy_out) cudaStreamDestroy(copy_out);
+        if (ev_bind) cudaEventDestroy(ev_bind);
         for (int i = 0; i < 2; ++i) {
             if (ev_in[i]) cudaEventDestroy(ev_in[i]);
             if (ev_compute[i]) cudaEventDestroy(ev_compute[i]);
@@ -745,15 +752,33 @@ int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, 
             VIDIL_CUDA_OK(cudaEventCreateWithFlags(&enc->ev_compute[i], cudaEventDisableTiming));
             VIDIL_CUDA_OK(cudaEventCreateWithFlags(&enc->ev_out[i], cudaEventDisableTiming));
         }
+        VIDIL_CUDA_OK(cudaEventCreateWithFlags(&enc->ev_bind, cudaEventDisableTiming));
     }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    if (dev_scratch != enc->pipe_scratch || dev_scratch_bytes != enc->pipe_bytes || batch > enc->pipe_cap) {
+        // (Re)binding the pipeline to a scratch buffer or to a larger capacity moves the slot offsets: drain everything
+        // in flight first (rare: once per stream of batches), then order the copy engines after whatever the caller's
+        // stream still has enqueued on this memory.
+        for (int i = 0; i < 2; ++i) VIDIL_CUDA_OK(cudaEventSynchronize(enc->ev_out[i]));
+        VIDIL_CUDA_OK(cudaStreamSynchronize(enc->copy_in));
+        VIDIL_CUDA_OK(cudaStreamSynchronize(enc->copy_out));
+        VIDIL_CUDA_OK(cudaEventRecord(enc->ev_bind, s));
+        VIDIL_CUDA_OK(cudaStreamWaitEvent(enc->copy_in, enc->ev_bind, 0));
+        VIDIL_CUDA_OK(cudaStreamWaitEvent(enc->copy_out, enc->ev_bind, 0));
+        enc->pipe_scratch = dev_scratch;
+        enc->pipe_bytes = dev_scratch_bytes;
+        enc->pipe_cap = batch;
+    }
     const bool clip = enc->cfg.proj_dim > 0;
+    const int cap = enc->pipe_cap;  // batch <= cap: a ragged last batch uses the same slot offsets as the full ones
     const size_t in_bytes = static_cast<size_t>(batch) * 3 * enc->cfg.img_size * enc->cfg.img_size * 4;
     const size_t out_tok_bytes = static_cast<size_t>(batch) * enc->tokens * enc->cfg.embed_dim * 4;
-    const size_t per_slot = align_up(in_bytes) + align_up(out_tok_bytes);
+    const size_t cap_in = align_up(static_cast<size_t>(cap) * 3 * enc->cfg.img_size * enc->cfg.img_size * 4);
+    const size_t cap_out = align_up(static_cast<size_t>(cap) * enc->tokens * enc->cfg.embed_dim * 4);
+    const size_t per_slot = cap_in + cap_out;
     uint8_t* base = reinterpret_cast<uint8_t*>(dev_scratch);
     float* d_in = reinterpret_cast<float*>(base + slot * per_slot);
-    float* d_out = reinterpret_cast<float*>(base + slot * per_slot + align_up(in_bytes));
+    float* d_out = reinterpret_cast<float*>(base + slot * per_slot + cap_in);
     void* ws = base + 2 * per_slot;
     const size_t ws_bytes = dev_scratch_bytes - 2 * per_slot;
     // H2D: may start as soon as the previous forward that read this slot's frames is done

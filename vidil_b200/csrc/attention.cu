@@ -682,11 +682,8 @@ int cross_decode_mma_run(const CUtensorMap& kv_map_sw128, int row0, const void* 
 #define VIDIL_XDEC(T)                                                                                                          \
     do {                                                                                                                       \
         auto k = chunked ? cross_decode_mma_chunked_kernel<T> : cross_decode_mma_kernel<T>;                                    \
-        static size_t configured[2] = {0, 0}; /* largest dynamic shared memory size set so far, per kernel */                  \
-        if (smem > configured[chunked ? 1 : 0]) {                                                                              \
-            VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));       \
-            configured[chunked ? 1 : 0] = smem;                                                                                \
-        }                                                                                                                      \
+        /* per launch (cheap): the attribute belongs to the current device's copy of the function */                         \
+        VIDIL_CUDA_OK(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));           \
         VIDIL_CUDA_OK(launch_pdl(k, dim3(H, F), dim3(32), smem, stream, kv_map_sw128, reinterpret_cast<const T*>(q),         \
                                  reinterpret_cast<T*>(out), row0, Nv, nq, H, sl2));                                           \
     } while (0)

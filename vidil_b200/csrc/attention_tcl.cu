@@ -656,11 +656,8 @@ template <typename T>
 int launch_long(const AttentionMaps& m, float scale, cudaStream_t stream) {
     auto kern = attention_tcl_kernel<T>;
     const Layout lay = make_layout(m.KB);
-    static bool configured = false;
-    if (!configured) {
-        VIDIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, make_layout(MAX_KB).total));
-        configured = true;
-    }
+    // per launch (cheap): the attribute belongs to the current device's copy of the function
+    VIDIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, make_layout(MAX_KB).total));
     const int rounds = (m.n_qt + 1) / 2;
     const int n_items = m.B * m.H * rounds;
     int grid = gemm_num_sms();

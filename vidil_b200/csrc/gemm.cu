@@ -559,11 +559,8 @@ template <typename T, int EPI, int CG>
 int launch(const GemmProblem& p, cudaStream_t stream) {
     using C = Cfg<CG>;
     auto kern = gemm_tcgen05_kernel<T, EPI, CG>;
-    static bool configured = false;  // per instantiation
-    if (!configured) {
-        VIDIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        configured = true;
-    }
+    // per launch (cheap): the attribute belongs to the current device's copy of the function
+    VIDIL_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     const int tiles_m = (p.M + BLOCK_M * CG - 1) / (BLOCK_M * CG);
     const int tiles_n = (p.N + BLOCK_N - 1) / BLOCK_N;
     const int num_tiles = tiles_m * tiles_n;

@@ -167,11 +167,8 @@ int preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const floa
     VIDIL_CUDA_OK(cudaMemcpyAsync(tab_h, ch.table.data(), ch.table.size() * 4, cudaMemcpyHostToDevice, stream));
     VIDIL_CUDA_OK(cudaMemcpyAsync(tab_v, cv.table.data(), cv.table.size() * 4, cudaMemcpyHostToDevice, stream));
     const size_t smem = static_cast<size_t>(W) * 3 + 16;
-    static bool configured = false;
-    if (!configured) {
-        VIDIL_CUDA_OK(cudaFuncSetAttribute(resize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
-        configured = true;
-    }
+    // per launch (cheap): the attribute belongs to the current device's copy of the function
+    VIDIL_CUDA_OK(cudaFuncSetAttribute(resize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
     resize_rows_kernel<<<B * H, 256, smem, stream>>>(frames, tmp, tab_h, ch.ksize, W, S);
     VIDIL_CUDA_OK(cudaGetLastError());
     const dim3 grid((S + 255) / 256, S, B);

@@ -126,11 +126,8 @@ int topk_rerank_run(const float* scores, int64_t ld_scores, const float* img, co
                   200 * 1024 / 4);
         return 1;
     }
-    static bool configured = false;
-    if (!configured) {
-        VIDIL_CUDA_OK(cudaFuncSetAttribute(topk_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        configured = true;
-    }
+    // per launch (cheap): the attribute belongs to the current device's copy of the function
+    VIDIL_CUDA_OK(cudaFuncSetAttribute(topk_rerank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     topk_rerank_kernel<<<F, TK_THREADS, smem, stream>>>(scores, ld_scores, img, bank, T, D, k, out_scores, out_idx);
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);

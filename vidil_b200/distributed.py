@@ -88,7 +88,7 @@ def all_gather_json(obj, device: torch.device | str | None = None) -> list:
     padded[:payload.numel()] = payload
     bufs = [torch.empty(width, dtype=torch.uint8, device=device) for _ in range(world)]
     dist.all_gather(bufs, padded)
-    return [json.loads(bytes(b[:s].cpu().tolist()).decode("utf-8")) if s else None for b, s in zip(bufs, sizes)]
+    return [json.loads(b[:s].cpu().numpy().tobytes().decode("utf-8")) if s else None for b, s in zip(bufs, sizes)]
 
 
 def merge_rank_dicts(per_rank: list) -> dict:

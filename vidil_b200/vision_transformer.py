@@ -100,8 +100,15 @@ class NativeEncoder:
         _lib.check(st, f"vidil_encoder_load({name})")
 
     def pipeline_scratch(self, batch: int, device) -> torch.Tensor:
+        """Device scratch of the two-slot host pipeline.  It only ever grows; the library fixes the slot offsets from the
+        batch it was first bound with, so later, smaller (ragged last) batches reuse it as is.  Growing it means the old
+        buffer is about to be freed under copy streams torch's allocator does not know: drain both slots first."""
         need = self.lib.vidil_encoder_host_pipeline_scratch_bytes(self.handle, batch)
         if self._pipe is None or self._pipe.numel() < need or self._pipe.device != device:
+            if self._pipe is not None:
+                self.host_wait(0)
+                self.host_wait(1)
+                torch.cuda.current_stream().synchronize()
             self._pipe = self._aligned(need, device)
         return self._pipe
 
@@ -196,6 +203,7 @@ class VisionTransformer(nn.Module):
         self.cache_identical_inputs = cache_identical_inputs
         self._cache_key = None
         self._cache_out = None
+        self._cache_in = None
 
     @staticmethod
     def _init_weights(m):
@@ -250,6 +258,7 @@ class VisionTransformer(nn.Module):
                 key = (x.data_ptr(), tuple(x.shape), tuple(x.stride()), x.dtype, x._version, self._packed_sig)
                 if key == self._cache_key and self._cache_out is not None:
                     return self._cache_out
+            x_orig = x  # the cache key is THIS tensor's address and version: it must stay alive while the entry does
             x = x.contiguous().float()
             B = x.shape[0]
             out = torch.empty(B, enc.tokens, self.embed_dim, dtype=torch.float32, device=x.device)
@@ -260,7 +269,9 @@ class VisionTransformer(nn.Module):
                                            torch.cuda.current_stream().cuda_stream)
             _lib.check(st, "vidil_vit_forward")
             if key is not None:
-                self._cache_key, self._cache_out, self._cache_in = key, out, x  # keep x alive: its address is the key
+                # Pin the ORIGINAL input (not the converted copy): while it is referenced here the caching allocator cannot
+                # hand its address to another tensor, so (data_ptr, _version) identifies these very frames.
+                self._cache_key, self._cache_out, self._cache_in = key, out, x_orig
         return out
 
     @torch.no_grad()
@@ -289,7 +300,8 @@ class VisionTransformer(nn.Module):
     def encode_host_stream(self, batches, outs=None):
         """Encode a stream of host batches with copies overlapped with compute.
 
-        `batches`: iterable of CPU fp32 tensors [B,3,S,S] (pinned for full PCIe rate; all the same B).  Yields one CPU
+        `batches`: iterable of CPU fp32 tensors [B,3,S,S] (pinned for full PCIe rate; B may vary — a ragged last batch
+        reuses the slots of the full ones, a larger batch drains the pipeline and re-binds it).  Yields one CPU
         tensor [B, N+1, D] per batch, in order.  `outs`: optional pair of pinned output tensors to cycle through (the
         yielded tensor is then only valid until two batches later).  Batch k+1's H2D runs during batch k's forward and
         batch k's D2H during batch k+1's (vidil_encoder_host_submit / _wait, two slots)."""
