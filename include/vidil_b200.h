@@ -11,6 +11,8 @@
  *                                                                    -> vidil_sim_topk
  *   run_visual_tokenization.py:84-96     CLIPModel(**inputs).text_embeds  -> vidil_clip_text_forward
  *   run_video_CapFilt.py:128-137         process_frame (PIL resize + ToTensor + Normalize) -> vidil_preprocess_frames
+ *   run_visual_tokenization.py:138-140   processor(images=frames) = transformers' CLIPImageProcessor (shortest edge 224
+ *                                        bicubic, centre crop, rescale, normalise)       -> vidil_clip_preprocess_frames
  *   models/blip.py:127-167 BLIP_Decoder.generate(sample=False) from the image tokens on: models/med.py:811-955
  *                                        BertLMHeadModel + transformers' beam search      -> vidil_med_generate
  *   models/blip_itm.py:49-57 text_encoder(mode multimodal) + itm_head; models/med.py:871-893 teacher-forced logits
@@ -37,7 +39,7 @@
 extern "C" {
 #endif
 
-#define VIDIL_B200_ABI_VERSION 1
+#define VIDIL_B200_ABI_VERSION 2
 
 /* Tensor-core operand type.  Accumulation, LayerNorm/softmax statistics and the residual stream are fp32. */
 enum { VIDIL_DTYPE_BF16 = 0, VIDIL_DTYPE_FP16 = 1 };
@@ -237,6 +239,16 @@ int32_t vidil_preprocess_frames(const uint8_t* frames_u8, int32_t batch, int32_t
                                 const float* mean3, const float* std3, float* out, void* workspace, size_t workspace_bytes,
                                 void* stream);
 
+/* The CLIP side (run_visual_tokenization.py:138-140: `processor(images=frames, return_tensors="pt")`, transformers'
+ * CLIPImageProcessor with its PIL backend): resize so that the SHORTER side becomes S (the longer one int(S * long / short)),
+ * Pillow BICUBIC as above; keep the centre S x S window (top = (rh - S) / 2, left = (rw - S) / 2, integer division);
+ * rescale by the double 1/255 rounded to float32; (x - mean) / std in float32.  Bit-identical to the processor's output
+ * (tests/golden/clip_preprocess.npz).  Only the columns / rows of the window are computed. */
+size_t  vidil_clip_preprocess_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size);
+int32_t vidil_clip_preprocess_frames(const uint8_t* frames_u8, int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size,
+                                     const float* mean3, const float* std3, float* out, void* workspace,
+                                     size_t workspace_bytes, void* stream);
+
 /* ---- per-kernel-class device timing (bench.py's roofline figures) ---------------------------- */
 /* With profiling on, every kernel a forward enqueues is bracketed by CUDA events on the caller's stream.
  * vidil_encoder_read_profile synchronises those events, adds up elapsed time / algorithmic FLOPs / algorithmic
@@ -258,8 +270,23 @@ int32_t vidil_med_set_profiling(vidil_med* med, int32_t enable);
 int32_t vidil_med_read_profile(vidil_med* med, vidil_kernel_stats* out);
 
 /* ---- similarity + top-k ----------------------------------------------------------------------- */
-/* img fp32 [F,D], bank fp32 [T,D] (device, D multiple of 64) -> out_scores fp32 [F,k], out_idx int32 [F,k]:
- * for each frame the k phrases with the largest fp32 dot product, best first (k <= 12). */
+/* Replaces run_visual_tokenization.py:276 (`sims = image_embeds @ text_embeds.t()`), :299 (D2H of [F,T]) and :306
+ * (`np.argsort(score)[::-1][:k]` per frame).  img fp32 [F,D], bank fp32 [T,D] (device, D a multiple of 64) -> out_scores
+ * fp32 [F,k], out_idx int32 [F,k]: for each frame the k phrases with the largest FP32 dot product, best first (k <= 12;
+ * exact ties are reported index-descending).  The [F,T] matrix is never written: a tcgen05 GEMM on fp16 copies of the
+ * operands keeps the two best scores of every 32-phrase group in its epilogue, and candidates are then re-scored in fp32 from
+ * the original embeddings until the fp32 ranking is certain (error bound 2^-10 |img| max|bank row| on the fp16 product), so
+ * the indices are those of the fp32 ranking for any data, near-duplicate phrases included.  Any T that fits memory.
+ *
+ * A phrase bank is constant for a whole run: vidil_sim_bank_create converts it once (fp16 copy for the tensor cores, fp32
+ * copy for the re-scoring, largest row norm) and vidil_sim_bank_topk uses the handle.  vidil_sim_topk is the one-shot form
+ * (the bank is converted inside the call, in the workspace). */
+typedef struct vidil_sim_bank vidil_sim_bank;
+int32_t vidil_sim_bank_create(const float* bank, int32_t T, int32_t D, void* stream, vidil_sim_bank** out);
+void    vidil_sim_bank_destroy(vidil_sim_bank* bank);
+size_t  vidil_sim_bank_topk_workspace_bytes(const vidil_sim_bank* bank, int32_t F);
+int32_t vidil_sim_bank_topk(const vidil_sim_bank* bank, const float* img, int32_t F, int32_t k, float* out_scores,
+                            int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);
 size_t  vidil_sim_topk_workspace_bytes(int32_t F, int32_t T, int32_t D);
 int32_t vidil_sim_topk(const float* img, const float* bank, int32_t F, int32_t T, int32_t D, int32_t k,
                        float* out_scores, int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream);

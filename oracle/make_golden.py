@@ -19,6 +19,7 @@ stored):
   clip_text_large14.npz   transformers.CLIPModel text tower of clip-vit-large-patch14's shape, 3 phrases of 20 tokens
   med_tiny.npz            reference med.py (D=128, 2 layers): teacher-forced decoder logits, cached one-token steps, ITM logits
   med_base_l.npz          reference med.py at BERT-base shape with ViT-L tokens (197 x 1024): the same, every 97th vocabulary entry
+  clip_preprocess.json    transformers' CLIPImageProcessor (PIL backend) pixel_values on synthetic uint8 frames of 10 geometries
   preprocess.json         torchvision/PIL process_frame (run_video_CapFilt.py:128-137) on synthetic uint8 frames of 7 geometries:
                           SHA-256 of the float32 output + a 5x5 sample per channel
   tokenization.json       sim top-k indices computed with the reference's own lines (:276, :306), and
@@ -183,6 +184,31 @@ def golden_preprocess():
     print("wrote preprocess.json")
 
 
+CLIP_PREPROCESS_CASES = [(240, 320), (320, 240), (224, 224), (360, 640), (720, 1280), (225, 300), (100, 150), (500, 333),
+                         (1080, 1920), (224, 225)]
+
+
+def golden_clip_preprocess():
+    """transformers' CLIPImageProcessor with its PIL backend — what `processor(images=frames, return_tensors="pt")` at
+    run_visual_tokenization.py:138-140 runs — on synthetic uint8 frames: SHA-256 of the float32 pixel_values plus a sample."""
+    import hashlib
+    import warnings
+
+    from transformers.models.clip.image_processing_pil_clip import CLIPImageProcessorPil
+    warnings.filterwarnings("ignore")
+    proc = CLIPImageProcessorPil()
+    cases = []
+    for (H, Wd) in CLIP_PREPROCESS_CASES:
+        frames = W.u8_frames(2, H, Wd, seed=H * 7 + Wd).numpy()
+        out = proc(images=[f for f in frames], return_tensors="np")["pixel_values"]
+        assert out.shape == (2, 3, 224, 224) and out.dtype == np.float32
+        cases.append({"H": H, "W": Wd, "S": 224, "sha256": hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest(),
+                      "sample": out[:, :, ::56, ::56].tolist()})
+    with open(os.path.join(GOLDEN_DIR, "clip_preprocess.json"), "w") as f:
+        json.dump(cases, f)
+    print("wrote clip_preprocess.json")
+
+
 def golden_tokenization():
     # similarity + per-frame argsort exactly as run_visual_tokenization.py:276,298-306
     F_, T, D, k = 64, 1000, 768, 5
@@ -243,6 +269,7 @@ def main():
     golden_med("tiny", 3, 9, 5, 1, "med_tiny.npz")
     golden_med("base_l", 2, 8, 197, 97, "med_base_l.npz")
     golden_preprocess()
+    golden_clip_preprocess()
     golden_tokenization()
     golden_sharding()
 

@@ -84,3 +84,32 @@ def process_frame(frame: np.ndarray, image_size: int, mean=MEAN, std=STD) -> np.
     x = r.astype(np.float32) / np.float32(255.0)                      # ToTensor
     x = (x - np.asarray(mean, dtype=np.float32)) / np.asarray(std, dtype=np.float32)   # Normalize, float32 sub then div
     return np.ascontiguousarray(x.transpose(2, 0, 1))
+
+
+CLIP_MEAN = (0.48145466, 0.4578275, 0.40821073)   # transformers.image_utils.OPENAI_CLIP_MEAN
+CLIP_STD = (0.26862954, 0.26130258, 0.27577711)   # OPENAI_CLIP_STD
+
+
+def clip_resize_geometry(h: int, w: int, size: int):
+    """transformers' get_resize_output_image_size(image, size=shortest_edge, default_to_square=False): the shorter side
+    becomes `size`, the longer one int(size * long / short).  Returns (new_h, new_w, top, left) with the centre-crop
+    origin of image_transforms.center_crop: (new - size) // 2 on each axis."""
+    short, long_ = (w, h) if w <= h else (h, w)
+    new_short, new_long = size, int(size * long_ / short)
+    nh, nw = (new_long, new_short) if w <= h else (new_short, new_long)
+    return nh, nw, (nh - size) // 2, (nw - size) // 2
+
+
+def clip_process_frame(frame: np.ndarray, size: int = 224, mean=CLIP_MEAN, std=CLIP_STD) -> np.ndarray:
+    """run_visual_tokenization.py:138-140 `processor(images=frames, return_tensors="pt")` for one frame = transformers'
+    CLIPImageProcessor with the PIL backend (the only one that existed when the reference was written; un-vendored,
+    unpinned — 5.5.0 installed here, class CLIPImageProcessorPil): PIL bicubic resize of the shortest edge to `size`,
+    centre crop size x size, rescale = float64(u8) * (1/255) cast to float32, normalise (x - mean) / std in float32.
+    [H, W, 3] uint8 -> [3, size, size] float32.  Pinned bit-for-bit against the processor itself:
+    tests/golden/clip_preprocess.npz (oracle/make_golden.py) and live in tests/test_oracle_golden.py."""
+    h, w = frame.shape[:2]
+    nh, nw, top, left = clip_resize_geometry(h, w, size)
+    r = resize_bicubic_u8(np.ascontiguousarray(frame), nh, nw)[top:top + size, left:left + size]
+    x = (r.astype(np.float64) * (1 / 255)).astype(np.float32)
+    x = (x - np.asarray(mean, dtype=np.float32)) / np.asarray(std, dtype=np.float32)
+    return np.ascontiguousarray(x.transpose(2, 0, 1))

@@ -1,8 +1,9 @@
-"""Import the UNMODIFIED reference modules from /root/reference in the build container.
+"""Import the UNMODIFIED reference modules: from /root/reference in the build container, or from the staged copy
+under oracle/_ref/ (git-ignored, made by oracle/stage_ref.py; it travels to the GPU box like a built .so).
 
-TEST INFRASTRUCTURE, build-container only: /root/reference does not exist on the GPU box, so nothing that
-runs there (pytest -m gpu, smoke(), bench.py) may call this.  It is used by oracle/make_golden.py to create
-the committed fixtures and by tests that are skipped when the reference tree is absent.
+TEST / BASELINE INFRASTRUCTURE: used by oracle/make_golden.py to create the committed fixtures, by tests that are
+skipped when no reference tree is present, and by `bench.py --impl reference` / the `cpu_baseline` leg to time
+the reference's own models/vit.py on the host cores.  Never imported by anything under vidil_b200/.
 
 `models/vit.py` imports timm and fairscale, neither of which is installed.  The stand-ins
 below carry no arithmetic except PatchEmbed, which restates timm's (Conv2d(k=s=patch) -> flatten(2) ->
@@ -18,7 +19,19 @@ import types
 import torch
 import torch.nn as nn
 
-REFERENCE_ROOT = os.environ.get("VIDIL_REFERENCE_ROOT", "/root/reference")
+STAGED_ROOT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")
+
+
+def _reference_root() -> str:
+    env = os.environ.get("VIDIL_REFERENCE_ROOT")
+    if env:
+        return env
+    if os.path.isfile("/root/reference/models/vit.py"):
+        return "/root/reference"
+    return STAGED_ROOT  # oracle/stage_ref.py: the reference's own files, byte for byte, outside the git history
+
+
+REFERENCE_ROOT = _reference_root()
 
 
 def reference_available() -> bool:

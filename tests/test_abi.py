@@ -38,7 +38,7 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 def test_header_compiles_as_plain_c(tmp_path):
     src = tmp_path / "t.c"
-    src.write_text('#include "vidil_b200.h"\nint main(void){ vidil_encoder_cfg c; (void)c; return VIDIL_B200_ABI_VERSION - 1; }\n')
+    src.write_text('#include "vidil_b200.h"\nint main(void){ vidil_encoder_cfg c; (void)c; return VIDIL_B200_ABI_VERSION - 2; }\n')
     r = subprocess.run(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src), "-o",
                         str(tmp_path / "t.o")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
@@ -54,7 +54,7 @@ def test_sass_contains_tcgen05_and_tma():
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU failure mode")
 def test_compute_entry_points_fail_loudly_without_a_gpu():
     lib = _lib.load()
-    assert lib.vidil_abi_version() == 1
+    assert lib.vidil_abi_version() == _lib.ABI_VERSION
     cfg = _lib.EncoderCfg(img_size=224, patch_size=16, embed_dim=1024, depth=24, num_heads=16, mlp_dim=4096,
                           ln_eps=1e-6, act=0, patch_bias=1, pre_ln=0, proj_dim=0, dtype=0, cta_group=0)
     h = ctypes.c_void_p()

@@ -173,6 +173,56 @@ def test_sim_topk_near_ties_below_fp16_resolution(cuda):
     assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx)
 
 
+def test_sim_topk_combined_vg_bank_and_beyond_the_old_row_limit(cuda):
+    """The four `vg` banks as ONE 44 437-phrase bank (19 965 + 16 693 + 365 + 7 414, run_visual_tokenization.py:371-383), and a
+    bank larger than the 51 200-row shared-memory limit the first-generation kernel had: indices equal the fp32 argsort."""
+    for Fr, T, D, k in [(256, 44437, 768, 5), (40, 70001, 64, 7)]:
+        img, bank = W.unit_rows(Fr, D, seed=Fr + 1), W.unit_rows(T, D, seed=T)
+        ref_scores, ref_idx = tokenization_oracle.sim_topk(img.numpy(), bank.numpy(), k)
+        scores, idx = ops.sim_topk(img.to(cuda), bank.to(cuda), k)
+        assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx), (Fr, T)
+        assert np.abs(scores.cpu().numpy() - ref_scores).max() < 1e-5
+
+
+def test_sim_topk_clusters_of_near_synonyms(cuda):
+    """Real ontology banks contain clusters of near-duplicate phrases.  40 phrases within ~1e-4 of one another in score — far
+    more than any fixed candidate count, and below the resolution of the fp16 tensor-core pass — all inside ONE 32-phrase
+    group or spread over many: the selection keeps re-scoring until the fp32 ranking is certain (the margin guard)."""
+    D, k = 768, 10
+    base = W.unit_rows(1, D, seed=21)[0]
+    noise = W.unit_rows(64, D, seed=22)
+    for layout in ("one_group", "spread"):
+        bank = W.unit_rows(4000, D, seed=23)
+        for j in range(40):
+            v = base + (2e-3 * (j + 1)) * noise[j]                      # consecutive scores ~1e-5 apart: above fp32 summation noise
+            row = 1024 + j if layout == "one_group" else 37 + 97 * j      # one_group: columns 1024..1063 = groups 32 and 33
+            bank[row] = v / v.norm()
+        img = torch.stack([base, base + 1e-3 * noise[50], W.unit_rows(1, D, seed=24)[0]])
+        img = img / img.norm(dim=1, keepdim=True)
+        ref_scores, ref_idx = tokenization_oracle.sim_topk(img.numpy(), bank.numpy(), k)
+        assert (ref_scores[0][0] - ref_scores[0][-1]) < 1e-3 and (-np.diff(ref_scores[0])).min() > 2e-6   # a cluster, but rankable
+        scores, idx = ops.sim_topk(img.to(cuda), bank.to(cuda), k)
+        assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx), layout
+
+
+def test_sim_topk_cached_bank_equals_one_shot_and_follows_updates(cuda):
+    """ops.sim_topk prepares a bank once per tensor (SimBank); the one-shot ABI call converts it inside the call.  Same
+    result; an in-place update of the bank tensor is seen (the cache keys on the tensor's version)."""
+    img, bank = W.unit_rows(33, 256, seed=1).to(cuda), W.unit_rows(777, 256, seed=2).to(cuda)
+    a = ops.sim_topk(img, bank, 5)
+    b = ops.sim_topk(img, bank, 5, cache_bank=False)
+    c = ops.sim_topk(img, bank, 5)
+    assert torch.equal(a[1], b[1]) and torch.equal(a[0], b[0]) and torch.equal(a[1], c[1])
+    bank[5] = img[0]
+    d = ops.sim_topk(img, bank, 5)
+    assert int(d[1][0, 0]) == 5 and abs(float(d[0][0, 0]) - 1.0) < 1e-5
+    # non-unit rows: the error bound scales with the norms
+    img2, bank2 = img * 7.5, bank * 0.01
+    ref_scores, ref_idx = tokenization_oracle.sim_topk(img2.cpu().numpy(), bank2.cpu().numpy(), 5)
+    _, idx = ops.sim_topk(img2, bank2, 5)
+    assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx)
+
+
 def test_sim_topk_errors(cuda):
     img, bank = W.unit_rows(4, 64, seed=0).to(cuda), W.unit_rows(10, 64, seed=1).to(cuda)
     with pytest.raises(RuntimeError):

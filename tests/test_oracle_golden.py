@@ -80,6 +80,28 @@ def test_preprocess_oracle_is_bit_identical_to_pil_fixture(golden_dir):
         assert np.array_equal(out[:, :, ::st, ::st], np.asarray(case["sample"], dtype=np.float32))
 
 
+def test_clip_preprocess_oracle_is_bit_identical_to_hf_processor_fixture(golden_dir):
+    """run_visual_tokenization.py:138-140: the restatement of transformers' CLIPImageProcessor (shortest edge 224 bicubic,
+    centre crop, rescale, normalise) reproduces the processor's own pixel_values exactly (SHA-256 of the float32 bytes)."""
+    import hashlib
+    for case in json.load(open(os.path.join(golden_dir, "clip_preprocess.json"))):
+        frames = W.u8_frames(2, case["H"], case["W"], seed=case["H"] * 7 + case["W"]).numpy()
+        out = np.stack([preprocess_oracle.clip_process_frame(f, case["S"]) for f in frames])
+        assert hashlib.sha256(np.ascontiguousarray(out).tobytes()).hexdigest() == case["sha256"], (case["H"], case["W"])
+        assert np.array_equal(out[:, :, ::56, ::56], np.asarray(case["sample"], dtype=np.float32))
+
+
+def test_clip_preprocess_oracle_vs_live_hf_processor():
+    import warnings
+    m = pytest.importorskip("transformers.models.clip.image_processing_pil_clip")
+    warnings.filterwarnings("ignore")
+    proc = m.CLIPImageProcessorPil()
+    for (H, Wd) in [(97, 131), (300, 200)]:
+        frame = W.u8_frames(1, H, Wd, seed=2).numpy()[0]
+        want = proc(images=[frame], return_tensors="np")["pixel_values"][0]
+        assert np.array_equal(want, preprocess_oracle.clip_process_frame(frame, 224))
+
+
 def test_preprocess_oracle_vs_live_pil():
     torchvision = pytest.importorskip("torchvision")
     from torchvision import transforms

@@ -12,6 +12,7 @@ from ctypes import POINTER, c_char_p, c_float, c_int32, c_int64, c_size_t, c_voi
 
 from . import build as _build
 
+ABI_VERSION = 2  # VIDIL_B200_ABI_VERSION of include/vidil_b200.h this binding was written against
 DTYPE_BF16, DTYPE_FP16 = 0, 1
 ACT_GELU_ERF, ACT_QUICK_GELU = 0, 1
 EPI_STORE, EPI_GELU, EPI_QUICKGELU, EPI_RESID, EPI_PATCH, EPI_STORE_F32 = range(6)
@@ -103,6 +104,9 @@ SIGNATURES = {
     "vidil_preprocess_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
     "vidil_preprocess_frames": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_float), POINTER(c_float),
                                           c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vidil_clip_preprocess_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32, c_int32]),
+    "vidil_clip_preprocess_frames": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_int32, POINTER(c_float), POINTER(c_float),
+                                               c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_encoder_set_profiling": (c_int32, [c_void_p, c_int32]),
     "vidil_encoder_read_profile": (c_int32, [c_void_p, POINTER(KernelStats)]),
     "vidil_encoder_host_scratch_bytes": (c_size_t, [c_void_p, c_int32]),
@@ -111,6 +115,10 @@ SIGNATURES = {
     "vidil_encoder_host_pipeline_scratch_bytes": (c_size_t, [c_void_p, c_int32]),
     "vidil_encoder_host_submit": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
     "vidil_encoder_host_wait": (c_int32, [c_void_p, c_int32]),
+    "vidil_sim_bank_create": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, POINTER(c_void_p)]),
+    "vidil_sim_bank_destroy": (None, [c_void_p]),
+    "vidil_sim_bank_topk_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
+    "vidil_sim_bank_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_sim_topk_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "vidil_sim_topk": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p,
                                  c_size_t, c_void_p]),
@@ -142,8 +150,8 @@ def load() -> ctypes.CDLL:
         fn = getattr(lib, name)  # AttributeError here means the .so is stale: rebuild with --force
         fn.restype = res
         fn.argtypes = args
-    if lib.vidil_abi_version() != 1:
-        raise RuntimeError(f"libvidil_b200.so ABI {lib.vidil_abi_version()} != 1; run python -m vidil_b200.build --force")
+    if lib.vidil_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"libvidil_b200.so ABI {lib.vidil_abi_version()} != {ABI_VERSION}; run python -m vidil_b200.build --force")
     _lib = lib
     return lib
 

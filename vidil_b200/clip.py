@@ -225,6 +225,14 @@ class CLIPVisionB200(nn.Module):
                 yield o0
 
 
+    def encode_u8_stream(self, batches_u8, outs=None):
+        """Decoded frames in, image_embeds out: `batches_u8` is an iterable of pinned CPU uint8 tensors [B, H, W, 3]; each
+        is uploaded as bytes, pre-processed on the GPU exactly as transformers' CLIPImageProcessor would
+        (vidil_clip_preprocess_frames) and encoded; uploads and downloads overlap the neighbouring batches' kernels."""
+        from . import preprocess
+        return preprocess.encode_u8_stream(self, batches_u8, self.cfg["image_size"], outs=outs, recipe="clip")
+
+
 class CLIPTextB200(nn.Module):
     """CLIP text tower + text_projection on the native path (vidil_clip_text_forward).  Parameters use transformers'
     CLIPModel key names (`text_model.*`, `text_projection.weight`)."""

@@ -815,10 +815,128 @@ int32_t vidil_encoder_host_wait(vidil_encoder* enc, int32_t slot) {
 }
 
 // ---- similarity + top-k ---------------------------------------------------------------------------
+// image_embeds @ text_embeds.t() -> per-frame top-k (run_visual_tokenization.py:276,306) without ever writing the [F, T]
+// score matrix: the fp16 tcgen05 GEMM's epilogue keeps the two best scores of every 32-phrase group (EPI_TOP2, 8 bytes per
+// group instead of 128), topk_select_kernel re-scores candidates in fp32 until the fp32 ranking is certain.
+}  // extern "C"
+
+struct vidil_sim_bank {
+    int T = 0, D = 0;
+    DevBuf bank16, bank32, max_norm;
+    // the GEMM of the last call (TMA maps encoded): a run scores batch after batch of the same size in the same workspace
+    mutable GemmProblem plan;
+    mutable int plan_F = 0;
+    mutable const void* plan_ws = nullptr;
+};
+
+namespace {
+
+inline int sim_groups(int T) { return (T + 31) / 32; }
+inline int sim_ld(int T) { return 2 * ((sim_groups(T) + 1) & ~1); }  // floats per row of the EPI_TOP2 output, 16-byte multiple
+
+struct SimWs {
+    size_t img16, top2, total;
+};
+SimWs sim_ws(int F, int T, int D) {
+    SimWs w;
+    w.img16 = 0;
+    w.top2 = align_up(static_cast<size_t>(F) * D * 2);
+    w.total = w.top2 + align_up(static_cast<size_t>(F) * sim_ld(T) * sizeof(float));
+    return w;
+}
+
+int sim_topk_core(const float* img, const void* bank16, const float* bank32, const float* max_norm_dev, int F, int T, int D, int k,
+                  float* out_scores, int32_t* out_idx, uint8_t* ws, cudaStream_t s, const vidil_sim_bank* cache = nullptr) {
+    const SimWs L = sim_ws(F, T, D);
+    void* img_h = ws + L.img16;
+    float* top2 = reinterpret_cast<float*>(ws + L.top2);
+    const int G = sim_groups(T);
+    // fp16 operands: unit-norm embeddings sit well inside fp16 range and keep 3 more mantissa bits than bf16
+    if (cast_run(img, img_h, DT_FP16, F, D, D, s)) return 1;
+    GemmProblem local;
+    GemmProblem& g = cache ? cache->plan : local;
+    if (cache == nullptr || cache->plan_F != F || cache->plan_ws != ws) {
+        g = GemmProblem();
+        g.dt = DT_FP16;
+        g.epi = EPI_TOP2;
+        g.cta_group = 2;
+        g.M = F; g.N = T; g.K = D;
+        g.A = img_h; g.lda = D;
+        g.W = bank16; g.ldw = D;
+        g.out = top2; g.ldo = sim_ld(T);
+        if (gemm_prepare(g)) return 1;
+        if (cache) {
+            cache->plan_F = F;
+            cache->plan_ws = ws;
+        }
+    }
+    if (gemm_run(g, s)) return 1;
+    return topk_select_run(top2, sim_ld(T), G, img, bank32, max_norm_dev, F, T, D, k, out_scores, out_idx, s);
+}
+
+int sim_check(const char* who, int F, int T, int D) {
+    if (F <= 0 || T <= 0 || D <= 0 || D % 64 != 0) {
+        set_error("%s: need F, T > 0 and D a positive multiple of 64 (F=%d T=%d D=%d)", who, F, T, D);
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t vidil_sim_bank_create(const float* bank, int32_t T, int32_t D, void* stream, vidil_sim_bank** out) {
+    if (bank == nullptr || out == nullptr) {
+        set_error("vidil_sim_bank_create: null argument");
+        return 1;
+    }
+    *out = nullptr;
+    if (sim_check("vidil_sim_bank_create", 1, T, D)) return 1;
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    std::unique_ptr<vidil_sim_bank> b(new vidil_sim_bank());
+    b->T = T;
+    b->D = D;
+    const size_t n = static_cast<size_t>(T) * D;
+    if (b->bank16.alloc(n * 2) || b->bank32.alloc(n * 4) || b->max_norm.alloc(sizeof(float))) return 1;
+    VIDIL_CUDA_OK(cudaMemcpyAsync(b->bank32.p, bank, n * 4, cudaMemcpyDeviceToDevice, s));
+    if (cast_run(bank, b->bank16.p, DT_FP16, T, D, D, s)) return 1;
+    if (max_row_norm_run(bank, T, D, reinterpret_cast<float*>(b->max_norm.p), s)) return 1;
+    *out = b.release();
+    return 0;
+}
+
+void vidil_sim_bank_destroy(vidil_sim_bank* bank) { delete bank; }
+
+size_t vidil_sim_bank_topk_workspace_bytes(const vidil_sim_bank* bank, int32_t F) {
+    if (bank == nullptr || F <= 0) return 0;
+    return sim_ws(F, bank->T, bank->D).total;
+}
+
+int32_t vidil_sim_bank_topk(const vidil_sim_bank* bank, const float* img, int32_t F, int32_t k, float* out_scores,
+                            int32_t* out_idx, void* workspace, size_t workspace_bytes, void* stream) {
+    if (bank == nullptr || img == nullptr || out_scores == nullptr || out_idx == nullptr || workspace == nullptr) {
+        set_error("vidil_sim_bank_topk: null argument");
+        return 1;
+    }
+    if (sim_check("vidil_sim_bank_topk", F, bank->T, bank->D)) return 1;
+    if (workspace_bytes < sim_ws(F, bank->T, bank->D).total || (reinterpret_cast<uintptr_t>(workspace) & (ALIGN - 1))) {
+        set_error("vidil_sim_bank_topk: workspace too small or not %zu-byte aligned", ALIGN);
+        return 1;
+    }
+    return sim_topk_core(img, bank->bank16.p, reinterpret_cast<const float*>(bank->bank32.p),
+                         reinterpret_cast<const float*>(bank->max_norm.p), F, bank->T, bank->D, k, out_scores, out_idx,
+                         reinterpret_cast<uint8_t*>(workspace), reinterpret_cast<cudaStream_t>(stream), bank);
+}
+
+// One-shot form: the bank is converted inside the call (workspace), nothing is cached.
 size_t vidil_sim_topk_workspace_bytes(int32_t F, int32_t T, int32_t D) {
     if (F <= 0 || T <= 0 || D <= 0) return 0;
-    return align_up(static_cast<size_t>(F) * D * 2) + align_up(static_cast<size_t>(T) * D * 2) +
-           align_up(static_cast<size_t>(F) * round_up(T, 4) * 4);
+    return sim_ws(F, T, D).total + align_up(static_cast<size_t>(T) * D * 2) + ALIGN;
 }
 
 int32_t vidil_sim_topk(const float* img, const float* bank, int32_t F, int32_t T, int32_t D, int32_t k, float* out_scores,
@@ -827,39 +945,19 @@ int32_t vidil_sim_topk(const float* img, const float* bank, int32_t F, int32_t T
         set_error("vidil_sim_topk: null argument");
         return 1;
     }
-    if (F <= 0 || T <= 0 || D <= 0 || D % 64 != 0) {
-        set_error("vidil_sim_topk: need F, T > 0 and D a positive multiple of 64 (F=%d T=%d D=%d)", F, T, D);
-        return 1;
-    }
+    if (sim_check("vidil_sim_topk", F, T, D)) return 1;
     if (workspace_bytes < vidil_sim_topk_workspace_bytes(F, T, D) || (reinterpret_cast<uintptr_t>(workspace) & (ALIGN - 1))) {
         set_error("vidil_sim_topk: workspace too small or not %zu-byte aligned", ALIGN);
         return 1;
     }
-    if (gemm_num_sms() == 0) {
-        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
-        return 1;
-    }
     cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
     uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
-    void* img_h = base;
-    void* bank_h = base + align_up(static_cast<size_t>(F) * D * 2);
-    float* scores = reinterpret_cast<float*>(base + align_up(static_cast<size_t>(F) * D * 2) +
-                                             align_up(static_cast<size_t>(T) * D * 2));
-    const int ld = round_up(T, 4);
-    // fp16 operands: unit-norm embeddings sit well inside fp16 range and keep 3 more mantissa bits than bf16
-    if (cast_run(img, img_h, DT_FP16, F, D, D, s)) return 1;
+    const size_t core = sim_ws(F, T, D).total;
+    void* bank_h = base + core;
+    float* max_norm = reinterpret_cast<float*>(base + core + align_up(static_cast<size_t>(T) * D * 2));
     if (cast_run(bank, bank_h, DT_FP16, T, D, D, s)) return 1;
-    GemmProblem g;
-    g.dt = DT_FP16;
-    g.epi = EPI_STORE_F32;
-    g.cta_group = 2;
-    g.M = F; g.N = T; g.K = D;
-    g.A = img_h; g.lda = D;
-    g.W = bank_h; g.ldw = D;
-    g.out = scores; g.ldo = ld;
-    if (gemm_prepare(g)) return 1;
-    if (gemm_run(g, s)) return 1;
-    return topk_rerank_run(scores, ld, img, bank, F, T, D, k, out_scores, out_idx, s);
+    if (max_row_norm_run(bank, T, D, max_norm, s)) return 1;
+    return sim_topk_core(img, bank_h, bank, max_norm, F, T, D, k, out_scores, out_idx, base, s);
 }
 
 // ---- frame pre-processing -------------------------------------------------------------------------------
@@ -880,6 +978,25 @@ int32_t vidil_preprocess_frames(const uint8_t* frames_u8, int32_t batch, int32_t
     }
     return preprocess_run(frames_u8, batch, in_h, in_w, out_size, mean3, std3, out, workspace, workspace_bytes,
                           reinterpret_cast<cudaStream_t>(stream));
+}
+
+size_t vidil_clip_preprocess_workspace_bytes(int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size) {
+    return clip_preprocess_workspace_bytes(batch, in_h, in_w, out_size);
+}
+
+int32_t vidil_clip_preprocess_frames(const uint8_t* frames_u8, int32_t batch, int32_t in_h, int32_t in_w, int32_t out_size,
+                                     const float* mean3, const float* std3, float* out, void* workspace, size_t workspace_bytes,
+                                     void* stream) {
+    if (frames_u8 == nullptr || mean3 == nullptr || std3 == nullptr || out == nullptr || workspace == nullptr) {
+        set_error("vidil_clip_preprocess_frames: null argument");
+        return 1;
+    }
+    if (gemm_num_sms() == 0) {
+        if (get_error()[0] == 0) set_error("no sm_100 CUDA device available");
+        return 1;
+    }
+    return clip_preprocess_run(frames_u8, batch, in_h, in_w, out_size, mean3, std3, out, workspace, workspace_bytes,
+                               reinterpret_cast<cudaStream_t>(stream));
 }
 
 void vidil_debug_set_attention_trace(void* dev_buf) { attention_set_trace(reinterpret_cast<long long*>(dev_buf)); }

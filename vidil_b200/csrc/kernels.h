@@ -20,7 +20,9 @@ enum EpiMode : int {
     EPI_RESID = 3,      // out[f32] += acc + bias                     (residual stream, vit.py:108-109)
     EPI_PATCH = 4,      // out[f32][frame*(P+1)+1+p] = acc + bias + pos[1+p]   (vit.py:182-187)
     EPI_STORE_F32 = 5,  // out[f32] = acc + bias
-    EPI_COUNT = 6
+    EPI_TOP2 = 6,       // out[f32][row][col / 32][2] = the two largest acc of every 32-column group, the column's position in the
+                        // group packed into the 5 low mantissa bits (similarity + top-k: the [M,N] scores are never written)
+    EPI_COUNT = 7
 };
 
 void set_error(const char* fmt, ...);
@@ -156,13 +158,23 @@ int uncast_run(const void* in, float* out, DType dt, int64_t n, cudaStream_t str
 size_t preprocess_workspace_bytes(int B, int H, int W, int S);
 int preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const float* mean, const float* stdv, float* out,
                    void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// transformers' CLIPImageProcessor (run_visual_tokenization.py:138-140): shortest edge -> S bicubic, centre crop S x S,
+// rescale by the double 1/255, normalise.
+size_t clip_preprocess_workspace_bytes(int B, int H, int W, int S);
+int clip_preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const float* mean, const float* stdv, float* out,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------
-// Top-k of each row of an fp32 score matrix with exact fp32 re-ranking of the candidates
-// (run_visual_tokenization.py:276,306).
+// Similarity top-k (run_visual_tokenization.py:276,306).
 // ---------------------------------------------------------------------------------------
-int topk_rerank_run(const float* scores, int64_t ld_scores, const float* img, const float* bank, int F, int T,
-                    int D, int k, float* out_scores, int32_t* out_idx, cudaStream_t stream);
+// Exact top-k from the EPI_TOP2 output of the similarity GEMM: top2 [F][G][2] fp32 (G = ceil(T / 32) groups, index-tagged
+// approximate scores), img [F, D] / bank [T, D] fp32 originals.  Candidates are taken in order of approximate score and
+// re-scored in fp32 until the best remaining approximate score + eps_scale * |img row| * bank_max_norm cannot reach the
+// k-th exact score; a group whose second-best is taken is re-scored completely (a third member may hide behind it).
+int topk_select_run(const float* top2, int ld_top2, int G, const float* img, const float* bank, const float* bank_max_norm_dev, int F, int T, int D,
+                    int k, float* out_scores, int32_t* out_idx, cudaStream_t stream);
+// max over rows of ||row||_2 of an fp32 [rows, D] matrix -> out[0] (device)
+int max_row_norm_run(const float* m, int rows, int D, float* out, cudaStream_t stream);
 
 // ---------------------------------------------------------------------------------------
 // med.py text stack (caption decoder / ITM encoder): SIMT kernels around the GEMMs (med.cu).

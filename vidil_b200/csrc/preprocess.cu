@@ -1,5 +1,6 @@
-// Frame pre-processing on the device: uint8 HWC frames -> PIL-identical antialiased bicubic resize to S x S -> / 255 ->
-// (x - mean) / std -> fp32 NCHW.  Reference: run_video_CapFilt.py:128-137 (process_frame: torchvision ToPILImage, Resize
+// Frame pre-processing on the device: uint8 HWC frames -> PIL-identical antialiased bicubic resize (BLIP: to S x S; CLIP:
+// shortest edge to S, then the centre S x S window) -> [0,1] -> (x - mean) / std -> fp32 NCHW.
+// Reference: run_visual_tokenization.py:138-140 (HF CLIPProcessor, PIL backend) and run_video_CapFilt.py:128-137 (process_frame: torchvision ToPILImage, Resize
 // BICUBIC, ToTensor, Normalize), whose resize arithmetic is Pillow's src/libImaging/Resample.c: double-precision weights
 // rounded to 22-bit fixed point, int32 accumulation from 1 << 21, >> 22, clip to [0, 255], horizontal pass rounded to uint8
 // before the vertical pass.  The integer work is reproduced exactly (bit-identical output); the weight tables are computed
@@ -79,10 +80,10 @@ __device__ __forceinline__ uint8_t clip8(int acc) {
     return static_cast<uint8_t>(v < 0 ? 0 : (v > 255 ? 255 : v));
 }
 
-// One block per (frame, source row): [W,3] -> [S,3].
+// One block per (frame, source row): [W,3] -> [S,3], output columns left .. left+S-1 of the resized row (centre crop).
 __global__ void __launch_bounds__(256)
     resize_rows_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ tmp, const int32_t* __restrict__ tab, int ksize,
-                       int W, int S) {
+                       int W, int S, int left) {
     extern __shared__ uint8_t srow[];
     const int64_t r = blockIdx.x;
     const uint8_t* src = in + r * W * 3;
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(256)
     uint8_t* dst = tmp + r * S * 3;
     for (int o = threadIdx.x; o < S * 3; o += blockDim.x) {
         const int xx = o / 3, c = o - xx * 3;
-        const int32_t* row = tab + static_cast<int64_t>(xx) * (2 + ksize);
+        const int32_t* row = tab + static_cast<int64_t>(xx + left) * (2 + ksize);
         const int xmin = row[0], n = row[1];
         int acc = 1 << (PRECISION_BITS - 1);
         for (int x = 0; x < n; ++x) acc += static_cast<int>(srow[(xmin + x) * 3 + c]) * row[2 + x];
@@ -106,15 +107,22 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// One thread per output pixel (all three channels): vertical pass + ToTensor + Normalize.
+// uint8 -> [0,1]: torchvision's ToTensor divides in float32; transformers' rescale multiplies by the double 1/255 and casts
+__device__ __forceinline__ float unit_scale(uint8_t v, bool f64) {
+    return f64 ? __double2float_rn(__dmul_rn(static_cast<double>(v), 1.0 / 255.0)) : __fdiv_rn(static_cast<float>(v), 255.0f);
+}
+
+// One thread per output pixel (all three channels): vertical pass (output rows top .. top+S_h-1 of the resized image) +
+// rescale + normalise.
 __global__ void __launch_bounds__(256)
     resize_cols_normalize_kernel(const uint8_t* __restrict__ tmp, float* __restrict__ out, const int32_t* __restrict__ tab,
-                                 int ksize, int H, int S_w, int S_h, float m0, float m1, float m2, float s0, float s1, float s2) {
+                                 int ksize, int H, int S_w, int S_h, int top, bool rescale_f64, float m0, float m1, float m2,
+                                 float s0, float s1, float s2) {
     const int xx = blockIdx.x * blockDim.x + threadIdx.x;
     const int yy = blockIdx.y;
     const int64_t b = blockIdx.z;
     if (xx >= S_w) return;
-    const int32_t* row = tab + static_cast<int64_t>(yy) * (2 + ksize);
+    const int32_t* row = tab + static_cast<int64_t>(yy + top) * (2 + ksize);
     const int ymin = row[0], n = row[1];
     int a0 = 1 << (PRECISION_BITS - 1), a1 = a0, a2 = a0;
     const uint8_t* p = tmp + ((b * H + ymin) * S_w + xx) * 3;
@@ -126,9 +134,9 @@ __global__ void __launch_bounds__(256)
         p += static_cast<int64_t>(S_w) * 3;
     }
     // ToTensor: uint8 -> float32 / 255; Normalize: (x - mean) / std, each a single IEEE float32 operation (no FMA contraction)
-    const float v0 = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(clip8(a0)), 255.0f), m0), s0);
-    const float v1 = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(clip8(a1)), 255.0f), m1), s1);
-    const float v2 = __fdiv_rn(__fsub_rn(__fdiv_rn(static_cast<float>(clip8(a2)), 255.0f), m2), s2);
+    const float v0 = __fdiv_rn(__fsub_rn(unit_scale(clip8(a0), rescale_f64), m0), s0);
+    const float v1 = __fdiv_rn(__fsub_rn(unit_scale(clip8(a1), rescale_f64), m1), s1);
+    const float v2 = __fdiv_rn(__fsub_rn(unit_scale(clip8(a2), rescale_f64), m2), s2);
     const int64_t plane = static_cast<int64_t>(S_h) * S_w;
     float* o = out + b * 3 * plane + static_cast<int64_t>(yy) * S_w + xx;
     o[0] = v0;
@@ -138,28 +146,50 @@ __global__ void __launch_bounds__(256)
 
 inline size_t align1k(size_t x) { return (x + 1023) / 1024 * 1024; }
 
-}  // namespace
+// Geometry of one pre-processing recipe: resize the [H, W] frame to [rh, rw], keep the S x S window at (top, left).
+struct Geometry {
+    int rh, rw, top, left;
+    bool rescale_f64;
+};
+// run_video_CapFilt.py:128-137: Resize((S, S)) — both sides to S, no crop, ToTensor's float32 division.
+Geometry blip_geometry(int, int, int S) { return Geometry{S, S, 0, 0, false}; }
+// transformers' CLIPImageProcessor (PIL backend) as run_visual_tokenization.py:138-140 calls it: shortest edge to S keeping
+// the aspect ratio (the long side is int(S * long / short), image_transforms.get_resize_output_image_size), centre crop
+// S x S at ((rh - S) // 2, (rw - S) // 2), rescale by the double 1/255.
+Geometry clip_geometry(int H, int W, int S) {
+    Geometry g;
+    if (W <= H) {
+        g.rw = S;
+        g.rh = static_cast<int>(static_cast<int64_t>(S) * H / W);
+    } else {
+        g.rh = S;
+        g.rw = static_cast<int>(static_cast<int64_t>(S) * W / H);
+    }
+    g.top = (g.rh - S) / 2;
+    g.left = (g.rw - S) / 2;
+    g.rescale_f64 = true;
+    return g;
+}
 
-size_t preprocess_workspace_bytes(int B, int H, int W, int S) {
-    if (B <= 0 || H <= 0 || W <= 0 || S <= 0) return 0;
-    const Coeffs& ch = coeffs_for(W, S);
-    const Coeffs& cv = coeffs_for(H, S);
+size_t workspace_for(int B, int H, int W, int S, const Geometry& g) {
+    const Coeffs& ch = coeffs_for(W, g.rw);
+    const Coeffs& cv = coeffs_for(H, g.rh);
     return align1k(static_cast<size_t>(B) * H * S * 3) + align1k(ch.table.size() * 4) + align1k(cv.table.size() * 4);
 }
 
-int preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const float* mean, const float* stdv, float* out,
-                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+int run_geometry(const uint8_t* frames, int B, int H, int W, int S, const Geometry& g, const float* mean, const float* stdv,
+                 float* out, void* workspace, size_t workspace_bytes, cudaStream_t stream) {
     if (B <= 0) return 0;
     if (H <= 0 || W <= 0 || S <= 0 || W * 3 > 200 * 1024) {
         set_error("preprocess: unsupported geometry H=%d W=%d S=%d", H, W, S);
         return 1;
     }
-    if (workspace_bytes < preprocess_workspace_bytes(B, H, W, S) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) {
+    if (workspace_bytes < workspace_for(B, H, W, S, g) || (reinterpret_cast<uintptr_t>(workspace) & 1023)) {
         set_error("preprocess: workspace too small or not 1024-byte aligned");
         return 1;
     }
-    const Coeffs& ch = coeffs_for(W, S);
-    const Coeffs& cv = coeffs_for(H, S);
+    const Coeffs& ch = coeffs_for(W, g.rw);
+    const Coeffs& cv = coeffs_for(H, g.rh);
     uint8_t* base = reinterpret_cast<uint8_t*>(workspace);
     uint8_t* tmp = base;
     int32_t* tab_h = reinterpret_cast<int32_t*>(base + align1k(static_cast<size_t>(B) * H * S * 3));
@@ -169,14 +199,34 @@ int preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const floa
     const size_t smem = static_cast<size_t>(W) * 3 + 16;
     // per launch (cheap): the attribute belongs to the current device's copy of the function
     VIDIL_CUDA_OK(cudaFuncSetAttribute(resize_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024 + 16));
-    resize_rows_kernel<<<B * H, 256, smem, stream>>>(frames, tmp, tab_h, ch.ksize, W, S);
+    resize_rows_kernel<<<B * H, 256, smem, stream>>>(frames, tmp, tab_h, ch.ksize, W, S, g.left);
     VIDIL_CUDA_OK(cudaGetLastError());
     const dim3 grid((S + 255) / 256, S, B);
-    resize_cols_normalize_kernel<<<grid, 256, 0, stream>>>(tmp, out, tab_v, cv.ksize, H, S, S, mean[0], mean[1], mean[2], stdv[0],
-                                                          stdv[1], stdv[2]);
+    resize_cols_normalize_kernel<<<grid, 256, 0, stream>>>(tmp, out, tab_v, cv.ksize, H, S, S, g.top, g.rescale_f64, mean[0],
+                                                          mean[1], mean[2], stdv[0], stdv[1], stdv[2]);
     VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(2);
     return 0;
+}
+
+}  // namespace
+
+size_t preprocess_workspace_bytes(int B, int H, int W, int S) {
+    if (B <= 0 || H <= 0 || W <= 0 || S <= 0) return 0;
+    return workspace_for(B, H, W, S, blip_geometry(H, W, S));
+}
+size_t clip_preprocess_workspace_bytes(int B, int H, int W, int S) {
+    if (B <= 0 || H <= 0 || W <= 0 || S <= 0) return 0;
+    return workspace_for(B, H, W, S, clip_geometry(H, W, S));
+}
+
+int preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const float* mean, const float* stdv, float* out,
+                   void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    return run_geometry(frames, B, H, W, S, blip_geometry(H, W, S), mean, stdv, out, workspace, workspace_bytes, stream);
+}
+int clip_preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const float* mean, const float* stdv, float* out,
+                        void* workspace, size_t workspace_bytes, cudaStream_t stream) {
+    return run_geometry(frames, B, H, W, S, clip_geometry(H, W, S), mean, stdv, out, workspace, workspace_bytes, stream);
 }
 
 }  // namespace vidil

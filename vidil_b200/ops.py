@@ -88,12 +88,73 @@ def attention(qkv: torch.Tensor, num_heads: int, scale: float | None = None, dty
     return out
 
 
-def sim_topk(image_embeds: torch.Tensor, text_embeds: torch.Tensor, k: int):
+class SimBank:
+    """A phrase bank prepared once for many `topk` calls (vidil_sim_bank_create): fp16 copy for the tensor cores, fp32 copy
+    for the exact re-scoring, largest row norm for the error bound — all owned by the native handle."""
+
+    def __init__(self, text_embeds: torch.Tensor):
+        import ctypes
+        self.lib = _lib.load()
+        bank = _dev_f32(text_embeds, "text_embeds")
+        self.T, self.D = bank.shape
+        self.device = bank.device
+        self.handle = ctypes.c_void_p()
+        self._ws = None   # workspace, kept between calls: same address -> the library reuses its encoded TMA maps
+        with torch.cuda.device(self.device):
+            st = self.lib.vidil_sim_bank_create(bank.data_ptr(), self.T, self.D, _stream(), ctypes.byref(self.handle))
+        _lib.check(st, "vidil_sim_bank_create")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                self.lib.vidil_sim_bank_destroy(self.handle)
+                self.handle = None
+        except Exception:  # noqa: BLE001 - interpreter teardown
+            pass
+
+    def topk(self, image_embeds: torch.Tensor, k: int):
+        img = _dev_f32(image_embeds, "image_embeds")
+        F, D = img.shape
+        assert D == self.D
+        scores = torch.empty(F, k, dtype=torch.float32, device=img.device)
+        idx = torch.empty(F, k, dtype=torch.int32, device=img.device)
+        if F == 0:
+            return scores, idx
+        with torch.cuda.device(img.device):
+            need = self.lib.vidil_sim_bank_topk_workspace_bytes(self.handle, F)
+            if self._ws is None or self._ws.numel() < need:
+                self._ws = _workspace(need, img.device)
+            ws = self._ws
+            st = self.lib.vidil_sim_bank_topk(self.handle, img.data_ptr(), F, k, scores.data_ptr(), idx.data_ptr(), ws.data_ptr(),
+                                              ws.numel(), _stream())
+        _lib.check(st, "vidil_sim_bank_topk")
+        return scores, idx
+
+
+_bank_cache: dict = {}
+
+
+def _cached_bank(text_embeds: torch.Tensor) -> SimBank:
+    """The phrase banks of a run are the same tensors call after call (visual_tokenization.tokens_from_embeddings): their
+    prepared form is cached on tensor identity + version.  The entry pins the tensor, so its address cannot be recycled."""
+    key = (text_embeds.data_ptr(), tuple(text_embeds.shape), tuple(text_embeds.stride()), text_embeds.dtype, text_embeds._version)
+    hit = _bank_cache.get(key)
+    if hit is None:
+        if len(_bank_cache) >= 16:
+            _bank_cache.pop(next(iter(_bank_cache)))
+        hit = (SimBank(text_embeds), text_embeds)
+        _bank_cache[key] = hit
+    return hit[0]
+
+
+def sim_topk(image_embeds: torch.Tensor, text_embeds: torch.Tensor, k: int, cache_bank: bool = True):
     """Top-k of image_embeds @ text_embeds.t() per row: (scores fp32 [F,k], indices int32 [F,k]), best first.
 
     Replaces `sims_matrix = image_embeds @ text_embeds.t()` + `.cpu().numpy()` + `np.argsort(...)[::-1][:k]`
-    (run_visual_tokenization.py:276,299,306) without materialising the matrix on the host.
-    """
+    (run_visual_tokenization.py:276,299,306): the [F,T] matrix is never written, on the device or the host.  With
+    cache_bank the phrase bank's fp16 / fp32 device copies are prepared once per bank tensor (SimBank)."""
+    if cache_bank:
+        return _cached_bank(text_embeds).topk(image_embeds, k)
     lib = _lib.load()
     img = _dev_f32(image_embeds, "image_embeds")
     bank = _dev_f32(text_embeds, "text_embeds")
