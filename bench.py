@@ -332,6 +332,19 @@ def run_vit(args):
     torch.cuda.synchronize()
     e2e_u8_fps = world * B * K / max_over_ranks(time.perf_counter() - t0)
 
+    # ---- the leanest host interface: uint8 frames up, 16-bit tokens down (vidil_vit_forward16): 59 + 103 MB per step instead
+    #      of 154 + 207 MB — what matters when eight ranks share one host's memory system
+    host_outs16 = [torch.empty(B, tokens, D, dtype=model.token_dtype16).pin_memory() for _ in range(2)]
+    for o in vpre.encode_u8_stream(model, (u8_in[i & 1] for i in range(3)), args.image_size, outs=host_outs16, half_tokens=True):
+        pass
+    barrier()
+    t0 = time.perf_counter()
+    for o in vpre.encode_u8_stream(model, (u8_in[i & 1] for i in range(K)), args.image_size, outs=host_outs16, half_tokens=True):
+        checksum += float(o[0, 0, 0])
+    torch.cuda.synchronize()
+    e2e_u8_16_fps = world * B * K / max_over_ranks(time.perf_counter() - t0)
+    del host_outs16
+
     # ---- the path's one collective: all-gather of per-rank result rows (JSON), rank-0 merge --------------------------
     t0 = time.perf_counter()
     rows = {f"rank{rank}_frame{i}": {"cls_l1": float(host_out[i, 0].abs().sum())} for i in range(0, B, 32)}
@@ -355,7 +368,10 @@ def run_vit(args):
                 "blocking_call_value": e2e_blocking_fps, "checksum": checksum,
                 "from_uint8_frames": {"value": e2e_u8_fps, "unit": "frames/s", "h2d_bytes_per_step": B * 240 * 320 * 3,
                                       "note": "decoded 320x240 uint8 frames in pinned memory; PIL-identical resize + "
-                                              "normalise on the GPU (vidil_preprocess_frames) inside the timed region"}},
+                                              "normalise on the GPU (vidil_preprocess_frames) inside the timed region"},
+                "from_uint8_frames_16bit_tokens": {"value": e2e_u8_16_fps, "unit": "frames/s", "h2d_bytes_per_step": B * 240 * 320 * 3,
+                                                   "d2h_bytes_per_step": B * tokens * D * 2,
+                                                   "note": "same, tokens delivered in the 16-bit operand type (vidil_vit_forward16)"}},
         "gpu_launches": launches,
         "roofline": {"bound": "tensor", "kernel": "gemm_tcgen05_kernel (patch-embed, qkv, proj, fc1, fc2: "
                                                   f"{g['launches'] // K} launches per step)",
@@ -487,12 +503,12 @@ def build_clip_models(args, ctx, want_text=True, dtype=None):
     from oracle import weights as W
     from vidil_b200.clip import CLIPTextB200, CLIPVisionB200
     torch.manual_seed(7)
-    vision = CLIPVisionB200(**W.CLIP_CONFIGS["large14"], compute_dtype=dtype or args.dtype)
+    vision = CLIPVisionB200(**W.CLIP_CONFIGS["large14"], compute_dtype=dtype or args.clip_dtype)
     _randomise(vision)
     vision = vision.to(ctx.dev).eval()
     text = None
     if want_text:
-        text = CLIPTextB200(**W.CLIP_TEXT_CONFIGS["large14"], compute_dtype=dtype or args.dtype)
+        text = CLIPTextB200(**W.CLIP_TEXT_CONFIGS["large14"], compute_dtype=dtype or args.clip_dtype)
         _randomise(text)
         text = text.to(ctx.dev).eval()
     return vision, text
@@ -521,6 +537,7 @@ def clip_record(args, ctx, vision, steps, warmup):
             "tflops_per_gpu": fps / ctx.world * gf / 1e3,
             "frac_of_sustained_peak": fps / ctx.world * gf / 1e3 / peaks["tflops_sustained"],
             "frac_of_burst_peak": fps / ctx.world * gf / 1e3 / peaks["tflops"],
+            "dtype": vision.compute_dtype,
             "config": {"workload": f"CLIP ViT-L/14 @224 image tower, batch {B} frames per GPU per step, device-resident"}}
 
 
@@ -1018,9 +1035,14 @@ def main():
     ap.add_argument("--vit", default="large", choices=list(VIT))
     ap.add_argument("--image-size", type=int, default=224)
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "fp16"])
+    ap.add_argument("--clip-dtype", default="fp16", choices=["bf16", "fp16"],
+                    help="operand type of the CLIP towers (fp16: fewest end-to-end top-k flips, see the sim record)")
     ap.add_argument("--ref-frames", type=int, default=8, help="--impl reference: frames per CPU step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    if os.environ.get("VIDIL_BENCH_WATCHDOG"):   # developer aid: dump every thread's Python stack and exit if the run stalls
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["VIDIL_BENCH_WATCHDOG"]), exit=True)
     if args.warmup < 3 and args.impl == "native":
         args.warmup = 3  # timing rule: at least 3 warm-up steps
     if args.impl == "reference":

@@ -97,6 +97,10 @@ int32_t vidil_encoder_tokens(const vidil_encoder* enc); /* P + 1 */
  * all tokens after the final LayerNorm (vit.py:192-194). */
 int32_t vidil_vit_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_tokens,
                           void* workspace, size_t workspace_bytes, void* stream);
+/* Same forward, tokens written in the handle's 16-bit operand type (bf16 / fp16) instead of fp32: for consumers that take
+ * 16-bit tokens anyway (this library's own text stack casts them on entry) and for host transfers — half the D2H bytes. */
+int32_t vidil_vit_forward16(vidil_encoder* enc, const float* frames, int32_t batch, void* out_tokens16, void* workspace,
+                            size_t workspace_bytes, void* stream);
 
 /* CLIP vision tower + visual_projection + L2 normalisation: frames -> image_embeds fp32 [B, proj_dim].
  * If out_hidden != NULL it also receives last_hidden_state (before post_layernorm) fp32 [B, P+1, D]. */
@@ -125,6 +129,10 @@ int32_t vidil_clip_forward_host(vidil_encoder* enc, const float* frames_host, in
 size_t  vidil_encoder_host_pipeline_scratch_bytes(const vidil_encoder* enc, int32_t batch);
 int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_host,
                                   int32_t slot, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+/* submit() with the ViT tokens delivered to the host in the handle's 16-bit operand type (out_host16: batch * tokens *
+ * embed_dim 16-bit values). */
+int32_t vidil_encoder_host_submit16(vidil_encoder* enc, const float* frames_host, int32_t batch, void* out_host16, int32_t slot,
+                                    void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 int32_t vidil_encoder_host_wait(vidil_encoder* enc, int32_t slot);
 
 /* ---- CLIP text tower (the phrase bank of run_visual_tokenization.py:84-96) ----------------------- */
@@ -305,6 +313,10 @@ int32_t vidil_op_layernorm(const float* in, const float* gamma, const float* bet
 size_t  vidil_op_attention_workspace_bytes(int32_t B, int32_t N, int32_t H);
 int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype,
                            void* workspace, size_t workspace_bytes, void* stream);
+/* Same with a causal mask (query i attends to keys 0..i): the CLIP text tower's attention
+ * (run_visual_tokenization.py:84-96 through transformers' CLIPTextTransformer).  N <= 208. */
+int32_t vidil_op_attention_causal(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype,
+                                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- developer hooks ---------------------------------------------------------------------------- */
 /* dev_buf: device buffer of 5*16*8 int64 (or NULL to switch off).  While set, CTA 0 of the tcgen05 attention kernel

@@ -29,6 +29,45 @@ import torch
 import torch.nn.functional as F
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Operand-dtype emulation.  The native path keeps the residual stream, LayerNorm / softmax statistics and every accumulator
+# in fp32 but feeds the tensor cores 16-bit operands and stores qkv / attention output / GELU hidden / cross K,V in 16 bits.
+# With `operand_dtype` set (torch.bfloat16 or torch.float16, see `emulate`) the functions below round at exactly those
+# points — weights and activations entering a Linear, the stored projections, the probabilities entering P @ V, the
+# tensors between LM-head stages — and compute everything else in fp32 like the default oracle.  What remains between this
+# emulation and the kernels is accumulation order and the approximate exp / erf (~1e-5 on BERT-base logits instead of the
+# ~0.2 that bf16 operand rounding alone causes), so caption TOKENS can be asserted equal (tests/test_gpu_med.py); the plain
+# fp32 oracle stays the reference restatement and the reported statistic.
+# ----------------------------------------------------------------------------------------------------------------------
+_OPERAND_DTYPE = None
+
+
+class emulate:
+    """with med_oracle.emulate(torch.bfloat16): ... — round 16-bit operands / stored tensors like the native kernels."""
+
+    def __init__(self, dtype):
+        self.dtype = dtype
+
+    def __enter__(self):
+        global _OPERAND_DTYPE
+        self.prev, _OPERAND_DTYPE = _OPERAND_DTYPE, self.dtype
+        return self
+
+    def __exit__(self, *exc):
+        global _OPERAND_DTYPE
+        _OPERAND_DTYPE = self.prev
+
+
+def _r(x: torch.Tensor) -> torch.Tensor:
+    """Round to the emulated operand dtype (identity for the default fp32 oracle)."""
+    return x if _OPERAND_DTYPE is None else x.to(_OPERAND_DTYPE).to(torch.float32)
+
+
+def _linear(x, w, b):
+    """A Linear as the tensor cores see it: 16-bit x and w (when emulating), exact products, fp32 accumulation, fp32 bias."""
+    return F.linear(_r(x), _r(w), b)
+
+
 def embeddings(sd: dict, pre: str, input_ids: torch.Tensor, past_len: int, eps: float) -> torch.Tensor:
     """BertEmbeddings.forward, med.py:74-96: word + absolute position -> LayerNorm (no token-type term)."""
     T = input_ids.shape[1]
@@ -46,9 +85,9 @@ def _heads(x: torch.Tensor, H: int) -> torch.Tensor:
 def attention_block(sd: dict, p: str, x: torch.Tensor, kv_src: torch.Tensor, add_mask, H: int, eps: float, past=None):
     """BertAttention = BertSelfAttention (med.py:146-232) + BertSelfOutput (:235-246).
     `kv_src` is x for self-attention, the image tokens for cross-attention; `past` = (K, V) of earlier positions."""
-    q = _heads(F.linear(x, sd[p + "self.query.weight"], sd[p + "self.query.bias"]), H)
-    k = _heads(F.linear(kv_src, sd[p + "self.key.weight"], sd[p + "self.key.bias"]), H)
-    v = _heads(F.linear(kv_src, sd[p + "self.value.weight"], sd[p + "self.value.bias"]), H)
+    q = _heads(_r(_linear(x, sd[p + "self.query.weight"], sd[p + "self.query.bias"])), H)
+    k = _heads(_r(_linear(kv_src, sd[p + "self.key.weight"], sd[p + "self.key.bias"])), H)
+    v = _heads(_r(_linear(kv_src, sd[p + "self.value.weight"], sd[p + "self.value.bias"])), H)
     if past is not None:
         k = torch.cat([past[0], k], dim=2)                                                     # :173-174
         v = torch.cat([past[1], v], dim=2)
@@ -56,8 +95,8 @@ def attention_block(sd: dict, p: str, x: torch.Tensor, kv_src: torch.Tensor, add
     if add_mask is not None:
         s = s + add_mask                                                                       # :205
     pr = s.softmax(dim=-1)                                                                     # :208
-    ctx = (pr @ v).permute(0, 2, 1, 3).reshape(x.shape)                                        # :222-226
-    out = F.linear(ctx, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
+    ctx = _r((_r(pr) @ v).permute(0, 2, 1, 3).reshape(x.shape))                                # :222-226
+    out = _linear(ctx, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
     D = x.shape[-1]
     out = F.layer_norm(out + x, (D,), sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], eps)  # :245
     return out, (k, v)
@@ -68,8 +107,8 @@ def layer(sd: dict, p: str, x, self_mask, enc, H: int, eps: float, past=None, mo
     x, present = attention_block(sd, p + "attention.", x, x, self_mask, H, eps, past)
     if mode == "multimodal":
         x, _ = attention_block(sd, p + "crossattention.", x, enc, None, H, eps)                # all-ones image mask
-    h = F.gelu(F.linear(x, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"]))   # :297-303
-    h = F.linear(h, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
+    h = _r(F.gelu(_linear(x, sd[p + "intermediate.dense.weight"], sd[p + "intermediate.dense.bias"])))   # :297-303
+    h = _linear(h, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
     D = x.shape[-1]
     x = F.layer_norm(h + x, (D,), sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], eps)   # :316
     return x, present
@@ -108,10 +147,10 @@ def bert_forward(sd: dict, pre: str, input_ids, attention_mask, enc, H: int, dep
 def lm_head(sd: dict, pre: str, x: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
     """BertOnlyMLMHead, med.py:501-541: dense -> GELU -> LayerNorm -> decoder (+ output-only bias)."""
     c = pre + "cls.predictions."
-    h = F.gelu(F.linear(x, sd[c + "transform.dense.weight"], sd[c + "transform.dense.bias"]))
+    h = _r(F.gelu(_linear(x, sd[c + "transform.dense.weight"], sd[c + "transform.dense.bias"])))
     D = h.shape[-1]
-    h = F.layer_norm(h, (D,), sd[c + "transform.LayerNorm.weight"], sd[c + "transform.LayerNorm.bias"], eps)
-    return F.linear(h, sd[c + "decoder.weight"], sd[c + "bias"])
+    h = _r(F.layer_norm(h, (D,), sd[c + "transform.LayerNorm.weight"], sd[c + "transform.LayerNorm.bias"], eps))
+    return _linear(h, sd[c + "decoder.weight"], sd[c + "bias"])
 
 
 def decoder_logits(sd: dict, pre: str, input_ids, image_embeds, H: int, depth: int, past=None):
@@ -123,7 +162,7 @@ def decoder_logits(sd: dict, pre: str, input_ids, image_embeds, H: int, depth: i
 def itm_logits(sd: dict, image_embeds, input_ids, attention_mask, H: int, depth: int) -> torch.Tensor:
     """BLIP_ITM.forward(match_head='itm'), blip_itm.py:49-57: multimodal encoder -> itm_head on the [CLS]/[ENC] row."""
     x, _ = bert_forward(sd, "text_encoder.", input_ids, attention_mask, image_embeds, H, depth, causal=False)
-    return F.linear(x[:, 0, :], sd["itm_head.weight"], sd["itm_head.bias"])
+    return F.linear(x[:, 0, :], sd["itm_head.weight"], sd["itm_head.bias"])   # fp32 SIMT head in the native path too
 
 
 # ----------------------------------------------------------------------------------------------------------------------
@@ -238,9 +277,13 @@ def beam_search_from_logits(step_logits, batch: int, prompt: list, num_beams: in
 @torch.no_grad()
 def generate(sd: dict, image_embeds: torch.Tensor, prompt: list, H: int, depth: int, pre: str = "text_decoder.",
              num_beams: int = 3, max_length: int = 20, min_length: int = 5, eos: int = 102, pad: int = 0,
-             length_penalty: float = 1.0, device=None):
+             length_penalty: float = 1.0, device=None, operand_dtype=None):
     """BLIP_Decoder.generate(sample=False), blip.py:127-167, from the image tokens on: repeat_interleave the image
     tokens over the beams (:130), run the cached decoder (prepare_inputs_for_generation / _reorder_cache, med.py:929-955)."""
+    if operand_dtype is not None:
+        with emulate(operand_dtype):
+            return generate(sd, image_embeds, prompt, H, depth, pre, num_beams, max_length, min_length, eos, pad, length_penalty,
+                            device, None)
     B = image_embeds.shape[0]
     dev = image_embeds.device if device is None else device   # `device`: where sd / image_embeds live (bench.py's eager-GPU baseline)
     enc = image_embeds.repeat_interleave(num_beams, dim=0)

@@ -113,6 +113,22 @@ def test_attention(cuda, B, N, H, dtype):
     assert err.mean().item() < (2e-3 if dtype == "bf16" else 3e-4)
 
 
+@pytest.mark.parametrize("B,N,H,dtype", [(3, 77, 12, "bf16"), (2, 5, 2, "fp16"), (2, 197, 4, "bf16"), (1, 130, 2, "fp16"),
+                                         (65, 77, 12, "fp16"), (2, 33, 1, "bf16")])
+def test_attention_causal(cuda, B, N, H, dtype):
+    """The CLIP text tower's mask (query i attends to keys 0..i): per-lane different key counts inside one warp, one and two
+    query tiles."""
+    torch.manual_seed(N)
+    qkv = torch.randn(B, N, 3 * H * 64, device=cuda)
+    got = ops.attention(qkv, H, dtype=dtype, causal=True)
+    q, k, v = qkv.view(B, N, 3, H, 64).permute(2, 0, 3, 1, 4).double()
+    s = q @ k.transpose(-1, -2) * 0.125
+    s = s.masked_fill(torch.triu(torch.ones(N, N, dtype=torch.bool, device=cuda), 1), float("-inf"))
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B, N, H * 64)
+    err = (got.double() - ref).abs().max().item()
+    assert err < (3e-3 if dtype == "fp16" else 2.5e-2), err
+
+
 def test_attention_large_logits_are_stable(cuda):
     qkv = torch.randn(1, 197, 3 * 64, generator=torch.Generator().manual_seed(1)).to(cuda) * 30
     got = ops.attention(qkv, 1, dtype="bf16")

@@ -211,6 +211,26 @@ def test_vit_host_stream_ragged_and_growing_batches(cuda):
             assert torch.equal(a, b)
 
 
+def test_vit_16bit_token_output(cuda):
+    """vidil_vit_forward16 / host_submit16: the final LayerNorm rounds to the operand type instead of writing fp32 — the
+    16-bit tokens equal the fp32 tokens rounded once, on the device call, the host stream and the uint8 stream."""
+    from vidil_b200 import preprocess
+    for dtype, tdt in (("bf16", torch.bfloat16), ("fp16", torch.float16)):
+        m, _ = _build("tiny", 32, dtype, cuda)
+        x = W.frames(5, 32, seed=11)
+        full = m(x.to(cuda))
+        half = m.forward_tokens16(x.to(cuda))
+        assert half.dtype == tdt and torch.equal(half, full.to(tdt))
+        batches = [W.frames(b, 32, seed=60 + i).pin_memory() for i, b in enumerate([4, 4, 3])]
+        got = [o.clone() for o in m.encode_host_stream(iter(batches), half_tokens=True)]
+        for g, b in zip(got, batches):
+            assert g.dtype == tdt and torch.equal(g, m(b.to(cuda)).to(tdt).cpu())
+        u8 = [W.u8_frames(3, 40, 56, seed=70 + i).pin_memory() for i in range(3)]
+        got = [o.clone() for o in preprocess.encode_u8_stream(m, iter(u8), 32, half_tokens=True)]
+        for g, b in zip(got, u8):
+            assert g.dtype == tdt and torch.equal(g, m(preprocess.process_frames(b.to(cuda), 32)).to(tdt).cpu())
+
+
 def test_native_library_is_the_path(cuda):
     m, _ = _build("tiny", 32, "bf16", cuda)
     x = W.frames(2, 32, seed=0).to(cuda)

@@ -78,6 +78,7 @@ SIGNATURES = {
     "vidil_encoder_workspace_bytes": (c_size_t, [c_void_p, c_int32]),
     "vidil_encoder_tokens": (c_int32, [c_void_p]),
     "vidil_vit_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "vidil_vit_forward16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_clip_forward": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_text_encoder_create": (c_int32, [POINTER(TextCfg), POINTER(c_void_p)]),
     "vidil_text_encoder_destroy": (None, [c_void_p]),
@@ -114,6 +115,7 @@ SIGNATURES = {
     "vidil_clip_forward_host": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "vidil_encoder_host_pipeline_scratch_bytes": (c_size_t, [c_void_p, c_int32]),
     "vidil_encoder_host_submit": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
+    "vidil_encoder_host_submit16": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_int32, c_void_p, c_size_t, c_void_p]),
     "vidil_encoder_host_wait": (c_int32, [c_void_p, c_int32]),
     "vidil_sim_bank_create": (c_int32, [c_void_p, c_int32, c_int32, c_void_p, POINTER(c_void_p)]),
     "vidil_sim_bank_destroy": (None, [c_void_p]),
@@ -130,6 +132,8 @@ SIGNATURES = {
     "vidil_op_attention_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
     "vidil_op_attention": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p,
                                      c_size_t, c_void_p]),
+    "vidil_op_attention_causal": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_int32, c_void_p,
+                                            c_size_t, c_void_p]),
 }
 
 _lib = None

@@ -605,8 +605,8 @@ size_t vidil_encoder_workspace_bytes(const vidil_encoder* enc, int32_t batch) {
 
 int32_t vidil_encoder_tokens(const vidil_encoder* enc) { return enc ? enc->tokens : 0; }
 
-int32_t vidil_vit_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_tokens, void* workspace,
-                          size_t workspace_bytes, void* stream) {
+static int vit_forward_any(vidil_encoder* enc, const float* frames, int32_t batch, void* out_tokens, bool out_f32, void* workspace,
+                           size_t workspace_bytes, void* stream) {
     if (check_common(enc, frames, batch, out_tokens, workspace, workspace_bytes)) return 1;
     if (enc->cfg.proj_dim > 0 || enc->cfg.pre_ln) {
         set_error("vidil_vit_forward: this handle is a CLIP-style tower; use vidil_clip_forward");
@@ -616,7 +616,17 @@ int32_t vidil_vit_forward(vidil_encoder* enc, const float* frames, int32_t batch
     Plan* pl = get_plan(enc, batch, workspace);
     if (pl == nullptr) return 1;
     if (run_trunk(enc, *pl, frames, s)) return 1;
-    return ln_timed(enc, s, pl->resid, enc->cfg.embed_dim, enc->norm_w, enc->norm_b, out_tokens, true, batch * enc->tokens);
+    return ln_timed(enc, s, pl->resid, enc->cfg.embed_dim, enc->norm_w, enc->norm_b, out_tokens, out_f32, batch * enc->tokens);
+}
+
+int32_t vidil_vit_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_tokens, void* workspace,
+                          size_t workspace_bytes, void* stream) {
+    return vit_forward_any(enc, frames, batch, out_tokens, true, workspace, workspace_bytes, stream);
+}
+
+int32_t vidil_vit_forward16(vidil_encoder* enc, const float* frames, int32_t batch, void* out_tokens16, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+    return vit_forward_any(enc, frames, batch, out_tokens16, false, workspace, workspace_bytes, stream);
 }
 
 int32_t vidil_clip_forward(vidil_encoder* enc, const float* frames, int32_t batch, float* out_embeds, float* out_hidden,
@@ -729,8 +739,8 @@ size_t vidil_encoder_host_pipeline_scratch_bytes(const vidil_encoder* enc, int32
     return 2 * (in + out_tok) + ws_layout(enc, batch).total;
 }
 
-int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_host, int32_t slot,
-                                  void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+static int host_submit_any(vidil_encoder* enc, const float* frames_host, int32_t batch, void* out_host, bool out16, int32_t slot,
+                           void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
     if (enc == nullptr || frames_host == nullptr || out_host == nullptr || dev_scratch == nullptr || batch <= 0) {
         set_error("vidil_encoder_host_submit: null argument or empty batch");
         return 1;
@@ -793,8 +803,8 @@ int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, 
         if (vidil_clip_forward(enc, d_in, batch, d_out, nullptr, ws, ws_bytes, stream)) return 1;
         out_bytes = static_cast<size_t>(batch) * enc->cfg.proj_dim * 4;
     } else {
-        if (vidil_vit_forward(enc, d_in, batch, d_out, ws, ws_bytes, stream)) return 1;
-        out_bytes = out_tok_bytes;
+        if (vit_forward_any(enc, d_in, batch, d_out, !out16, ws, ws_bytes, stream)) return 1;
+        out_bytes = out16 ? out_tok_bytes / 2 : out_tok_bytes;
     }
     VIDIL_CUDA_OK(cudaEventRecord(enc->ev_compute[slot], s));
     // D2H on the other copy engine
@@ -802,6 +812,20 @@ int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, 
     VIDIL_CUDA_OK(cudaMemcpyAsync(out_host, d_out, out_bytes, cudaMemcpyDeviceToHost, enc->copy_out));
     VIDIL_CUDA_OK(cudaEventRecord(enc->ev_out[slot], enc->copy_out));
     return 0;
+}
+
+int32_t vidil_encoder_host_submit(vidil_encoder* enc, const float* frames_host, int32_t batch, float* out_host, int32_t slot,
+                                  void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+    return host_submit_any(enc, frames_host, batch, out_host, false, slot, dev_scratch, dev_scratch_bytes, stream);
+}
+
+int32_t vidil_encoder_host_submit16(vidil_encoder* enc, const float* frames_host, int32_t batch, void* out_host16, int32_t slot,
+                                    void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+    if (enc != nullptr && enc->cfg.proj_dim > 0) {
+        set_error("vidil_encoder_host_submit16: 16-bit output is for token outputs (ViT handles); CLIP embeds stay fp32");
+        return 1;
+    }
+    return host_submit_any(enc, frames_host, batch, out_host16, true, slot, dev_scratch, dev_scratch_bytes, stream);
 }
 
 int32_t vidil_encoder_host_wait(vidil_encoder* enc, int32_t slot) {
@@ -1073,8 +1097,8 @@ size_t vidil_op_attention_workspace_bytes(int32_t B, int32_t N, int32_t H) {
     return align_up(rows * 3 * H * 64 * 2) + align_up(rows * H * 64 * 2);
 }
 
-int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype,
-                           void* workspace, size_t workspace_bytes, void* stream) {
+static int op_attention_any(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype, bool causal,
+                            void* workspace, size_t workspace_bytes, void* stream) {
     if (qkv == nullptr || out == nullptr || workspace == nullptr) {
         set_error("vidil_op_attention: null argument");
         return 1;
@@ -1095,9 +1119,14 @@ int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, i
     void* qkv_h = base;
     void* out_h = base + align_up(static_cast<size_t>(rows) * 3 * H * 64 * 2);
     if (cast_run(qkv, qkv_h, dt, rows, 3 * H * 64, 3 * H * 64, s)) return 1;
+    if (causal && !attention_tc_supported(N)) {
+        set_error("vidil_op_attention_causal: the causal mask is implemented for sequences of at most 208 tokens (N=%d)", N);
+        return 1;
+    }
     if (attention_tc_supported(N)) {
         AttentionMaps maps;
         if (attention_tc_prepare(maps, qkv_h, out_h, dt, B, N, H)) return 1;
+        maps.causal = causal;
         if (attention_tc_run(maps, scale, s)) return 1;
     } else if (attention_tcl_supported(N)) {
         AttentionMaps maps;
@@ -1107,6 +1136,16 @@ int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, i
         return 1;
     }
     return uncast_run(out_h, out, dt, rows * H * 64, s);
+}
+
+int32_t vidil_op_attention(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+    return op_attention_any(qkv, out, B, N, H, scale, dtype, false, workspace, workspace_bytes, stream);
+}
+
+int32_t vidil_op_attention_causal(const float* qkv, float* out, int32_t B, int32_t N, int32_t H, float scale, int32_t dtype,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+    return op_attention_any(qkv, out, B, N, H, scale, dtype, true, workspace, workspace_bytes, stream);
 }
 
 }  // extern "C"

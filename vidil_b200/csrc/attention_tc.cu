@@ -146,7 +146,9 @@ __device__ __forceinline__ void chunk_exp_impl(const uint32_t (&r)[W], int c0, i
 template <typename T, int W, int POLY>
 __device__ __forceinline__ void chunk_exp(const uint32_t (&r)[W], int c0, int nv, float c, float neg_mxs, uint32_t taddr_p,
                                           float (&sum)[4]) {
-    if (c0 + W <= nv)
+    // warp-uniform choice: both variants end in a tcgen05.st.sync.aligned, which the whole warp must execute together (under a
+    // causal mask nv differs from lane to lane; the masked variant is correct for every lane)
+    if (__all_sync(0xffffffffu, c0 + W <= nv))
         chunk_exp_impl<T, W, false, POLY>(r, c0, nv, c, neg_mxs, taddr_p, sum);
     else
         chunk_exp_impl<T, W, true, POLY>(r, c0, nv, c, neg_mxs, taddr_p, sum);

@@ -71,8 +71,9 @@ def layernorm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: fl
     return out
 
 
-def attention(qkv: torch.Tensor, num_heads: int, scale: float | None = None, dtype: str = "bf16") -> torch.Tensor:
-    """qkv [B, N, 3*H*64] (the fused-QKV Linear output, models/vit.py:72) -> [B, N, H*64]."""
+def attention(qkv: torch.Tensor, num_heads: int, scale: float | None = None, dtype: str = "bf16", causal: bool = False) -> torch.Tensor:
+    """qkv [B, N, 3*H*64] (the fused-QKV Linear output, models/vit.py:72) -> [B, N, H*64].  causal: query i sees keys 0..i
+    (the CLIP text tower)."""
     lib = _lib.load()
     qkv = _dev_f32(qkv, "qkv")
     B, N, C3 = qkv.shape
@@ -82,8 +83,8 @@ def attention(qkv: torch.Tensor, num_heads: int, scale: float | None = None, dty
         scale = 64 ** -0.5
     out = torch.empty(B, N, H * 64, dtype=torch.float32, device=qkv.device)
     ws = _workspace(lib.vidil_op_attention_workspace_bytes(B, N, H), qkv.device)
-    st = lib.vidil_op_attention(qkv.data_ptr(), out.data_ptr(), B, N, H, float(scale), _lib.DTYPES[dtype], ws.data_ptr(),
-                                ws.numel(), _stream())
+    fn = lib.vidil_op_attention_causal if causal else lib.vidil_op_attention
+    st = fn(qkv.data_ptr(), out.data_ptr(), B, N, H, float(scale), _lib.DTYPES[dtype], ws.data_ptr(), ws.numel(), _stream())
     _lib.check(st, "vidil_op_attention")
     return out
 

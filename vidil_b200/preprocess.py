@@ -111,11 +111,12 @@ def process_frame(frame, config, device):
 
 
 @torch.no_grad()
-def encode_u8_stream(visual_encoder, batches_u8, image_size: int, outs=None, recipe: str = "blip"):
+def encode_u8_stream(visual_encoder, batches_u8, image_size: int, outs=None, recipe: str = "blip", half_tokens: bool = False):
     """Decoded frames in, tokens out, nothing else on the host: `batches_u8` is an iterable of pinned CPU uint8 tensors
     [B, H, W, 3]; each is copied to the device on a side stream, resized / normalised there (process_frames), encoded by
     `visual_encoder` (a vidil_b200 VisionTransformer) and its [B, N+1, D] tokens copied back to pinned host memory on the
-    side stream.  Batch k+1's upload and batch k-1's download overlap batch k's kernels.  Yields one CPU tensor per batch,
+    side stream (half_tokens: in the encoder's 16-bit operand type, half the bytes).  Batch k+1's upload and batch k-1's
+    download overlap batch k's kernels.  Yields one CPU tensor per batch,
     in order; with `outs` (two pinned tensors) the yielded tensor is only valid until two batches later."""
     dev = next(visual_encoder.parameters()).device
     if dev.type != "cuda":
@@ -147,7 +148,7 @@ def encode_u8_stream(visual_encoder, batches_u8, image_size: int, outs=None, rec
             x = process_frames(dev_u8[slot], image_size, recipe=recipe)
             freed[slot] = torch.cuda.Event()
             freed[slot].record(main)
-            tokens = visual_encoder(x)
+            tokens = visual_encoder.forward_tokens16(x) if half_tokens else visual_encoder(x)
             done = torch.cuda.Event()
             done.record(main)
             host = outs[slot] if outs is not None else torch.empty(tokens.shape, dtype=tokens.dtype, pin_memory=True)

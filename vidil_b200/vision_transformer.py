@@ -116,8 +116,9 @@ class NativeEncoder:
         """Enqueue H2D -> forward -> D2H of one host batch into `slot` (0/1); returns immediately."""
         B = frames.shape[0]
         scratch = self.pipeline_scratch(B, device)
-        st = self.lib.vidil_encoder_host_submit(self.handle, frames.data_ptr(), B, out.data_ptr(), slot, scratch.data_ptr(),
-                                                scratch.numel(), torch.cuda.current_stream().cuda_stream)
+        fn = self.lib.vidil_encoder_host_submit if out.dtype == torch.float32 else self.lib.vidil_encoder_host_submit16
+        st = fn(self.handle, frames.data_ptr(), B, out.data_ptr(), slot, scratch.data_ptr(), scratch.numel(),
+                torch.cuda.current_stream().cuda_stream)
         _lib.check(st, "vidil_encoder_host_submit")
 
     def host_wait(self, slot: int) -> None:
@@ -274,6 +275,34 @@ class VisionTransformer(nn.Module):
                 self._cache_key, self._cache_out, self._cache_in = key, out, x_orig
         return out
 
+    _TORCH_DTYPES = {"bf16": torch.bfloat16, "bfloat16": torch.bfloat16, "fp16": torch.float16, "float16": torch.float16,
+                     "half": torch.float16}
+
+    @property
+    def token_dtype16(self) -> torch.dtype:
+        """torch dtype of the 16-bit token output (the handle's tensor-core operand type)."""
+        return self._TORCH_DTYPES[self.compute_dtype]
+
+    @torch.no_grad()
+    def forward_tokens16(self, x: torch.Tensor) -> torch.Tensor:
+        """frames [B,3,S,S] (CUDA) -> tokens [B, N+1, D] in the 16-bit operand type (vidil_vit_forward16): the final LayerNorm
+        writes 16 bits instead of fp32.  For consumers that take 16-bit tokens anyway and for host transfers."""
+        if not x.is_cuda:
+            raise RuntimeError("vidil_b200: frames must be on a CUDA device")
+        _check_frames(x, self.img_size)
+        with torch.cuda.device(x.device):
+            enc = self._ensure_packed()
+            x = x.contiguous().float()
+            B = x.shape[0]
+            out = torch.empty(B, enc.tokens, self.embed_dim, dtype=self.token_dtype16, device=x.device)
+            if B == 0:
+                return out
+            ws = enc.workspace(B, x.device)
+            st = enc.lib.vidil_vit_forward16(enc.handle, x.data_ptr(), B, out.data_ptr(), ws.data_ptr(), ws.numel(),
+                                             torch.cuda.current_stream().cuda_stream)
+            _lib.check(st, "vidil_vit_forward16")
+        return out
+
     @torch.no_grad()
     def encode_host(self, frames: torch.Tensor, out: torch.Tensor | None = None) -> torch.Tensor:
         """Host-buffer call: frames is a CPU fp32 tensor (pinned for full PCIe rate); the result comes back as a
@@ -297,8 +326,9 @@ class VisionTransformer(nn.Module):
         return out
 
     @torch.no_grad()
-    def encode_host_stream(self, batches, outs=None):
-        """Encode a stream of host batches with copies overlapped with compute.
+    def encode_host_stream(self, batches, outs=None, half_tokens: bool = False):
+        """Encode a stream of host batches with copies overlapped with compute.  half_tokens: deliver the tokens in the
+        16-bit operand type (token_dtype16) — half the device-to-host bytes.
 
         `batches`: iterable of CPU fp32 tensors [B,3,S,S] (pinned for full PCIe rate; B may vary — a ragged last batch
         reuses the slots of the full ones, a larger batch drains the pipeline and re-binds it).  Yields one CPU
@@ -322,8 +352,11 @@ class VisionTransformer(nn.Module):
                     s0, o0, _ = pending.pop(0)
                     enc.host_wait(s0)
                     yield o0
-                out = outs[slot] if outs is not None else torch.empty(frames.shape[0], enc.tokens, self.embed_dim,
-                                                                      dtype=torch.float32, pin_memory=True)
+                out = outs[slot] if outs is not None else torch.empty(
+                    frames.shape[0], enc.tokens, self.embed_dim, dtype=self.token_dtype16 if half_tokens else torch.float32,
+                    pin_memory=True)
+                if out.dtype != (self.token_dtype16 if half_tokens else torch.float32):
+                    raise RuntimeError(f"encode_host_stream: output buffers must be {self.token_dtype16 if half_tokens else torch.float32}")
                 enc.host_submit(frames, out, slot, dev)
                 pending.append((slot, out, frames))  # keep the input alive until its copy has run
                 k += 1
