@@ -711,8 +711,13 @@ def tokenize_record(args, ctx, vision, text, n_videos, num_frm=8, k=5, out_dir=N
         t0 = time.perf_counter()
         reps = {}
         for key, n in VG_BANK_SIZES.items():
-            embs = [text(W.token_ids("large14", min(512, n - i), 77, seed=i).to(ctx.dev)) for i in range(0, n, 512)]
-            reps[key] = {"text_embeds": torch.cat(embs)}
+            # the bank's 512-phrase batches are split over the ranks and exchanged with one all-gather of embedding rows
+            # (visual_tokenization.get_text_embeddings_clip(shard_over_ranks=True)); the reference embeds it on every rank
+            starts = list(range(0, n, 512))
+            per = (len(starts) + ctx.world - 1) // ctx.world
+            embs = [text(W.token_ids("large14", min(512, n - i), 77, seed=i).to(ctx.dev)) for i in starts[ctx.rank * per:(ctx.rank + 1) * per]]
+            mine_rows = torch.cat(embs) if embs else torch.zeros(0, 768, device=ctx.dev)
+            reps[key] = {"text_embeds": vdist.all_gather_rows(mine_rows)}
         torch.cuda.synchronize()
         t_bank = time.perf_counter() - t0
         embeds = []

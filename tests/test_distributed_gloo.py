@@ -38,6 +38,28 @@ def _worker(rank, world, port, out_dir, n_videos):
     # every rank sees every rank's object from all_gather_json
     got = vd.all_gather_json({"r": rank, "empty": {}})
     assert [g["r"] for g in got] == list(range(world))
+    # the phrase bank embedded once ACROSS the ranks: every rank embeds a contiguous run of the 512-phrase batches, the rows
+    # come back in the original order on every rank (all_gather_rows), including ranks that got no batch at all
+    import torch
+    from types import SimpleNamespace
+
+    from vidil_b200 import visual_tokenization as vt
+    texts = [f"phrase {i}" for i in range(1300)]                      # 3 batches of <= 512
+
+    class Proc:
+        def __call__(self, text=None, **kw):
+            ids = torch.tensor([[len(t), int(t.split()[1])] for t in text])
+            return {"input_ids": ids, "attention_mask": torch.ones_like(ids)}
+
+    class Model:
+        def __call__(self, input_ids=None, attention_mask=None):
+            return SimpleNamespace(text_embeds=torch.stack([input_ids[:, 1].float(), input_ids[:, 1].float() * 0.5], dim=1))
+
+    whole, _, _ = vt.get_text_embeddings_clip(Model(), Proc(), texts, "cpu")
+    sharded, _, _ = vt.get_text_embeddings_clip(Model(), Proc(), texts, "cpu", shard_over_ranks=True)
+    assert torch.equal(whole, sharded) and tuple(sharded.shape) == (1300, 2)
+    assert torch.equal(vd.all_gather_rows(torch.full((rank, 3), float(rank))),
+                       torch.cat([torch.full((r, 3), float(r)) for r in range(world)]))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -65,6 +87,9 @@ def test_single_process_fallbacks():
     assert vd.shard_bounds(10) == (0, 10)
     assert vd.all_gather_json({"a": 1}) == [{"a": 1}]
     assert vd.merge_rank_dicts([{"a": 1}, None, {"a": 2, "b": 3}]) == {"a": 2, "b": 3}
+    import torch
+    t = torch.arange(6.).view(3, 2)
+    assert vd.all_gather_rows(t) is t
 
 
 def test_shard_bounds_matches_fixture(golden_dir):

@@ -91,6 +91,25 @@ def all_gather_json(obj, device: torch.device | str | None = None) -> list:
     return [json.loads(b[:s].cpu().numpy().tobytes().decode("utf-8")) if s else None for b, s in zip(bufs, sizes)]
 
 
+def all_gather_rows(t: torch.Tensor) -> torch.Tensor:
+    """Every rank contributes a [n_r, D] tensor (n_r may differ, 0 allowed); every rank gets the [sum n_r, D] concatenation
+    in rank order.  Two collectives (row counts, rows padded to the longest) — used to build the phrase-bank embeddings
+    once across the ranks instead of once per rank (run_visual_tokenization.py:84-96 runs the whole bank on every rank)."""
+    if not is_dist_avail_and_initialized():
+        return t
+    world = dist.get_world_size()
+    n = torch.tensor([t.shape[0]], dtype=torch.int64, device=t.device)
+    counts = [torch.zeros_like(n) for _ in range(world)]
+    dist.all_gather(counts, n)
+    counts = [int(c.item()) for c in counts]
+    width = max(max(counts), 1)
+    padded = torch.zeros((width,) + tuple(t.shape[1:]), dtype=t.dtype, device=t.device)
+    padded[:t.shape[0]] = t
+    bufs = [torch.empty_like(padded) for _ in range(world)]
+    dist.all_gather(bufs, padded.contiguous())
+    return torch.cat([b[:c] for b, c in zip(bufs, counts)], dim=0)
+
+
 def merge_rank_dicts(per_rank: list) -> dict:
     """`dict.update` in rank order — run_visual_tokenization.py:453-457."""
     merged = {}

@@ -91,14 +91,30 @@ def _to_device(inputs, device):
 
 
 @torch.no_grad()
-def get_text_embeddings_clip(model, processor, texts, device):
-    """:84-96 — [len(texts), proj] unit-norm text embeddings in batches of 512; returns (embeds, None, None)."""
+def get_text_embeddings_clip(model, processor, texts, device, shard_over_ranks: bool = False):
+    """:84-96 — [len(texts), proj] unit-norm text embeddings in batches of 512; returns (embeds, None, None).
+
+    shard_over_ranks (extra): under torch.distributed every rank embeds a contiguous run of the 512-phrase batches and the
+    rows are exchanged with one all-gather (vdist.all_gather_rows), instead of every rank embedding the whole bank as the
+    reference does.  The batches are the same batches, each row depends on its own phrase only, and the concatenation is in
+    the original order, so the bank is identical on every rank."""
+    starts = list(range(0, len(texts), EMBBDING_BATCH_LIMIT_TEXT))
+    if shard_over_ranks and vdist.get_world_size() > 1:
+        per = (len(starts) + vdist.get_world_size() - 1) // vdist.get_world_size()
+        starts = starts[vdist.get_rank() * per:(vdist.get_rank() + 1) * per]
     text_embeds = []
-    for i in range(0, len(texts), EMBBDING_BATCH_LIMIT_TEXT):
+    for i in starts:
         text = texts[i: i + EMBBDING_BATCH_LIMIT_TEXT]
         inputs = _to_device(processor(text=text, return_tensors="pt", padding=True, truncation=True), device)
         outputs = model(input_ids=inputs["input_ids"], attention_mask=inputs.get("attention_mask"))
         text_embeds.append(outputs.text_embeds)
+    if shard_over_ranks and vdist.get_world_size() > 1:
+        mine = torch.cat(text_embeds, dim=0) if text_embeds else None
+        width = torch.tensor([mine.shape[1] if mine is not None else 0], dtype=torch.int64, device=device)
+        torch.distributed.all_reduce(width, op=torch.distributed.ReduceOp.MAX)     # a rank without batches still needs D
+        if mine is None:
+            mine = torch.zeros(0, int(width.item()), dtype=torch.float32, device=device)
+        return vdist.all_gather_rows(mine.float()), None, None
     return torch.cat(text_embeds, dim=0), None, None
 
 
@@ -151,7 +167,7 @@ def tokens_from_embeddings(image_embeds: torch.Tensor, text_representations: dic
 
 @torch.no_grad()
 def predict_video(config, video_dataset, model, device, visual_token_texts, prompt_functions, encoder_version='clip',
-                  processor=None, frame_batch: int = 256):
+                  processor=None, frame_batch: int = 256, shard_text_bank: bool = False):
     """Same arguments and result as the reference's predict_video (:161-314) for encoder_version='clip':
     {video_id: {"frame_tokens": [{key: [k phrases]} x num_frm], "caption": ..., "aggregated_tokens": {key: [...]}}}."""
     if encoder_version != 'clip':
@@ -162,7 +178,7 @@ def predict_video(config, video_dataset, model, device, visual_token_texts, prom
     text_representations = {}
     for key in visual_token_texts.keys():
         texts = [prompt_functions[key](t) for t in visual_token_texts[key]]
-        text_embeds, text_ids, text_atts = get_text_embeddings_clip(model, processor, texts, device)
+        text_embeds, text_ids, text_atts = get_text_embeddings_clip(model, processor, texts, device, shard_over_ranks=shard_text_bank)
         text_representations[key] = {'text_embeds': text_embeds, 'text_ids': text_ids, 'text_atts': text_atts}
 
     image_embeds, video_ids, captions = [], [], []
@@ -204,6 +220,7 @@ def run(config, video_dataset, model, processor, device, visual_token_texts, out
     video_dataset.annotation = video_dataset.annotation[start:end]
     prompt_functions = get_prefix_prompt_functions(config['prompt_version_visual_tokenization'])
     result = predict_video(config, video_dataset, model, device, visual_token_texts, prompt_functions,
-                           encoder_version='clip', processor=processor, frame_batch=frame_batch)
+                           encoder_version='clip', processor=processor, frame_batch=frame_batch,
+                           shard_text_bank=vdist.get_world_size() > 1)
     path = os.path.join(output_dir, 'visual_tokens.json') if output_dir else None
     return vdist.gather_and_write(result, path)
