@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from vidil_b200 import _lib, ops  # noqa: E402
 
-B, N, H = 256, 197, 16
+B, N, H = 256, int(sys.argv[1]) if len(sys.argv) > 1 else 197, 16
 qkv = torch.randn(B, N, 3 * H * 64, device="cuda")
 lib = _lib.load()
 ops.attention(qkv, H)  # warm
@@ -23,7 +23,10 @@ names = {0: ["top", "qk_empty ok", "v_empty ok"],
          3: ["top", "s_full ok", "pass1 done", "token ok", "P written", "o_full ok", "O drained"]}
 names[2], names[4] = names[1], names[3]
 names[5] = names[6] = [f"c{i}" for i in range(8)]   # even chunks: after the TMEM-load wait; odd chunks: before it
-roles = ["producer", "mma L0", "mma L1", "softmax L0", "softmax L1", "chunks L0", "chunks L1"]
+if N == 257:
+    names[3] = names[4] = ["top", "sx done", "s_full ok", "pass1 done", "token ok", "P written", "o_full ok", "O drained"]
+    names[5] = ["top", "qk_full ok", "K released", "v_full ok", "V released"]
+roles = ["producer", "mma L0", "mma L1", "softmax L0", "softmax L1", "chunks L0" if N != 257 else "tail", "chunks L1"]
 for it in range(4, 9):
     print(f"--- item iteration {it}")
     for r in range(7):

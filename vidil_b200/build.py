@@ -20,7 +20,7 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 SRC_DIR = os.path.join(PKG_DIR, "csrc")
 OUT_DIR = os.path.join(PKG_DIR, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libvidil_b200.so")
-SOURCES = ["api.cu", "gemm.cu", "layernorm.cu", "attention.cu", "attention_tc.cu", "attention_tcl.cu", "elementwise.cu", "topk.cu", "preprocess.cu", "med.cu", "med_api.cu"]
+SOURCES = ["api.cu", "gemm.cu", "layernorm.cu", "attention.cu", "attention_tc.cu", "attention_tc257.cu", "attention_tcl.cu", "elementwise.cu", "topk.cu", "preprocess.cu", "med.cu", "med_api.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",

@@ -250,6 +250,9 @@ int build_plan(vidil_encoder* e, Plan& pl, int B, void* ws) {
     if (attention_tc_supported(e->tokens)) {
         pl.attn_tc = true;
         if (attention_tc_prepare(pl.attn_maps, pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads)) return 1;
+    } else if (attention_tc257_supported(e->tokens)) {
+        pl.attn_tc = true;
+        if (attention_tc257_prepare(pl.attn_maps, pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads)) return 1;
     } else if (attention_tcl_supported(e->tokens)) {
         pl.attn_tc = true;
         if (attention_tcl_prepare(pl.attn_maps, pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads)) return 1;
@@ -386,6 +389,7 @@ int run_trunk(vidil_encoder* e, Plan& pl, const float* frames, cudaStream_t s) {
         if (timed(e, s, VIDIL_KCLASS_ATTENTION, attn_flops, attn_bytes,
                   [&] {
                       if (!pl.attn_tc) return attention_run(pl.qkv, pl.attn, e->dt, B, e->tokens, c.num_heads, scale, s);
+                      if (pl.attn_maps.is_257) return attention_tc257_run(pl.attn_maps, scale, s);
                       return pl.attn_maps.is_long ? attention_tcl_run(pl.attn_maps, scale, s)
                                                   : attention_tc_run(pl.attn_maps, scale, s);
                   }))
@@ -1128,6 +1132,10 @@ static int op_attention_any(const float* qkv, float* out, int32_t B, int32_t N, 
         if (attention_tc_prepare(maps, qkv_h, out_h, dt, B, N, H)) return 1;
         maps.causal = causal;
         if (attention_tc_run(maps, scale, s)) return 1;
+    } else if (attention_tc257_supported(N)) {
+        AttentionMaps maps;
+        if (attention_tc257_prepare(maps, qkv_h, out_h, dt, B, N, H)) return 1;
+        if (attention_tc257_run(maps, scale, s)) return 1;
     } else if (attention_tcl_supported(N)) {
         AttentionMaps maps;
         if (attention_tcl_prepare(maps, qkv_h, out_h, dt, B, N, H)) return 1;

@@ -24,6 +24,7 @@
 
 #include <type_traits>
 
+#include "attention_common.cuh"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -38,121 +39,21 @@ constexpr int ATC_THREADS = 384; // warp 0 producer, 1-2 MMA issuers, 3 TMEM all
 
 constexpr int Q_BYTES = QT * HD * 2;               // 16 KB
 constexpr int KV_BYTES = MAX_KEYS * HD * 2;        // 26 KB
+// Q (two tiles), K and V are double-buffered: the TMA producer runs one (frame, head) item ahead, so the next item's tiles
+// travel from HBM while the current item is computed (in a forward the qkv matrix does not fit L2; with single buffers the
+// load latency of every item was exposed: 6 400 clocks per item cold against 4 700 warm)
+constexpr int STAGES = 2;
 constexpr int OFF_Q = 0;
-constexpr int OFF_K = 2 * Q_BYTES;
-constexpr int OFF_V = OFF_K + KV_BYTES;
-constexpr int OFF_OUT = OFF_V + KV_BYTES;          // 2 lanes x 4 quarters x [32 rows][128 B]
+constexpr int OFF_K = STAGES * 2 * Q_BYTES;
+constexpr int OFF_V = OFF_K + STAGES * KV_BYTES;
+constexpr int OFF_OUT = OFF_V + STAGES * KV_BYTES;  // 2 lanes x 4 quarters x [32 rows][128 B]
 constexpr int OFF_BAR = OFF_OUT + 8 * 4096;
 constexpr int ATC_SMEM = OFF_BAR + 256 + 1024;     // + alignment slack
 static_assert(OFF_K % 1024 == 0 && OFF_V % 1024 == 0 && OFF_OUT % 1024 == 0, "tile alignment");
 static_assert(ATC_SMEM <= 227 * 1024, "shared memory budget");
 static_assert(MAX_KEYS / 2 <= O_COL && O_COL + HD <= 256 && MAX_KEYS <= 256, "TMEM column plan");
 
-template <typename T>
-__device__ __forceinline__ uint32_t pack2(float a, float b);
-template <>
-__device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) {
-    __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-template <>
-__device__ __forceinline__ uint32_t pack2<__half>(float a, float b) {
-    __half2 v = __floats2half2_rn(a, b);
-    return *reinterpret_cast<uint32_t*>(&v);
-}
-
-// Row maximum over W (16 or 32) S values starting at key column c0; columns >= nv are masked or padding.  Four
-// independent accumulators: a warp issues in order, so one dependent FMNMX3 chain would expose its latency 16 times a chunk.
-template <int W>
-__device__ __forceinline__ void chunk_max(const uint32_t (&r)[W], int c0, int nv, float (&mx)[4]) {
-    if (c0 + W <= nv) {
-#pragma unroll
-        for (int i = 0; i < W; i += 8) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) mx[j] = ptx::max3(mx[j], __uint_as_float(r[i + 2 * j]), __uint_as_float(r[i + 2 * j + 1]));
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < W; ++i) mx[i & 3] = fmaxf(mx[i & 3], (c0 + i < nv) ? __uint_as_float(r[i]) : -INFINITY);
-    }
-}
-
-// exp2(c s - c max) of W (16 or 32) S values -> W/2 columns of packed 16-bit P in TMEM; accumulates the row sums.
-// A warp issues in order and the MUFU pipe takes one warp-wide ex2 every 8 clocks, so the consumers of an exponential (the
-// row-sum add and the 16-bit pack) are placed LAG pairs behind it in program order: with one softmax warp per sub-partition
-// nothing else would cover the MUFU latency, and a consumer right behind its producer stalls the whole warp (measured: 540-600
-// clocks per 32-column chunk with the add/pack or the mask select directly after each pair, against the 256 the MUFU pipe
-// needs).  LAG is in elements: 8 = 4 pairs = 8 MUFU slots = 64 clocks.
-// 2^a for a pair of arguments a <= 0 on the FMA / ALU pipes (no MUFU): a = n + f with n = round(a), f in [-0.5, 0.5];
-// 2^f by a degree-4 near-minimax polynomial (rel. err 3.7e-6, two orders below the rounding of a 16-bit P), 2^n by adding n
-// to the exponent field (the magic constant 1.5 * 2^23 leaves n in the low mantissa bits of t).  The MUFU pipe takes one
-// warp-wide ex2 every 8 clocks and is what bounds the softmax phase once the loop overhead is gone, while a single softmax
-// warp per sub-partition leaves most issue slots empty: evaluating POLY of every 16 pairs here moves work from the
-// saturated pipe to the idle one (the FlashAttention-4 trick).  ~11 instructions per pair, all packed fp32x2 but the clamp
-// and the exponent insert.
-__device__ __forceinline__ void exp2_poly2(float& a0, float& a1) {
-    a0 = fmaxf(a0, -126.0f);
-    a1 = fmaxf(a1, -126.0f);
-    float t0 = a0, t1 = a1, r0, r1, f0, f1, p0, p1;
-    ptx::add2(t0, t1, 12582912.0f, 12582912.0f);          // t = a + magic
-    r0 = t0, r1 = t1;
-    ptx::add2(r0, r1, -12582912.0f, -12582912.0f);        // r = round(a)
-    ptx::fma2v(f0, f1, r0, r1, -1.0f, -1.0f, a0, a1);     // f = a - r
-    ptx::fma2(p0, p1, f0, f1, 9.676037098e-03f, 5.592203565e-02f);
-    ptx::fma2v(p0, p1, f0, f1, p0, p1, 2.402210736e-01f, 2.402210736e-01f);
-    ptx::fma2v(p0, p1, f0, f1, p0, p1, 6.931210340e-01f, 6.931210340e-01f);
-    ptx::fma2v(p0, p1, f0, f1, p0, p1, 1.000000075e+00f, 1.000000075e+00f);
-    a0 = __int_as_float(__float_as_int(p0) + (__float_as_int(t0) << 23));
-    a1 = __int_as_float(__float_as_int(p1) + (__float_as_int(t1) << 23));
-}
-// pair p (0..15) of a chunk goes to the polynomial iff this is true: POLY pairs of every 16, evenly spread
-template <int POLY>
-__host__ __device__ constexpr bool poly_pair(int p) {
-    return (p * POLY) % 16 < POLY;
-}
-
-template <typename T, int W, bool MASKED, int POLY = 0, int LAG = 8>
-__device__ __forceinline__ void chunk_exp_impl(const uint32_t (&r)[W], int c0, int nv, float c, float neg_mxs, uint32_t taddr_p,
-                                               float (&sum)[4]) {
-    uint32_t pk[W / 2];
-    float a[W];
-#pragma unroll
-    for (int i = 0; i < W; i += 2) ptx::fma2(a[i], a[i + 1], __uint_as_float(r[i]), __uint_as_float(r[i + 1]), c, neg_mxs);
-#pragma unroll
-    for (int i = 0; i < W + LAG; i += 2) {
-        if (i < W) {
-            if (poly_pair<POLY>(i >> 1)) {
-                exp2_poly2(a[i], a[i + 1]);
-            } else {
-                a[i] = ptx::ex2_approx(a[i]);
-                a[i + 1] = ptx::ex2_approx(a[i + 1]);
-            }
-        }
-        if (i >= LAG) {
-            const int j = i - LAG;
-            if (MASKED) {  // the select is a consumer too: it sits LAG behind the exponential, not right after it
-                if (c0 + j >= nv) a[j] = 0.f;
-                if (c0 + j + 1 >= nv) a[j + 1] = 0.f;
-            }
-            ptx::add2(sum[j & 2], sum[(j & 2) + 1], a[j], a[j + 1]);
-            pk[j >> 1] = pack2<T>(a[j], a[j + 1]);
-        }
-    }
-    if constexpr (W == 32)
-        ptx::tmem_st_32x32b_x16(taddr_p + (c0 >> 1), pk);
-    else
-        ptx::tmem_st_32x32b_x8(taddr_p + (c0 >> 1), pk);
-}
-template <typename T, int W, int POLY>
-__device__ __forceinline__ void chunk_exp(const uint32_t (&r)[W], int c0, int nv, float c, float neg_mxs, uint32_t taddr_p,
-                                          float (&sum)[4]) {
-    // warp-uniform choice: both variants end in a tcgen05.st.sync.aligned, which the whole warp must execute together (under a
-    // causal mask nv differs from lane to lane; the masked variant is correct for every lane)
-    if (__all_sync(0xffffffffu, c0 + W <= nv))
-        chunk_exp_impl<T, W, false, POLY>(r, c0, nv, c, neg_mxs, taddr_p, sum);
-    else
-        chunk_exp_impl<T, W, true, POLY>(r, c0, nv, c, neg_mxs, taddr_p, sum);
-}
+using namespace attn;
 
 // Compile-time shape of a row for the specialised kernels.
 template <int NCT>
@@ -286,17 +187,17 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
     const uint32_t sbase = ptx::smem_u32(smem);
 
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
-    uint64_t* qk_full = bars + 0;
-    uint64_t* v_full = bars + 1;
-    uint64_t* qk_empty = bars + 2;
-    uint64_t* v_empty = bars + 3;
-    uint64_t* s_full = bars + 4;   // [2] per lane
-    uint64_t* p_full = bars + 6;   // [2]
-    uint64_t* o_full = bars + 8;   // [2]
-    uint64_t* s_free = bars + 10;  // [2]
-    uint64_t* tok = bars + 12;     // [2] "this lane is in the last chunk of its exponentials"
-    uint64_t* p_half = bars + 14;  // [2] keys [0,128) of P are in TMEM (specialised kernels with more than 128 keys)
-    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 16);
+    uint64_t* qk_full = bars + 0;   // [2] per stage
+    uint64_t* v_full = bars + 2;    // [2]
+    uint64_t* qk_empty = bars + 4;  // [2]
+    uint64_t* v_empty = bars + 6;   // [2]
+    uint64_t* s_full = bars + 8;    // [2] per lane
+    uint64_t* p_full = bars + 10;   // [2]
+    uint64_t* o_full = bars + 12;   // [2]
+    uint64_t* s_free = bars + 14;   // [2]
+    uint64_t* tok = bars + 16;      // [2] "this lane is in the last chunk of its exponentials"
+    uint64_t* p_half = bars + 18;   // [2] keys [0,128) of P are in TMEM (specialised kernels with more than 128 keys)
+    uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bars + 20);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -310,10 +211,12 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
         ptx::prefetch_tensormap(&map_q);
         ptx::prefetch_tensormap(&map_kv);
         ptx::prefetch_tensormap(&map_out);
-        ptx::mbar_init(qk_full, 1);
-        ptx::mbar_init(v_full, 1);
-        ptx::mbar_init(qk_empty, n_tiles);  // one commit per lane that issued an S MMA for the item
-        ptx::mbar_init(v_empty, n_tiles);
+        for (int st = 0; st < STAGES; ++st) {
+            ptx::mbar_init(&qk_full[st], 1);
+            ptx::mbar_init(&v_full[st], 1);
+            ptx::mbar_init(&qk_empty[st], n_tiles);  // one commit per lane that issued an S MMA for the item
+            ptx::mbar_init(&v_empty[st], n_tiles);
+        }
         for (int l = 0; l < 2; ++l) {
             ptx::mbar_init(&s_full[l], 1);
             ptx::mbar_init(&p_full[l], 4);  // lane 0 of each of the lane's 4 softmax warps
@@ -338,20 +241,22 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             // ===================== TMA producer =====================
             int it = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const uint32_t ph = it & 1;
+                const int st = it & 1;
+                const uint32_t ph = (it >> 1) & 1;
                 const int b = item / H, h = item - b * H;
                 const int row0 = b * N;
+                uint8_t* sq = smem + OFF_Q + st * 2 * Q_BYTES;
                 ATC_TRACE(0, 0);
-                ptx::mbar_wait(qk_empty, ph ^ 1);  // previous item's S MMAs have consumed Q and K
+                ptx::mbar_wait(&qk_empty[st], ph ^ 1);  // the S MMAs of the item two back have consumed this stage's Q and K
                 ATC_TRACE(0, 1);
-                ptx::mbar_arrive_expect_tx(qk_full, n_tiles * Q_BYTES + nk16 * HD * 2);
-                ptx::tma_load_2d(&map_q, qk_full, smem + OFF_Q, h * HD, row0);
-                if (n_tiles == 2) ptx::tma_load_2d(&map_q, qk_full, smem + OFF_Q + Q_BYTES, h * HD, row0 + QT);
-                ptx::tma_load_2d(&map_kv, qk_full, smem + OFF_K, D + h * HD, row0);
-                ptx::mbar_wait(v_empty, ph ^ 1);  // previous item's PV MMAs have consumed V
+                ptx::mbar_arrive_expect_tx(&qk_full[st], n_tiles * Q_BYTES + nk16 * HD * 2);
+                ptx::tma_load_2d(&map_q, &qk_full[st], sq, h * HD, row0);
+                if (n_tiles == 2) ptx::tma_load_2d(&map_q, &qk_full[st], sq + Q_BYTES, h * HD, row0 + QT);
+                ptx::tma_load_2d(&map_kv, &qk_full[st], smem + OFF_K + st * KV_BYTES, D + h * HD, row0);
+                ptx::mbar_wait(&v_empty[st], ph ^ 1);  // the PV MMAs of the item two back have consumed this stage's V
                 ATC_TRACE(0, 2);
-                ptx::mbar_arrive_expect_tx(v_full, nk16 * HD * 2);
-                ptx::tma_load_2d(&map_kv, v_full, smem + OFF_V, 2 * D + h * HD, row0);
+                ptx::mbar_arrive_expect_tx(&v_full[st], nk16 * HD * 2);
+                ptx::tma_load_2d(&map_kv, &v_full[st], smem + OFF_V + st * KV_BYTES, 2 * D + h * HD, row0);
             }
         }
         __syncwarp();
@@ -369,29 +274,31 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int t = (n_tiles == 2) ? ((L + it) & 1) : L;  // one tile: lane 0 does every item, lane 1 idles
                 if (t >= n_tiles) continue;
-                const uint32_t ph = it & 1, par = n & 1;
+                const int st = it & 1;
+                const uint32_t ph = (it >> 1) & 1, par = n & 1;
                 ++n;
                 ATC_TRACE(1 + L, 0);
-                ptx::mbar_wait(qk_full, ph);
+                ptx::mbar_wait(&qk_full[st], ph);
                 ATC_TRACE(1 + L, 1);
                 ptx::mbar_wait(&s_free[L], par ^ 1);  // this lane's previous O (inside the S columns) has been read out
                 ATC_TRACE(1 + L, 2);
                 ptx::tcgen05_fence_after();
-                const uint64_t dk = ptx::make_kmajor_sw128_desc(sbase + OFF_K);
-                const uint64_t dq = ptx::make_kmajor_sw128_desc(sbase + OFF_Q + t * Q_BYTES);
+                const uint64_t dk = ptx::make_kmajor_sw128_desc(sbase + OFF_K + st * KV_BYTES);
+                const uint64_t dq = ptx::make_kmajor_sw128_desc(sbase + OFF_Q + (st * 2 + t) * Q_BYTES);
+                const uint32_t sv = sbase + OFF_V + st * KV_BYTES;
 #pragma unroll
                 for (int k = 0; k < HD / 16; ++k) ptx::umma_f16<1>(tmem_s, dq + 2 * k, dk + 2 * k, idesc_s, k != 0);
                 ptx::umma_commit<1>(&s_full[L]);
-                ptx::umma_commit<1>(qk_empty);
+                ptx::umma_commit<1>(&qk_empty[st]);
                 ATC_TRACE(1 + L, 3);
-                ptx::mbar_wait(v_full, ph);
+                ptx::mbar_wait(&v_full[st], ph);
                 ATC_TRACE(1 + L, 4);
                 if constexpr (kSplit) {
                     ptx::mbar_wait(&p_half[L], par);  // P of keys [0,128) is in TMEM columns [0,64); S columns [0,128) are dead
                     ptx::tcgen05_fence_after();
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        const uint64_t db = ptx::make_smem_desc(sbase + OFF_V + j * 2048, 0, 1024, 2);
+                        const uint64_t db = ptx::make_smem_desc(sv + j * 2048, 0, 1024, 2);
                         ptx::umma_f16_tmem_a(tmem_o, tmem_s + j * 8, db, idesc_o, j != 0);
                     }
                 }
@@ -402,11 +309,11 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
                 for (int j = kSplit ? 8 : 0; j < ksteps; ++j) {
                     // A: P k-step j = 16 keys = 8 packed TMEM columns
                     // B: V rows 16j..16j+15 (two 8-row 1024-byte swizzle groups), 64 contiguous channels per row
-                    const uint64_t db = ptx::make_smem_desc(sbase + OFF_V + j * 2048, 0, 1024, 2);
+                    const uint64_t db = ptx::make_smem_desc(sv + j * 2048, 0, 1024, 2);
                     ptx::umma_f16_tmem_a(tmem_o, tmem_s + (kSplit ? 128 + (j - 8) * 8 : j * 8), db, idesc_o, j != 0);
                 }
                 ptx::umma_commit<1>(&o_full[L]);
-                ptx::umma_commit<1>(v_empty);
+                ptx::umma_commit<1>(&v_empty[st]);
                 ATC_TRACE(1 + L, 6);
             }
         }
@@ -611,7 +518,11 @@ int launch_tc(const AttentionMaps& m, int B, int N, int H, float scale_log2e, cu
 
 }  // namespace
 
-void attention_set_trace(long long* dev_buf) { g_trace = dev_buf; }
+void attention_tc257_set_trace(long long* dev_buf);
+void attention_set_trace(long long* dev_buf) {
+    g_trace = dev_buf;
+    attention_tc257_set_trace(dev_buf);
+}
 
 bool attention_tc_supported(int N) { return N >= 1 && N <= MAX_KEYS; }
 

@@ -113,6 +113,8 @@ int attention_run(const void* qkv, void* out, DType dt, int B, int N, int H, flo
 // buffer addresses and the shape, so a forward plan encodes them once.
 struct AttentionMaps {
     CUtensorMap q, kv, out;
+    CUtensorMap kv16;      // attention_tc257.cu: the 16-row K / V box holding token 256
+    bool is_257 = false;   // prepared for attention_tc257_run
     const void* qkv = nullptr;
     void* out_ptr = nullptr;
     int B = 0, N = 0, H = 0;
@@ -127,6 +129,10 @@ void attention_set_trace(long long* dev_buf);
 bool attention_tc_supported(int N);
 int attention_tc_prepare(AttentionMaps& m, const void* qkv, void* out, DType dt, int B, int N, int H);
 int attention_tc_run(const AttentionMaps& m, float scale, cudaStream_t stream);
+// CLIP ViT-L/14's 257 tokens: single-pass kernel with the 257th key / query handled by SIMT (attention_tc257.cu)
+bool attention_tc257_supported(int N);
+int attention_tc257_prepare(AttentionMaps& m, const void* qkv, void* out, DType dt, int B, int N, int H);
+int attention_tc257_run(const AttentionMaps& m, float scale, cudaStream_t stream);
 // tcgen05 version with a key-block loop for 128 < N <= 768 (attention_tcl.cu); non-causal
 bool attention_tcl_supported(int N);
 int attention_tcl_prepare(AttentionMaps& m, const void* qkv, void* out, DType dt, int B, int N, int H);
