@@ -1,6 +1,10 @@
 """Turn the scratch ncu outputs in gpurun_out/ into the tracked summaries under profiles/.
 
-    python tools/summarize_profiles.py <tag>        e.g.  r01a
+    python tools/summarize_profiles.py <tag> [--launches FILE] [--bench FILE] [--reports PREFIX]      e.g.  r02
+      --launches  launch-list csv inside gpurun_out/ (default launches.csv)
+      --bench     bench JSON line inside gpurun_out/ (default bench.json)
+      --reports   only *.ncu-rep files whose name starts with PREFIX (default: all)
+Also refreshes profiles/traffic.json (DRAM bytes per launch of the GEMM kernel, read back by bench.py's roofline.traffic).
 
 Writes profiles/<tag>_launches.csv   one forward's launch list (kernel, grid, duration) from launches.csv
        profiles/<tag>_summary.md     per-kernel totals of that forward + selected `ncu --set full` metrics of every
@@ -34,12 +38,16 @@ def short(name):
     return name.split("(")[0]
 
 
+def opt(name, default):
+    return sys.argv[sys.argv.index(name) + 1] if name in sys.argv else default
+
+
 def launches(tag, lines):
-    path = os.path.join(OUT, "launches.csv")
+    path = os.path.join(OUT, opt("--launches", "launches.csv"))
     if not os.path.exists(path):
         return
     with open(path) as f:
-        rows = list(csv.DictReader([l for l in f if l.startswith('"')]))
+        rows = [r for r in csv.DictReader([l for l in f if l.startswith('"')]) if r.get("Metric Name", "gpu__time_duration.sum") == "gpu__time_duration.sum"]
     starts = [i for i, r in enumerate(rows) if "im2col" in r["Kernel Name"]]
     if len(starts) < 2:
         return
@@ -67,7 +75,8 @@ def launches(tag, lines):
 
 
 def reports(lines):
-    for rep in sorted(glob.glob(os.path.join(OUT, "*.ncu-rep"))):
+    traffic = {}
+    for rep in sorted(glob.glob(os.path.join(OUT, opt("--reports", "") + "*.ncu-rep"))):
         r = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True)
         rows = list(csv.reader(r.stdout.splitlines()))
         if len(rows) < 3:
@@ -82,13 +91,29 @@ def reports(lines):
                 i = hdr.index(m)
                 lines.append(f"| {m} | {units[i]} | " + " | ".join(d[i] for d in data) + " |")
         lines.append("")
+        # DRAM bytes per launch of the per-layer GEMMs (a capture of 4 consecutive gemm_tcgen05 launches = qkv, proj, fc1, fc2)
+        if all("gemm_tcgen05_kernel" in d[kn] for d in data) and len(data) == 4 and "dram__bytes_read.sum" in hdr:
+            def to_bytes(v, u):
+                return float(v.replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
+            ri, wi = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+            per = [to_bytes(d[ri], units[ri]) + to_bytes(d[wi], units[wi]) for d in data]
+            traffic = {"bytes_per_launch": sum(per) / len(per),
+                       "source": f"profiles/{sys.argv[1]}_summary.md ({os.path.basename(rep)}): ncu --set full, dram__bytes_read.sum + "
+                                 f"dram__bytes_write.sum, mean over 4 consecutive per-layer GEMM launches "
+                                 f"({', '.join(f'{x / 1e6:.0f}' for x in per)} MB)"}
+    if traffic:
+        path = os.path.join(ROOT, "profiles", "traffic.json")
+        allt = json.load(open(path)) if os.path.exists(path) else {}
+        allt.setdefault("gemm_tcgen05_kernel", {})["vit_large_224_b256"] = traffic
+        with open(path, "w") as f:
+            json.dump(allt, f, indent=1)
 
 
 def main():
     tag = sys.argv[1]
     os.makedirs(os.path.join(ROOT, "profiles"), exist_ok=True)
     lines = [f"# Profile summary {tag}\n"]
-    bj = os.path.join(OUT, "bench.json")
+    bj = os.path.join(OUT, opt("--bench", "bench.json"))
     if os.path.exists(bj):
         txt = open(bj).read().strip().splitlines()
         if txt:

@@ -1,8 +1,12 @@
-"""Mirror of the ViT factory in the reference's `models/blip.py` (create_vit, :298-326).
+"""Mirror of the reference's `models/blip.py` / `models/blip_itm.py` on the CapFilt path.
 
-The BLIP wrappers (BLIP_Decoder, BLIP_ITM, ...) stay the reference's: they obtain their image tower from
-`create_vit` and call it as `self.visual_encoder(image)` (blip.py:94,106,128; blip_itm.py:27,43), so
-re-pointing this one import makes every one of those call sites run on the native path.
+* `create_vit` (:298-326): the ViT factory every BLIP wrapper obtains its image tower from and calls as
+  `self.visual_encoder(image)` (blip.py:94,106,128; blip_itm.py:27,43).  Re-pointing this one import is enough to put every
+  reference wrapper's image tower on the native path.
+* `BLIP_Decoder` (blip.py:80-167, `generate` with beam search) and `BLIP_ITM` (blip_itm.py:11-58, `match_head='itm'`), with
+  the reference's constructor arguments and `state_dict` keys, re-implemented here on the native text stack
+  (`vidil_b200.med`: vidil_med_generate / vidil_med_forward) — they are what `blip_decoder(...)` / `blip_itm(...)` return.
+  Not covered (no shipped pipeline config uses them): nucleus sampling, the ITC head, the training forward.
 """
 from __future__ import annotations
 
