@@ -46,22 +46,31 @@ constexpr int SEL_BATCH = 8;   // candidates re-scored per round (their bank row
 constexpr int SEL_SCRATCH = 32;  // floats of per-warp scratch behind the embedding (>= 2 * SEL_MAX_K, >= 2 * SEL_BATCH)
 
 // Exact fp32 dot products of the frame's embedding q (shared memory) with up to SEL_BATCH bank rows (col[c] < 0: skip):
-// lane l sums elements l, l + 32, ... in order, then a butterfly — ONE arithmetic for every exact score, so equal rows give
-// equal scores.  d outer / candidate inner with the d loop unrolled keeps 4 x SEL_BATCH row segments in flight per warp.
+// lane l sums elements 4l..4l+3, 4l+128.., ... in order, then a butterfly — ONE arithmetic for every exact score, so equal
+// rows give equal scores.  16-byte loads, d outer / candidate inner, the d loop unrolled by 3: 24 row segments of 16 bytes
+// in flight per lane (the kernel is bound by the latency of these loads: 47 % of its stall samples).
 __device__ __forceinline__ void score_batch(const float* __restrict__ q, const float* __restrict__ bank, int D, int lane,
                                             const int (&col)[SEL_BATCH], float (&acc)[SEL_BATCH]) {
-    const float* p[SEL_BATCH];
+    const float4* p[SEL_BATCH];
 #pragma unroll
     for (int c = 0; c < SEL_BATCH; ++c) {
-        p[c] = bank + static_cast<int64_t>(col[c] < 0 ? 0 : col[c]) * D;
+        p[c] = reinterpret_cast<const float4*>(bank + static_cast<int64_t>(col[c] < 0 ? 0 : col[c]) * D);
         acc[c] = 0.f;
     }
-#pragma unroll 4
-    for (int d = lane; d < D; d += 32) {
-        const float qd = q[d];
+    const float4* q4 = reinterpret_cast<const float4*>(q);
+#pragma unroll 3
+    for (int d4 = lane; d4 < (D >> 2); d4 += 32) {
+        const float4 qd = q4[d4];
 #pragma unroll
-        for (int c = 0; c < SEL_BATCH; ++c)
-            if (col[c] >= 0) acc[c] = fmaf(qd, p[c][d], acc[c]);
+        for (int c = 0; c < SEL_BATCH; ++c) {
+            if (col[c] >= 0) {
+                const float4 b = __ldg(p[c] + d4);
+                acc[c] = fmaf(qd.x, b.x, acc[c]);
+                acc[c] = fmaf(qd.y, b.y, acc[c]);
+                acc[c] = fmaf(qd.z, b.z, acc[c]);
+                acc[c] = fmaf(qd.w, b.w, acc[c]);
+            }
+        }
     }
 #pragma unroll
     for (int c = 0; c < SEL_BATCH; ++c) {
@@ -112,7 +121,7 @@ struct TopList {
     }
 };
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 4)
     topk_select_kernel(const float* __restrict__ top2, int ld_top2, int G, const float* __restrict__ img,
                        const float* __restrict__ bank, float eps_scale, const float* __restrict__ bank_max_norm, int F, int T, int D,
                        int k, float* __restrict__ out_scores, int32_t* __restrict__ out_idx) {
@@ -120,8 +129,9 @@ __global__ void __launch_bounds__(128)
     const int warps = blockDim.x >> 5, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int f = blockIdx.x * warps + warp;
     if (f >= F) return;
-    float* pool = sel_smem + static_cast<size_t>(warp) * (2 * G + D + SEL_SCRATCH);   // [2 G] tagged scores, the frame's embedding [D], batch scratch
-    float* q = pool + 2 * G;
+    const int pool_len = (2 * G + 3) & ~3;   // keeps the embedding behind it 16-byte aligned
+    float* pool = sel_smem + static_cast<size_t>(warp) * (pool_len + D + SEL_SCRATCH);   // [2 G] tagged scores, the frame's embedding [D], batch scratch
+    float* q = pool + pool_len;
     const float* src = top2 + static_cast<int64_t>(f) * ld_top2;
     for (int i = lane; i < 2 * G; i += 32) pool[i] = src[i];
     float nrm = 0.f;
@@ -272,7 +282,7 @@ int topk_select_run(const float* top2, int ld_top2, int G, const float* img, con
         set_error("sim_topk: k=%d must be in [1, min(%d, T=%d)]", k, SEL_MAX_K, T);
         return 1;
     }
-    const size_t per_warp = (2 * static_cast<size_t>(G) + D + SEL_SCRATCH) * sizeof(float);
+    const size_t per_warp = (((2 * static_cast<size_t>(G) + 3) & ~static_cast<size_t>(3)) + D + SEL_SCRATCH) * sizeof(float);
     int warps = 4;
     while (warps > 1 && per_warp * warps > 200 * 1024) warps >>= 1;
     if (per_warp * warps > 200 * 1024) {
