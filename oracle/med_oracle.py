@@ -10,13 +10,18 @@ Parity status
     against *outputs of the reference itself*: oracle/make_golden.py imports the unmodified
     /root/reference/models/med.py (behind the import shims SURVEY.md §8c lists), runs it on seeded inputs and
     commits the results under tests/golden/med_*.npz; tests/test_oracle_golden.py checks this file against them.
-  * Beam search: **parity unpinned.**  The reference delegates to `transformers` `generate()` (un-vendored,
-    unpinned, `docker/requirements.txt:9`; med.py is "based on v4.15.0"), which cannot drive med.py under the
-    installed transformers 5.5.  `beam_search` below restates the published v4.15.0 algorithm
+  * Beam search: **pinned to real transformers code for everything but three lines.**  The reference delegates to
+    `transformers` `generate()` (un-vendored, unpinned, `docker/requirements.txt:9`; med.py is "based on v4.15.0" and only
+    imports under transformers of that era, which cannot be installed here and whose `generate()` cannot drive med.py under
+    the installed 5.5).  `beam_search_from_logits` restates the published v4.15.0 algorithm
     (`GenerationMixin.beam_search`, `BeamSearchScorer.process/finalize`, `BeamHypotheses.add/is_done`,
     `MinLengthLogitsProcessor`) with the arguments of the reference's call site (blip.py:150-158,
     run_video_CapFilt.py:102: num_beams 3, max_length 20, min_length 5, length_penalty 1.0, early_stopping False,
-    repetition_penalty 1.0) and is anchored on that call site only.
+    repetition_penalty 1.0).  The same function body also runs the rule set of the installed transformers (`rules="v5"`,
+    three lines differ — see RULES below), and under those rules it is token- and score-identical to the installed
+    `generate(num_beams=K)` on 120 searches of random language models (tests/test_beam_search_pin.py).  What stays
+    "parity unpinned" are the three v4.15-specific lines (hypothesis length normalisation, max_length normalisation,
+    operands of the stopping heuristic): anchored on the published source, the call site and hand-worked cases only.
 
 Plain functional tensor arithmetic on a parameter dict with the reference's state_dict keys.
 """
@@ -77,6 +82,22 @@ def embeddings(sd: dict, pre: str, input_ids: torch.Tensor, past_len: int, eps: 
     return F.layer_norm(x, (D,), sd[pre + "embeddings.LayerNorm.weight"], sd[pre + "embeddings.LayerNorm.bias"], eps)
 
 
+def _flash_emulated(s: torch.Tensor, v: torch.Tensor, block: int = 64) -> torch.Tensor:
+    """softmax(s) @ v computed the way the flash-style tensor-core kernels do (see attention_block)."""
+    m = torch.full(s.shape[:-1], float("-inf"), dtype=s.dtype, device=s.device)
+    l = torch.zeros_like(m)
+    o = torch.zeros(s.shape[:-1] + (v.shape[-1],), dtype=s.dtype, device=s.device)
+    for j0 in range(0, s.shape[-1], block):
+        sb = s[..., j0:j0 + block]
+        m_new = torch.maximum(m, sb.max(dim=-1).values)
+        corr = torch.exp(m - m_new)
+        p = torch.exp(sb - m_new[..., None])
+        l = l * corr + p.sum(dim=-1)
+        o = o * corr[..., None] + _r(p) @ v[..., j0:j0 + block, :]
+        m = m_new
+    return o / l[..., None]
+
+
 def _heads(x: torch.Tensor, H: int) -> torch.Tensor:
     B, T, D = x.shape
     return x.view(B, T, H, D // H).permute(0, 2, 1, 3)                                        # transpose_for_scores :141-144
@@ -94,8 +115,17 @@ def attention_block(sd: dict, p: str, x: torch.Tensor, kv_src: torch.Tensor, add
     s = q @ k.transpose(-1, -2) / math.sqrt(q.shape[-1])                                       # :184,:202
     if add_mask is not None:
         s = s + add_mask                                                                       # :205
-    pr = s.softmax(dim=-1)                                                                     # :208
-    ctx = _r((_r(pr) @ v).permute(0, 2, 1, 3).reshape(x.shape))                                # :222-226
+    if _OPERAND_DTYPE is None:
+        ctx = (s.softmax(dim=-1) @ v).permute(0, 2, 1, 3).reshape(x.shape)                     # :208, :222-226
+    elif kv_src is x and past is not None:
+        # one-token decode step of the self-attention (med_self_attn_decode_kernel): probabilities normalised in fp32 and
+        # multiplied with the 16-bit cached V without being rounded
+        ctx = _r((s.softmax(dim=-1) @ v).permute(0, 2, 1, 3).reshape(x.shape))
+    else:
+        # the tensor-core attentions (attention_x_kernel, cross_decode_mma_kernel): online softmax over 64-key blocks; the
+        # un-normalised exponentials are rounded to the operand type for P.V, the row sum accumulates them unrounded, and the
+        # output is divided by the sum at the end
+        ctx = _r(_flash_emulated(s, v).permute(0, 2, 1, 3).reshape(x.shape))
     out = _linear(ctx, sd[p + "output.dense.weight"], sd[p + "output.dense.bias"])
     D = x.shape[-1]
     out = F.layer_norm(out + x, (D,), sd[p + "output.LayerNorm.weight"], sd[p + "output.LayerNorm.bias"], eps)  # :245
@@ -176,21 +206,40 @@ class _BeamHyps:
         self.beams: list = []
         self.worst_score = 1e9
 
-    def add(self, hyp: list, sum_logprobs: float) -> None:
-        score = sum_logprobs / (len(hyp) ** self.length_penalty)
+    def add(self, hyp: list, sum_logprobs: float, norm_len: int | None = None) -> float:
+        """`norm_len`: the length the score is normalised by (v4.15: the hypothesis as stored, len(hyp)).
+        Returns the gap (in sum-of-log-probability units) by which the comparisons made here were decided."""
+        norm_len = len(hyp) if norm_len is None else norm_len
+        score = sum_logprobs / (norm_len ** self.length_penalty)
+        gap = math.inf
+        if len(self.beams) >= self.num_beams:
+            gap = abs(score - self.worst_score) * min(norm_len, min(n for _, _, n in self.beams)) ** self.length_penalty
         if len(self.beams) < self.num_beams or score > self.worst_score:
-            self.beams.append((score, hyp))
+            self.beams.append((score, hyp, norm_len))
             if len(self.beams) > self.num_beams:
-                ranked = sorted([(s, idx) for idx, (s, _) in enumerate(self.beams)])
+                ranked = sorted([(s, idx) for idx, (s, _, _) in enumerate(self.beams)])
                 del self.beams[ranked[0][1]]
                 self.worst_score = ranked[1][0]
             else:
                 self.worst_score = min(score, self.worst_score)
+        return gap
 
     def is_done(self, best_sum_logprobs: float, cur_len: int) -> bool:
         if len(self.beams) < self.num_beams:
             return False
         return self.worst_score >= best_sum_logprobs / cur_len ** self.length_penalty    # early_stopping False
+
+
+# What the vectorised beam search of transformers >= 4.50 (checked against the installed 5.5, generation/utils.py
+# `_beam_search` / `_update_finished_beams` / `_check_early_stop_heuristic`) does differently from v4.15 for the call-site
+# arguments of blip.py:150-158.  Everything else below is shared by the two rule sets, which is what lets the installed
+# transformers pin the restatement (tests/test_beam_search_pin.py) although it is not the version the reference ran:
+#   * a finished hypothesis is normalised by its generated length INCLUDING the eos and EXCLUDING the prompt,
+#     (cur_len + 1 - prompt_len); v4.15 divides by the stored hypothesis, prompt included, eos not (cur_len);
+#   * beams still open at max_length are normalised by (max_length - prompt_len); v4.15 by max_length;
+#   * the stopping heuristic compares the worst kept hypothesis with the best beam that stays OPEN after the step, over
+#     (cur_len + 1 - prompt_len); v4.15 with the best of all 2K candidates of the step (eos included), over cur_len.
+RULES = ("v4.15", "v5")
 
 
 def topk_candidates(scores: np.ndarray, k: int):
@@ -207,11 +256,37 @@ def topk_candidates(scores: np.ndarray, k: int):
     return scores[order], order
 
 
+def _step_margin(row: np.ndarray, K: int, V: int, eos: int, kept_min: float) -> float:
+    """How far one step's selection is from going the other way (see `margins` below): the gap between the K-th surviving
+    non-eos continuation and the best one dropped, and for every beam's eos candidate its distance from the score that
+    separates rank K-1 from rank K among the other candidates (an eos candidate counts only inside the first K)."""
+    eos_pos = np.arange(K) * V + eos
+    eos_scores = row[eos_pos].copy()
+    others = row.copy()
+    others[eos_pos] = -np.inf
+    top = np.sort(np.partition(others, others.size - (K + 1))[others.size - (K + 1):])[::-1]     # K+1 best non-eos, descending
+    assert top[K - 1] == kept_min
+    gap = float(top[K - 1] - top[K])
+    for j in range(K):
+        if np.isfinite(eos_scores[j]):
+            rest = np.sort(np.concatenate([top[:K], np.delete(eos_scores, j)]))[::-1]               # candidates that can outrank it
+            gap = min(gap, abs(float(eos_scores[j]) - float(rest[K - 1])))
+    return gap
+
+
 def beam_search_from_logits(step_logits, batch: int, prompt: list, num_beams: int = 3, max_length: int = 20,
-                            min_length: int = 5, eos: int = 102, pad: int = 0, length_penalty: float = 1.0):
+                            min_length: int = 5, eos: int = 102, pad: int = 0, length_penalty: float = 1.0,
+                            margins: list | None = None, rules: str = "v4.15"):
     """`step_logits(input_ids [batch*beams, n] (np.int64), beam_idx or None) -> fp32 logits [batch*beams, V]` is called
     once per step with the full current sequences and the beam reordering of the previous step.
-    Returns (tokens list per frame incl. a trailing eos when it fits, scores, state trace per step)."""
+    Returns (tokens list per frame incl. a trailing eos when it fits, scores, state trace per step).
+    `margins` (a list, filled with one float per frame): the smallest gap, in sum-of-log-probability units, by which any
+    comparison that shaped this frame's result was decided — which K continuations survive a step, whether an eos
+    candidate ranks inside the first K, every BeamHypotheses comparison, the stopping test and the final choice.  A path
+    whose candidate scores differ from this one's by less than half that gap necessarily returns the same tokens."""
+    assert rules in RULES
+    v5, P = rules == "v5", len(prompt)
+    margin = np.full(batch, np.inf)
     K = num_beams
     ids = np.tile(np.asarray(prompt, dtype=np.int64)[None], (batch * K, 1))
     beam_scores = np.zeros((batch, K), dtype=np.float32)
@@ -245,14 +320,19 @@ def beam_search_from_logits(step_logits, batch: int, prompt: list, num_beams: in
                 if tok == eos:
                     if rank >= K:
                         continue
-                    hyps[b].add(ids[row].tolist(), float(cs[rank]))
+                    margin[b] = min(margin[b], hyps[b].add(ids[row].tolist(), float(cs[rank]), cur_len + 1 - P if v5 else cur_len))
                 else:
                     nb_scores[b, slot], nb_tokens[b, slot], nb_idx[b, slot] = cs[rank], tok, row
                     slot += 1
                 if slot == K:
                     break
             assert slot == K
-            done[b] = done[b] or hyps[b].is_done(float(cs.max()), cur_len)
+            best_open, open_len = (float(nb_scores[b, 0]), cur_len + 1 - P) if v5 else (float(cs.max()), cur_len)
+            if margins is not None:
+                margin[b] = min(margin[b], _step_margin(scores[b], K, V, eos, float(nb_scores[b, K - 1])))
+                if len(hyps[b].beams) >= K:
+                    margin[b] = min(margin[b], abs(hyps[b].worst_score * open_len ** length_penalty - best_open))
+            done[b] = done[b] or hyps[b].is_done(best_open, open_len)
         beam_scores = nb_scores.reshape(-1)
         beam_idx = nb_idx.reshape(-1)
         ids = np.concatenate([ids[beam_idx], nb_tokens.reshape(-1, 1)], axis=1)
@@ -264,26 +344,32 @@ def beam_search_from_logits(step_logits, batch: int, prompt: list, num_beams: in
     for b in range(batch):                                                                # BeamSearchScorer.finalize
         if not done[b]:
             for j in range(K):
-                hyps[b].add(ids[b * K + j].tolist(), float(beam_scores[b * K + j]))
-        best = sorted(hyps[b].beams, key=lambda x: x[0]).pop()
+                margin[b] = min(margin[b], hyps[b].add(ids[b * K + j].tolist(), float(beam_scores[b * K + j]),
+                                                       max_length - P if v5 else None))
+        ranked = sorted(hyps[b].beams, key=lambda x: x[0])
+        if len(ranked) > 1:
+            margin[b] = min(margin[b], (ranked[-1][0] - ranked[-2][0]) * min(ranked[-1][2], ranked[-2][2]) ** length_penalty)
+        best = ranked.pop()
         seq = list(best[1])
         if len(seq) < max_length:
             seq.append(eos)
         out_tokens.append(seq)
         out_scores.append(best[0])
+    if margins is not None:
+        margins[:] = [float(x) for x in margin]
     return out_tokens, out_scores, trace
 
 
 @torch.no_grad()
 def generate(sd: dict, image_embeds: torch.Tensor, prompt: list, H: int, depth: int, pre: str = "text_decoder.",
              num_beams: int = 3, max_length: int = 20, min_length: int = 5, eos: int = 102, pad: int = 0,
-             length_penalty: float = 1.0, device=None, operand_dtype=None):
+             length_penalty: float = 1.0, device=None, operand_dtype=None, margins: list | None = None):
     """BLIP_Decoder.generate(sample=False), blip.py:127-167, from the image tokens on: repeat_interleave the image
     tokens over the beams (:130), run the cached decoder (prepare_inputs_for_generation / _reorder_cache, med.py:929-955)."""
     if operand_dtype is not None:
         with emulate(operand_dtype):
             return generate(sd, image_embeds, prompt, H, depth, pre, num_beams, max_length, min_length, eos, pad, length_penalty,
-                            device, None)
+                            device, None, margins)
     B = image_embeds.shape[0]
     dev = image_embeds.device if device is None else device   # `device`: where sd / image_embeds live (bench.py's eager-GPU baseline)
     enc = image_embeds.repeat_interleave(num_beams, dim=0)
@@ -301,4 +387,4 @@ def generate(sd: dict, image_embeds: torch.Tensor, prompt: list, H: int, depth: 
         state["past"] = presents
         return logits[:, -1, :].float().cpu().numpy()
 
-    return beam_search_from_logits(step, B, prompt, num_beams, max_length, min_length, eos, pad, length_penalty)
+    return beam_search_from_logits(step, B, prompt, num_beams, max_length, min_length, eos, pad, length_penalty, margins)

@@ -143,3 +143,37 @@ def test_beam_search_single_beam_is_greedy_and_scores_are_consistent():
                 greedy.append(nxt)
             expect = greedy + ([eos] if len(greedy) < max_length else [])
             assert toks[0] == expect and toks[1] == expect
+
+
+def test_decision_margins_bound_what_a_perturbation_can_change():
+    """`margins`: a frame whose every comparison was decided by more than the accumulated perturbation of the candidate scores
+    returns the same tokens under that perturbation (the property tests/test_gpu_med.py relies on to assert token equality
+    against 16-bit kernels), and some frames below the bound do change — the gate is not vacuous."""
+    rng = np.random.default_rng(0)
+    V, K, eos, max_length, min_length = 40, 3, 1, 12, 5
+    table = rng.standard_normal((V, max_length, V)).astype(np.float32)
+    noise = rng.uniform(-1.0, 1.0, (V, V, max_length, V)).astype(np.float32)
+
+    def lm(scale):
+        def step(ids, beam_idx):
+            cur = ids.shape[1]
+            return table[ids[:, -1], cur - 1] + 0.5 * table[ids[:, 0], cur - 1] + scale * noise[ids[:, 0], ids[:, -1], cur - 1]
+        return step
+
+    n_above, changed = {5e-4: 0, 3e-2: 0}, {5e-4: 0, 3e-2: 0}
+    for first in range(2, V):
+        for second in range(2, 12):
+            prompt = [first, second]
+            m = []
+            t0, _, _ = med_oracle.beam_search_from_logits(lm(0.0), 1, prompt, num_beams=K, max_length=max_length,
+                                                          min_length=min_length, eos=eos, pad=0, margins=m)
+            for eps in n_above:
+                t1, _, _ = med_oracle.beam_search_from_logits(lm(eps), 1, prompt, num_beams=K, max_length=max_length,
+                                                              min_length=min_length, eos=eos, pad=0)
+                # |noise| <= eps: a log-probability moves by at most 2 * eps per step, the difference of two by twice that
+                bound = 4 * eps * (max_length - len(prompt))
+                n_above[eps] += m[0] > bound
+                changed[eps] += t0 != t1
+                assert t0 == t1 or m[0] <= bound, (prompt, eps, m[0])
+    assert n_above[5e-4] > 50            # the small perturbation leaves many frames decided, and none of them moved
+    assert changed[3e-2] > 20            # the large one does change captions — only those the margin flagged
