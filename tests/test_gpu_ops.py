@@ -221,6 +221,25 @@ def test_sim_topk_clusters_of_near_synonyms(cuda):
         assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx), layout
 
 
+def test_sim_topk_best_entries_owned_by_one_lane(cuda):
+    """The selection kernel finds its threshold from four sorted heads per lane and falls back to a destructive extraction
+    when one lane owns more of the k best than that (csrc/topk.cu, step 1).  A lane's share of the tagged-score pool is
+    entry (lane + slice) mod 32 of every 32-entry slice, a group's best score is pool entry 4 * group: the best phrases of
+    groups 0, 33, 66, 99, 132 and 165 all belong to lane 0 — the fallback must give the oracle's ranking — and with the best
+    phrases in groups 0..5 (six different lanes) the fast path must."""
+    D, k = 768, 8
+    for groups in ([0, 33, 66, 99, 132, 165], [0, 1, 2, 3, 4, 5]):
+        bank = W.unit_rows(6000, D, seed=31)
+        cols = [g * 32 + 7 for g in groups]
+        img = sum((1.0 + 0.05 * j) * bank[c] for j, c in enumerate(cols)) + 0.5 * W.unit_rows(1, D, seed=32)[0]
+        img = torch.stack([img / img.norm(), W.unit_rows(1, D, seed=33)[0]])
+        ref_scores, ref_idx = tokenization_oracle.sim_topk(img.numpy(), bank.numpy(), k)
+        assert set(ref_idx[0][:6].tolist()) == set(cols)
+        scores, idx = ops.sim_topk(img.to(cuda), bank.to(cuda), k)
+        assert np.array_equal(idx.cpu().numpy().astype(np.int64), ref_idx), groups
+        assert np.abs(scores.cpu().numpy() - ref_scores).max() < 1e-5
+
+
 def test_sim_topk_cached_bank_equals_one_shot_and_follows_updates(cuda):
     """ops.sim_topk prepares a bank once per tensor (SimBank); the one-shot ABI call converts it inside the call.  Same
     result; an in-place update of the bank tensor is seen (the cache keys on the tensor's version)."""

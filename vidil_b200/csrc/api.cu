@@ -844,7 +844,7 @@ int32_t vidil_encoder_host_wait(vidil_encoder* enc, int32_t slot) {
 
 // ---- similarity + top-k ---------------------------------------------------------------------------
 // image_embeds @ text_embeds.t() -> per-frame top-k (run_visual_tokenization.py:276,306) without ever writing the [F, T]
-// score matrix: the fp16 tcgen05 GEMM's epilogue keeps the two best scores of every 32-phrase group (EPI_TOP2, 8 bytes per
+// score matrix: the fp16 tcgen05 GEMM's epilogue keeps the four best scores of every 32-phrase group (EPI_TOP4, 16 bytes per
 // group instead of 128), topk_select_kernel re-scores candidates in fp32 until the fp32 ranking is certain.
 }  // extern "C"
 
@@ -860,7 +860,7 @@ struct vidil_sim_bank {
 namespace {
 
 inline int sim_groups(int T) { return (T + 31) / 32; }
-inline int sim_ld(int T) { return 2 * ((sim_groups(T) + 1) & ~1); }  // floats per row of the EPI_TOP2 output, 16-byte multiple
+inline int sim_ld(int T) { return 4 * sim_groups(T); }  // floats per row of the EPI_TOP4 output
 
 struct SimWs {
     size_t img16, top2, total;
@@ -886,7 +886,7 @@ int sim_topk_core(const float* img, const void* bank16, const float* bank32, con
     if (cache == nullptr || cache->plan_F != F || cache->plan_ws != ws) {
         g = GemmProblem();
         g.dt = DT_FP16;
-        g.epi = EPI_TOP2;
+        g.epi = EPI_TOP4;
         g.cta_group = 2;
         g.M = F; g.N = T; g.K = D;
         g.A = img_h; g.lda = D;

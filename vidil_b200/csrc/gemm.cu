@@ -134,20 +134,25 @@ __device__ __forceinline__ void epilogue_chunk(float (&v)[32], const EpiArgs& e,
         for (int i = 0; i < 32; ++i) v[i] = quick_gelu(v[i]);
     }
 
-    if constexpr (EPI == EPI_TOP2) {
-        // Two largest of the 32 scores, each tagged with its position in the group in the 5 low mantissa bits (a perturbation
-        // of <= 2^-18 relative, far inside the margin the exact re-ranking allows for): three FMNMX + one LOP3 per score, no
-        // index registers, no divergence.  Columns beyond N (zero-filled W rows of the last tile) never qualify.
-        float m1 = -INFINITY, m2 = -INFINITY;
+    if constexpr (EPI == EPI_TOP4) {
+        // Four largest of the 32 scores, each tagged with its position in the group in the 5 low mantissa bits (a perturbation
+        // of <= 2^-18 relative, far inside the margin the exact re-ranking allows for): seven FMNMX + one LOP3 per score, no
+        // index registers, no divergence.  Columns beyond N (zero-filled W rows of the last tile) never qualify.  Four rather
+        // than two: the selection has to re-score a WHOLE group when the last entry it knows of is still above its bar, and
+        // with two entries that happened for 4 % of the frames (two of a frame's ~6 candidates in one group of 313), which made
+        // the one-wave selection kernel as slow as its unluckiest CTA; with four it needs five candidates in one group.
+        float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
             float t = __uint_as_float((__float_as_uint(v[i]) & 0xFFFFFFE0u) | static_cast<uint32_t>(i));
             if (!full && col0 + i >= N) t = -INFINITY;
+            m4 = fmaxf(m4, fminf(m3, t));
+            m3 = fmaxf(m3, fminf(m2, t));
             m2 = fmaxf(m2, fminf(m1, t));
             m1 = fmaxf(m1, t);
         }
-        float2* o = reinterpret_cast<float2*>(e.out) + static_cast<int64_t>(row) * (e.ldo >> 1) + (col0 >> 5);
-        *o = make_float2(m1, m2);
+        float4* o = reinterpret_cast<float4*>(e.out) + static_cast<int64_t>(row) * (e.ldo >> 2) + (col0 >> 5);
+        *o = make_float4(m1, m2, m3, m4);
     } else if constexpr (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_QUICKGELU) {
         T* o = reinterpret_cast<T*>(e.out) + static_cast<int64_t>(row) * e.ldo + col0;
         if (full) {
@@ -244,7 +249,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
     if (warp == 0 && lane == 0) {
         ptx::prefetch_tensormap(&map_a);
         ptx::prefetch_tensormap(&map_w);
-        if constexpr (EPI != EPI_PATCH && EPI != EPI_TOP2) ptx::prefetch_tensormap(&map_out);
+        if constexpr (EPI != EPI_PATCH && EPI != EPI_TOP4) ptx::prefetch_tensormap(&map_out);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -352,7 +357,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 1)
         const int ew = warp - 4;
         const int lane_quarter = ew & 3;  // TMEM lanes a warp may read: 32 * (warp % 4) ...
         const int col_half = ew >> 2;     // this warp's 128-column half of the 256-column accumulator
-        constexpr bool kTmaOut = (EPI != EPI_PATCH && EPI != EPI_TOP2);
+        constexpr bool kTmaOut = (EPI != EPI_PATCH && EPI != EPI_TOP4);
         constexpr bool kOut16 = (EPI == EPI_STORE || EPI == EPI_GELU || EPI == EPI_QUICKGELU);
         constexpr int PIECE_COLS = kOut16 ? 64 : 32;  // one staged piece is 32 rows x 128 bytes
         constexpr int PIECES = 128 / PIECE_COLS;
@@ -612,7 +617,7 @@ int dispatch_epi(const GemmProblem& p, cudaStream_t s) {
         case EPI_RESID: return launch<T, EPI_RESID, CG>(p, s);
         case EPI_PATCH: return launch<T, EPI_PATCH, CG>(p, s);
         case EPI_STORE_F32: return launch<T, EPI_STORE_F32, CG>(p, s);
-        case EPI_TOP2: return launch<T, EPI_TOP2, CG>(p, s);
+        case EPI_TOP4: return launch<T, EPI_TOP4, CG>(p, s);
         default: set_error("gemm: unknown epilogue mode %d", p.epi); return 1;
     }
 }
@@ -649,7 +654,7 @@ int gemm_prepare(GemmProblem& p) {
         set_error("gemm: operands must be 16-byte aligned with leading dimensions that are multiples of 8");
         return 1;
     }
-    const bool out_f32 = (p.epi == EPI_RESID || p.epi == EPI_PATCH || p.epi == EPI_STORE_F32 || p.epi == EPI_TOP2);
+    const bool out_f32 = (p.epi == EPI_RESID || p.epi == EPI_PATCH || p.epi == EPI_STORE_F32 || p.epi == EPI_TOP4);
     if (p.ldo % (out_f32 ? 4 : 8) != 0 || (reinterpret_cast<uintptr_t>(p.out) & 15)) {
         set_error("gemm: output must be 16-byte aligned with a 16-byte multiple leading dimension");
         return 1;
@@ -668,11 +673,11 @@ int gemm_prepare(GemmProblem& p) {
     }
     if (encode_operand_map(&p.map_a, p.dt, p.A, p.K, p.M, p.lda, BLOCK_M)) return 1;
     if (encode_operand_map(&p.map_w, p.dt, p.W, p.K, p.N, p.ldw, BLOCK_N / p.cta_group)) return 1;
-    if (p.epi == EPI_TOP2 && p.ldo < 2 * ((p.N + 31) / 32)) {
-        set_error("gemm: EPI_TOP2 needs ldo >= 2 * ceil(N / 32) floats per row");
+    if (p.epi == EPI_TOP4 && p.ldo < 4 * ((p.N + 31) / 32)) {
+        set_error("gemm: EPI_TOP4 needs ldo >= 4 * ceil(N / 32) floats per row");
         return 1;
     }
-    if (p.epi != EPI_PATCH && p.epi != EPI_TOP2) {
+    if (p.epi != EPI_PATCH && p.epi != EPI_TOP4) {
         const CUtensorMapDataType odt = out_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
                                                 : (p.dt == DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
         if (encode_output_map(&p.map_out, odt, out_f32 ? 4 : 2, p.out, p.N, p.M, p.ldo)) return 1;

@@ -20,7 +20,7 @@ enum EpiMode : int {
     EPI_RESID = 3,      // out[f32] += acc + bias                     (residual stream, vit.py:108-109)
     EPI_PATCH = 4,      // out[f32][frame*(P+1)+1+p] = acc + bias + pos[1+p]   (vit.py:182-187)
     EPI_STORE_F32 = 5,  // out[f32] = acc + bias
-    EPI_TOP2 = 6,       // out[f32][row][col / 32][2] = the two largest acc of every 32-column group, the column's position in the
+    EPI_TOP4 = 6,       // out[f32][row][col / 32][4] = the four largest acc of every 32-column group, the column's position in the
                         // group packed into the 5 low mantissa bits (similarity + top-k: the [M,N] scores are never written)
     EPI_COUNT = 7
 };
@@ -173,11 +173,11 @@ int clip_preprocess_run(const uint8_t* frames, int B, int H, int W, int S, const
 // ---------------------------------------------------------------------------------------
 // Similarity top-k (run_visual_tokenization.py:276,306).
 // ---------------------------------------------------------------------------------------
-// Exact top-k from the EPI_TOP2 output of the similarity GEMM: top2 [F][G][2] fp32 (G = ceil(T / 32) groups, index-tagged
-// approximate scores), img [F, D] / bank [T, D] fp32 originals.  Candidates are taken in order of approximate score and
-// re-scored in fp32 until the best remaining approximate score + eps_scale * |img row| * bank_max_norm cannot reach the
-// k-th exact score; a group whose second-best is taken is re-scored completely (a third member may hide behind it).
-int topk_select_run(const float* top2, int ld_top2, int G, const float* img, const float* bank, const float* bank_max_norm_dev, int F, int T, int D,
+// Exact top-k from the EPI_TOP4 output of the similarity GEMM: top4 [F][G][4] fp32 (G = ceil(T / 32) groups, index-tagged
+// approximate scores), img [F, D] / bank [T, D] fp32 originals.  Every entry within 2 * eps_scale * |img row| * bank_max_norm of
+// the k-th largest approximate score is re-scored in fp32; a group whose fourth-best qualifies is re-scored completely (a
+// fifth member may hide behind it).
+int topk_select_run(const float* top4, int ld_top4, int G, const float* img, const float* bank, const float* bank_max_norm_dev, int F, int T, int D,
                     int k, float* out_scores, int32_t* out_idx, cudaStream_t stream);
 // max over rows of ||row||_2 of an fp32 [rows, D] matrix -> out[0] (device)
 int max_row_norm_run(const float* m, int rows, int D, float* out, cudaStream_t stream);

@@ -60,6 +60,16 @@ __device__ __forceinline__ bool elect_one() {
 // its memory is visible, griddep_launch() lets the NEXT kernel of the stream start its own prologue.  Both are no-ops for a
 // kernel launched without the attribute.  Rule used throughout: nothing that reads or writes global memory precedes the wait.
 // ----------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+__device__ __forceinline__ uint32_t smid() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(r));
+    return r;
+}
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
@@ -162,6 +172,25 @@ __device__ __forceinline__ void cluster_sync() {
 // ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_tensormap(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
+}
+
+// 16 bytes global -> shared per thread without passing through a register (LDGSTS, L2-cached only); completion is per
+// issuing thread: commit the copies issued so far as a group, wait until at most N of the thread's groups are pending.
+__device__ __forceinline__ void cp_async_16(void* dst, const void* src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(src)) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// 1-D bulk copy global -> this CTA's shared memory (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned;
+// completion bytes land on `bar`.  One instruction moves a whole contiguous row without holding a register.
+__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
 }
 
 // 2-D tiled load into this CTA's shared memory; completion bytes land on `bar` (this CTA).
