@@ -15,6 +15,7 @@
  *                                        bicubic, centre crop, rescale, normalise)       -> vidil_clip_preprocess_frames
  *   models/blip.py:127-167 BLIP_Decoder.generate(sample=False) from the image tokens on: models/med.py:811-955
  *                                        BertLMHeadModel + transformers' beam search      -> vidil_med_generate
+ *                                        ... + transformers' nucleus sampling             -> vidil_med_sample
  *   models/blip_itm.py:49-57 text_encoder(mode multimodal) + itm_head; models/med.py:871-893 teacher-forced logits
  *                                                                                         -> vidil_med_forward
  *
@@ -229,6 +230,22 @@ int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_
                            int32_t min_length, int32_t eos_token, int32_t pad_token, float length_penalty, int32_t* out_tokens,
                            int32_t* out_lengths, float* out_scores, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Nucleus sampling, BLIP_Decoder.generate(sample=True) after the ViT (blip.py:139-148; run_video_CapFilt.py:104 with
+ * generation_mode "sample"): one sequence per frame, same prompt handling, K/V cache and early stop as vidil_med_generate with
+ * one beam (workspace: vidil_med_generate_workspace_bytes(..., num_beams = 1, ...)).  Every step applies, in transformers
+ * v4.15 order, RepetitionPenaltyLogitsProcessor (blip.py passes 1.1), MinLengthLogitsProcessor, TopKLogitsWarper (the
+ * PretrainedConfig default top_k = 50 that BLIP inherits) and TopPLogitsWarper, then draws from the softmax of what is left.
+ * The draw is an inverse-CDF lookup in descending-probability order with the caller's uniform numbers — `uniforms` fp32
+ * (device) [max_length - prompt_len, n_frames] in [0, 1), step-major — so a run is reproducible from its random stream;
+ * torch.multinomial's own stream cannot be reproduced, the distribution is the same.  Outputs as vidil_med_generate, except
+ * that out_tokens holds the sequence up to and including eos (no hypothesis selection) and out_scores the sum of the drawn
+ * tokens' log-probabilities under the sampled distributions.  top_k in [1, 1024]. */
+int32_t vidil_med_sample(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens,
+                         const int32_t* prompt_ids_host, int32_t prompt_len, int32_t max_length, int32_t min_length, int32_t eos_token,
+                         int32_t pad_token, int32_t top_k, float top_p, float repetition_penalty, const float* uniforms,
+                         int32_t* out_tokens, int32_t* out_lengths, float* out_scores, void* workspace, size_t workspace_bytes,
+                         void* stream);
+
 /* The search alone over given logits (parity of the bookkeeping): step_logits fp32 [n_steps, n_frames*num_beams, V]
  * (device) plays the decoder; step 0 reads the row of beam 0 of every frame. */
 size_t  vidil_op_beam_search_workspace_bytes(int32_t n_frames, int32_t num_beams, int32_t max_length);
@@ -236,6 +253,13 @@ int32_t vidil_op_beam_search(const float* step_logits, int32_t n_steps, int32_t 
                              const int32_t* prompt_ids_host, int32_t prompt_len, int32_t max_length, int32_t min_length,
                              int32_t eos_token, int32_t pad_token, float length_penalty, int32_t* out_tokens,
                              int32_t* out_lengths, float* out_scores, void* workspace, size_t workspace_bytes, void* stream);
+
+/* The sampling alone over given logits (parity of the processors / warpers and the draw): step_logits fp32
+ * [n_steps, n_frames, V] (device) plays the decoder; workspace: vidil_op_beam_search_workspace_bytes(n_frames, 1, max_length). */
+int32_t vidil_op_sample(const float* step_logits, int32_t n_steps, int32_t n_frames, int32_t V, const int32_t* prompt_ids_host,
+                        int32_t prompt_len, int32_t max_length, int32_t min_length, int32_t eos_token, int32_t pad_token, int32_t top_k,
+                        float top_p, float repetition_penalty, const float* uniforms, int32_t* out_tokens, int32_t* out_lengths,
+                        float* out_scores, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- frame pre-processing (run_video_CapFilt.py:128-137 process_frame) ------------------------- */
 /* frames_u8: device uint8 [B, H, W, 3] (decoded RGB frames, HWC) -> out: device fp32 [B, 3, S, S]:

@@ -360,6 +360,107 @@ def beam_search_from_logits(step_logits, batch: int, prompt: list, num_beams: in
     return out_tokens, out_scores, trace
 
 
+# ----------------------------------------------------------------------------------------------------------------------
+# Nucleus sampling — transformers v4.15.0 `GenerationMixin.sample` with the processors / warpers `generate(do_sample=True,
+# top_p=..., repetition_penalty=1.1, min_length=...)` builds (blip.py:141-148): RepetitionPenaltyLogitsProcessor,
+# MinLengthLogitsProcessor, then TopKLogitsWarper (the PretrainedConfig default top_k = 50 BLIP inherits) and
+# TopPLogitsWarper.  The four processors are pinned against the installed transformers' own classes
+# (tests/test_beam_search_pin.py::test_sampling_processors_equal_installed_transformers); the draw itself is an inverse-CDF
+# lookup with caller-supplied uniform numbers, because torch.multinomial's stream cannot be reproduced by another
+# implementation — what is compared with the native path is the same lookup on the same numbers.
+# ----------------------------------------------------------------------------------------------------------------------
+def process_sampling_scores(logits: np.ndarray, seq: np.ndarray, cur_len: int, min_length: int, eos: int, top_k: int = 50,
+                            top_p: float = 0.9, repetition_penalty: float = 1.1):
+    """One row: fp32 logits [V] and the tokens so far -> (token ids kept, in descending score order, ties by ascending id;
+    their processed scores).  v4.15 logits_process.py: RepetitionPenalty :146-158, MinLength :96-107, TopK :223-241 (keeps ties
+    at the k-th value), TopP :173-206 (a token goes once the probability mass before it exceeds top_p)."""
+    x = np.asarray(logits, dtype=np.float32).copy()
+    seen = np.unique(np.asarray(seq, dtype=np.int64))
+    x[seen] = np.where(x[seen] < 0, x[seen] * np.float32(repetition_penalty), x[seen] / np.float32(repetition_penalty))
+    if cur_len < min_length:
+        x[eos] = -np.inf
+    order = np.lexsort((np.arange(x.size), -x))                       # score descending, id ascending among equals
+    order = order[np.isfinite(x[order])]
+    if order.size > top_k:
+        kth = x[order[top_k - 1]]
+        order = order[x[order] >= kth]
+    v = x[order]
+    e = np.exp(v - v[0], dtype=np.float32)
+    total = np.float32(0.0)
+    for t in e:                                                        # the same sequential fp32 sums as the kernel
+        total = np.float32(total + t)
+    keep, cum = 0, np.float32(0.0)
+    for j in range(order.size):
+        if j > 0 and np.float32(cum / total) > np.float32(top_p):
+            break
+        cum = np.float32(cum + e[j])
+        keep += 1
+    return order[:keep], v[:keep]
+
+
+def sample_from_logits(step_logits, batch: int, prompt: list, uniforms: np.ndarray, max_length: int = 20, min_length: int = 5,
+                       eos: int = 102, pad: int = 0, top_k: int = 50, top_p: float = 0.9, repetition_penalty: float = 1.1):
+    """`step_logits(input_ids [batch, n], None) -> fp32 logits [batch, V]` as in beam_search_from_logits.  uniforms
+    [max_length - len(prompt), batch].  Returns (token lists incl. eos, sums of the drawn tokens' log-probabilities)."""
+    ids = np.tile(np.asarray(prompt, dtype=np.int64)[None], (batch, 1))
+    unfinished = np.ones(batch, dtype=bool)
+    logp = np.zeros(batch, dtype=np.float32)
+    step = 0
+    while True:
+        cur_len = ids.shape[1]
+        logits = np.asarray(step_logits(ids, None), dtype=np.float32)
+        nxt = np.full(batch, pad, dtype=np.int64)
+        for b in range(batch):
+            if not unfinished[b]:
+                continue
+            toks, v = process_sampling_scores(logits[b], ids[b], cur_len, min_length, eos, top_k, top_p, repetition_penalty)
+            e = np.exp(v - v[0], dtype=np.float32)
+            mass = np.float32(0.0)
+            for t in e:
+                mass = np.float32(mass + t)
+            target = np.float32(np.float32(uniforms[step, b]) * mass)
+            pick, run = len(toks) - 1, np.float32(0.0)
+            for j in range(len(toks)):
+                run = np.float32(run + e[j])
+                if run > target:
+                    pick = j
+                    break
+            nxt[b] = toks[pick]
+            logp[b] += np.float32((v[pick] - v[0]) - np.log(mass, dtype=np.float32))
+        ids = np.concatenate([ids, nxt[:, None]], axis=1)
+        unfinished &= nxt != eos
+        step += 1
+        if not unfinished.any() or ids.shape[1] >= max_length:
+            break
+    out = []
+    for b in range(batch):
+        seq = ids[b].tolist()
+        if eos in seq[len(prompt):]:
+            seq = seq[:len(prompt) + seq[len(prompt):].index(eos) + 1]
+        out.append(seq)
+    return out, logp
+
+
+@torch.no_grad()
+def generate_sample(sd: dict, image_embeds: torch.Tensor, prompt: list, H: int, depth: int, uniforms, pre: str = "text_decoder.",
+                    max_length: int = 20, min_length: int = 5, eos: int = 102, pad: int = 0, top_k: int = 50, top_p: float = 0.9,
+                    repetition_penalty: float = 1.1, operand_dtype=None):
+    """BLIP_Decoder.generate(sample=True), blip.py:139-148, from the image tokens on (cached decoder, one sequence per frame)."""
+    if operand_dtype is not None:
+        with emulate(operand_dtype):
+            return generate_sample(sd, image_embeds, prompt, H, depth, uniforms, pre, max_length, min_length, eos, pad, top_k, top_p,
+                                   repetition_penalty, None)
+    state = {"past": None}
+
+    def step(ids, _):
+        inp = torch.from_numpy(ids if state["past"] is None else ids[:, -1:])
+        logits, state["past"] = decoder_logits(sd, pre, inp, image_embeds, H, depth, state["past"])
+        return logits[:, -1, :].float().numpy()
+
+    return sample_from_logits(step, image_embeds.shape[0], prompt, np.asarray(uniforms, dtype=np.float32), max_length, min_length, eos,
+                              pad, top_k, top_p, repetition_penalty)
+
+
 @torch.no_grad()
 def generate(sd: dict, image_embeds: torch.Tensor, prompt: list, H: int, depth: int, pre: str = "text_decoder.",
              num_beams: int = 3, max_length: int = 20, min_length: int = 5, eos: int = 102, pad: int = 0,

@@ -93,6 +93,7 @@ def test_text_stack_entry_points_fail_loudly_without_a_gpu():
     assert len(_lib.last_error()) > 0
     assert lib.vidil_med_generate(None, None, 1, 1, None, 4, 3, 20, 5, 102, 0, 1.0, None, None, None, None, 0, None) != 0
     assert lib.vidil_med_forward(None, None, 1, 1, None, None, None, 0, 1, 8, 1, None, None, None, None, 0, None) != 0
+    assert lib.vidil_med_sample(None, None, 1, 1, None, 4, 20, 5, 102, 0, 50, 0.9, 1.1, None, None, None, None, None, 0, None) != 0
     buf = (ctypes.c_float * 64)()
     prompt = (ctypes.c_int32 * 4)(1, 2, 3, 4)
     # argument checks come first and name the offending values

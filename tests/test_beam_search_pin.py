@@ -90,3 +90,34 @@ def test_batched_search_equals_per_frame_search():
             t, s, _ = med_oracle.beam_search_from_logits(make_step([b]), 1, prompt, num_beams=K, max_length=12, min_length=4,
                                                          eos=1, pad=0, rules=rules)
             assert t[0] == all_t[b] and abs(s[0] - all_s[b]) < 1e-6
+
+
+def test_sampling_processors_equal_installed_transformers():
+    """The processors and warpers of the sampling path (blip.py:141-148: repetition_penalty 1.1, min_length, the inherited
+    top_k 50, top_p 0.9) as restated in med_oracle.process_sampling_scores keep exactly the tokens, with exactly the scores,
+    that the installed transformers' own RepetitionPenaltyLogitsProcessor -> MinLengthLogitsProcessor -> TopKLogitsWarper ->
+    TopPLogitsWarper chain keeps.  (Installed TopP sorts ascending and drops mass <= 1 - top_p, v4.15 sorts descending and drops
+    what follows mass > top_p: the same set except at exact equality.  Rows with exactly tied scores are compared by the
+    multiset of kept scores: which of two tied tokens survives a cut between them is sort-order dependent in transformers.)"""
+    lp = pytest.importorskip("transformers.generation.logits_process")
+    rng = np.random.default_rng(0)
+    for trial in range(300):
+        V = int(rng.choice([40, 200, 3000]))
+        logits = (rng.standard_normal(V) * rng.choice([0.5, 2.0, 6.0])).astype(np.float32)
+        tied = trial % 5 == 0
+        if tied:
+            logits[rng.integers(0, V, 10)] = logits[0]
+        seq = rng.integers(0, V, size=int(rng.integers(1, 12)))
+        min_length, eos = int(rng.choice([0, 5, 20])), 1
+        top_k, top_p = int(rng.choice([5, 50])), float(rng.choice([0.5, 0.9, 0.99]))
+        chain = lp.LogitsProcessorList([lp.RepetitionPenaltyLogitsProcessor(1.1), lp.MinLengthLogitsProcessor(min_length, eos),
+                                        lp.TopKLogitsWarper(top_k), lp.TopPLogitsWarper(top_p)])
+        out = chain(torch.from_numpy(seq)[None].long(), torch.from_numpy(logits)[None].clone())[0].numpy()
+        toks, v = med_oracle.process_sampling_scores(logits, seq, len(seq), min_length, eos, top_k, top_p, 1.1)
+        kept = np.nonzero(np.isfinite(out))[0]
+        if tied:
+            assert np.allclose(np.sort(out[kept]), np.sort(v), rtol=1e-6)
+        else:
+            assert set(kept.tolist()) == set(toks.tolist()), trial
+            assert np.allclose(out[toks], v, rtol=1e-6)
+        assert np.all(np.diff(v) <= 0)                             # descending: the order the draw walks

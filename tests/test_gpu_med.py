@@ -104,6 +104,83 @@ def test_beam_search_op_known_answer(cuda):
     assert abs(scores[0] - (2 * np.log(0.3) + np.log(0.6)) / 3) < 1e-4
 
 
+# ---- nucleus sampling: the processors, warpers and the draw alone, on given logits and given uniform numbers ---------------
+def _op_sample(dev, L, F, V, prompt, uniforms, max_length, min_length, eos, pad=0, top_k=50, top_p=0.9, rep=1.1):
+    lib = _lib.load()
+    S = len(L)
+    logits = torch.from_numpy(np.stack(L)).to(dev).contiguous()
+    uni = torch.from_numpy(np.ascontiguousarray(uniforms, dtype=np.float32)).to(dev)
+    need = lib.vidil_op_beam_search_workspace_bytes(F, 1, max_length)
+    buf = torch.empty(need + 1024, dtype=torch.uint8, device=dev)
+    off = (-buf.data_ptr()) % 1024
+    toks = torch.empty(F, max_length, dtype=torch.int32, device=dev)
+    lens = torch.empty(F, dtype=torch.int32, device=dev)
+    scores = torch.empty(F, dtype=torch.float32, device=dev)
+    p = (ctypes.c_int32 * len(prompt))(*prompt)
+    st = lib.vidil_op_sample(logits.data_ptr(), S, F, V, ctypes.cast(p, ctypes.c_void_p), len(prompt), max_length, min_length, eos, pad,
+                             top_k, top_p, rep, uni.data_ptr(), toks.data_ptr(), lens.data_ptr(), scores.data_ptr(), buf.data_ptr() + off,
+                             need, torch.cuda.current_stream().cuda_stream)
+    _lib.check(st, "vidil_op_sample")
+    torch.cuda.synchronize()
+    return [toks[b, :int(lens[b])].tolist() for b in range(F)], scores.cpu().numpy(), toks.cpu().numpy()
+
+
+@pytest.mark.parametrize("V,top_k,top_p,scale,eos_boost,quantise", [(200, 50, 0.9, 2.0, 3.0, False), (30524, 50, 0.9, 1.0, 6.0, False),
+                                                                    (30524, 50, 0.9, 4.0, 9.0, False), (64, 5, 0.5, 2.0, 2.0, False),
+                                                                    (400, 50, 0.99, 0.5, 1.0, False), (200, 50, 0.9, 2.0, 3.0, True),
+                                                                    (2048, 1000, 0.999, 0.01, 0.0, False)])
+def test_sample_op_matches_oracle(cuda, V, top_k, top_p, scale, eos_boost, quantise):
+    """Same logits, same uniform numbers: the drawn tokens are those of the oracle (med_oracle.sample_from_logits, whose
+    processors are pinned against transformers' own classes).  Covers the real vocabulary, a flat row with more than 256
+    survivors, quantised rows full of exact ties, an early and a late eos."""
+    F, prompt, max_length, min_length, eos, pad = 9, [V - 2, 5, 9, 11], 16, 7, 2, 0
+    rng = np.random.default_rng(V + top_k)
+    S = max_length - len(prompt)
+    L = []
+    for s in range(S):
+        x = rng.standard_normal((F, V)).astype(np.float32) * scale
+        x[:, eos] += eos_boost * rng.random((F,)).astype(np.float32) * 2
+        if quantise:
+            x = np.round(x * 2) / 2
+        L.append(x)
+    uniforms = rng.random((S, F)).astype(np.float32)
+    it = iter(L)
+    ref, ref_logp = med_oracle.sample_from_logits(lambda ids, _: next(it), F, prompt, uniforms, max_length, min_length, eos, pad, top_k,
+                                                  top_p, 1.1)
+    toks, logp, raw = _op_sample(cuda, L, F, V, prompt, uniforms, max_length, min_length, eos, pad, top_k, top_p, 1.1)
+    same = sum(t == r for t, r in zip(toks, ref))
+    print(f"sample op V={V} top_k={top_k}: {same}/{F} sequences identical")
+    # one draw in ~10^5 can land within fp32 rounding of a boundary of the cumulative distribution (expf vs numpy's exp)
+    assert same >= F - 1
+    assert all(eos not in t[len(prompt):min_length] for t in toks)
+    for b, t in enumerate(toks):
+        assert (raw[b, len(t):] == pad).all()
+        if t == ref[b]:
+            assert abs(logp[b] - ref_logp[b]) < 1e-3
+    if eos_boost >= 3.0:
+        assert any(t[-1] == eos and len(t) < max_length for t in toks), "the case should exercise finished frames"
+
+
+def test_sample_op_zero_uniform_is_greedy_and_draws_follow_the_distribution(cuda):
+    """u = 0 takes the most probable surviving token at every step; and over many frames with the SAME logits the drawn
+    tokens follow the renormalised top-k / top-p distribution (chi-square against the oracle's probabilities)."""
+    V, eos, pad, prompt = 200, 2, 0, [7, 9]
+    rng = np.random.default_rng(11)
+    row = (rng.standard_normal(V) * 1.5).astype(np.float32)
+    n = 4096
+    L = [np.tile(row, (n, 1))]
+    toks, _, _ = _op_sample(cuda, L, n, V, prompt, np.zeros((1, n), np.float32), 3, 0, eos, pad)
+    kept, v = med_oracle.process_sampling_scores(row, np.array(prompt), 2, 0, eos, 50, 0.9, 1.1)
+    assert all(t[2] == kept[0] for t in toks)
+    toks, _, _ = _op_sample(cuda, L, n, V, prompt, rng.random((1, n)).astype(np.float32), 3, 0, eos, pad)
+    drawn = np.array([t[2] for t in toks])
+    assert set(drawn.tolist()) <= set(kept.tolist())
+    p = np.exp(v - v[0])
+    p /= p.sum()
+    counts = np.array([(drawn == k).sum() for k in kept])
+    assert (((counts - n * p) ** 2) / (n * p)).sum() < 3 * len(kept) + 20
+
+
 # ---- network arithmetic ------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dtype", ["fp16", "bf16"])
 def test_decoder_logits_tiny_vs_fixture_and_oracle(cuda, golden_dir, dtype):
@@ -316,8 +393,14 @@ def test_med_errors_are_loud(cuda):
     enc = W.image_tokens(2, 5, 128, seed=0)
     with pytest.raises(RuntimeError):          # CPU tensors: no fallback
         m(torch.tensor([sp["prompt"]] * 2), encoder_hidden_states=enc)
-    with pytest.raises(NotImplementedError):
-        m.generate(input_ids=torch.tensor([sp["prompt"]] * 2), do_sample=True, eos_token_id=sp["eos"],
+    with pytest.raises(NotImplementedError):   # sampling is built as blip.py calls it: one beam
+        m.generate(input_ids=torch.tensor([sp["prompt"]] * 2), do_sample=True, num_beams=3, eos_token_id=sp["eos"],
+                   encoder_hidden_states=enc.to(cuda))
+    with pytest.raises(NotImplementedError):   # the beam-search path of the reference never sets a repetition penalty
+        m.generate(input_ids=torch.tensor([sp["prompt"]] * 2), num_beams=3, repetition_penalty=1.1, eos_token_id=sp["eos"],
+                   encoder_hidden_states=enc.to(cuda))
+    with pytest.raises(RuntimeError):          # top_k beyond what the sampling kernel's candidate list holds
+        m.generate(input_ids=torch.tensor([sp["prompt"]] * 2), do_sample=True, top_k=5000, eos_token_id=sp["eos"],
                    encoder_hidden_states=enc.to(cuda))
     with pytest.raises(RuntimeError):          # max_length beyond the 64-token limit of the search state
         m.generate(input_ids=torch.tensor([sp["prompt"]] * 2), max_length=100, num_beams=3, eos_token_id=sp["eos"],
@@ -457,3 +540,40 @@ def test_generate_stops_early_when_all_frames_are_done(cuda):
     assert np.allclose(scores.cpu().numpy(), np.asarray(ref_scores, dtype=np.float32), atol=2e-2)
     per_step = 2 * 17 + 8                                                       # kernels of one tiny decode step (2 layers)
     assert launches < 12 * per_step, f"{launches} kernels: the search did not stop early (a 36-step run takes > {30 * per_step})"
+
+
+@pytest.mark.parametrize("dtype", ["fp16", "bf16"])
+def test_generate_sample_tiny_vs_oracle(cuda, dtype):
+    """BLIP_Decoder.generate(sample=True) from the image tokens on (blip.py:139-148: top_p 0.9, repetition_penalty 1.1, inherited
+    top_k 50) against the oracle's cached decoder driving the same draws.  16-bit operands move a logit by ~1e-2, which moves
+    a boundary of the cumulative distribution by ~1e-3 of probability: a few draws in a hundred may fall on the other side, and
+    the sequences differ from there on — so most sequences, not all, are identical; every sequence obeys the rules."""
+    name = "tiny"
+    m, sd = _decoder(name, dtype, cuda)
+    c, sp = W.MED_CONFIGS[name], W.MED_SPECIAL[name]
+    F, n_img, max_length, min_length = 32, 5, 14, 6
+    enc = W.image_tokens(F, n_img, c["encoder_width"], seed=5)
+    prompt = torch.tensor([sp["prompt"]], dtype=torch.long).repeat(F, 1)
+    uniforms = torch.rand(max_length - len(sp["prompt"]), F, generator=torch.Generator().manual_seed(7))
+    out, logp, lens = m.generate(input_ids=prompt, max_length=max_length, min_length=min_length, do_sample=True, top_p=0.9,
+                                 eos_token_id=sp["eos"], pad_token_id=sp["pad"], repetition_penalty=1.1,
+                                 encoder_hidden_states=enc.to(cuda), return_scores=True, uniforms=uniforms)
+    ref, ref_logp = med_oracle.generate_sample(sd, enc, sp["prompt"], c["num_attention_heads"], c["num_hidden_layers"], uniforms.numpy(),
+                                               max_length=max_length, min_length=min_length, eos=sp["eos"], pad=sp["pad"],
+                                               operand_dtype=_TORCH_DT[dtype])
+    got = [out[b, :int(lens[b])].tolist() for b in range(F)]
+    same = sum(g == r for g, r in zip(got, ref))
+    print(f"generate(sample=True) tiny {dtype}: {same}/{F} sequences identical to the oracle's")
+    assert same >= (F * 3) // 4
+    for g in got:
+        assert g[:4] == sp["prompt"] and sp["eos"] not in g[4:min_length] and len(g) <= max_length
+        assert g[-1] == sp["eos"] or len(g) == max_length
+    assert out.shape[1] == max(len(g) for g in got)
+    # reproducible from the random stream: a generator seed gives the same captions twice, another seed other captions
+    a = m.generate(input_ids=prompt, max_length=max_length, min_length=min_length, do_sample=True, top_p=0.9, eos_token_id=sp["eos"],
+                   pad_token_id=sp["pad"], repetition_penalty=1.1, encoder_hidden_states=enc.to(cuda), generator=torch.Generator().manual_seed(1))
+    b = m.generate(input_ids=prompt, max_length=max_length, min_length=min_length, do_sample=True, top_p=0.9, eos_token_id=sp["eos"],
+                   pad_token_id=sp["pad"], repetition_penalty=1.1, encoder_hidden_states=enc.to(cuda), generator=torch.Generator().manual_seed(1))
+    d = m.generate(input_ids=prompt, max_length=max_length, min_length=min_length, do_sample=True, top_p=0.9, eos_token_id=sp["eos"],
+                   pad_token_id=sp["pad"], repetition_penalty=1.1, encoder_hidden_states=enc.to(cuda), generator=torch.Generator().manual_seed(2))
+    assert torch.equal(a, b) and (a.shape != d.shape or not torch.equal(a, d))

@@ -177,3 +177,49 @@ def test_decision_margins_bound_what_a_perturbation_can_change():
                 assert t0 == t1 or m[0] <= bound, (prompt, eps, m[0])
     assert n_above[5e-4] > 50            # the small perturbation leaves many frames decided, and none of them moved
     assert changed[3e-2] > 20            # the large one does change captions — only those the margin flagged
+
+
+def _sampling_lm(V, seed=0):
+    table = np.random.default_rng(seed).standard_normal((V, V)).astype(np.float32) * 2.0
+    return lambda ids, _: table[ids[:, -1]]
+
+
+def test_sampling_oracle_known_answers():
+    """u = 0 always takes the most probable surviving token; a banned eos cannot be drawn before min_length; a frame that has
+    drawn eos is padded while the others go on; the sequence ends with eos."""
+    V, eos, pad = 30, 1, 0
+    lm = _sampling_lm(V)
+    steps, B = 8, 3
+    toks, logp = med_oracle.sample_from_logits(lm, B, [5, 7], np.zeros((steps, B), np.float32), max_length=10, min_length=6, eos=eos, pad=pad)
+    ids = np.array([5, 7])
+    expect = [5, 7]
+    for _ in range(steps):
+        kept, _ = med_oracle.process_sampling_scores(lm(np.array([expect]), None)[0], np.array(expect), len(expect), 6, eos)
+        expect.append(int(kept[0]))
+        if expect[-1] == eos:
+            break
+    assert toks[0] == expect and toks[1] == expect
+    assert all(eos not in t[:6] for t in toks)
+    # an eos-heavy model: every frame stops right at min_length
+    table = np.zeros((V, V), np.float32)
+    table[:, eos] = 10.0
+    toks, _ = med_oracle.sample_from_logits(lambda ids, _: table[ids[:, -1]], 2, [5, 7], np.full((8, 2), 0.3, np.float32), max_length=10,
+                                            min_length=4, eos=eos, pad=pad)
+    assert all(len(t) == 5 and t[-1] == eos for t in toks)
+
+
+def test_sampling_oracle_draws_follow_the_filtered_distribution():
+    """Inverse-CDF draws with uniform numbers reproduce the renormalised top-k / top-p distribution (chi-square)."""
+    V, eos = 50, 1
+    rng = np.random.default_rng(3)
+    logits = (rng.standard_normal(V) * 1.5).astype(np.float32)
+    kept, v = med_oracle.process_sampling_scores(logits, np.array([3, 4]), 2, 0, eos, top_k=20, top_p=0.9, repetition_penalty=1.1)
+    p = np.exp(v - v[0]); p /= p.sum()
+    n = 20000
+    toks, _ = med_oracle.sample_from_logits(lambda ids, _: np.tile(logits, (ids.shape[0], 1)), n, [3, 4],
+                                            rng.random((1, n)).astype(np.float32), max_length=3, min_length=0, eos=eos, top_k=20)
+    drawn = np.array([t[2] for t in toks])
+    assert set(drawn.tolist()) <= set(kept.tolist())
+    counts = np.array([(drawn == k).sum() for k in kept])
+    chi2 = ((counts - n * p) ** 2 / (n * p)).sum()
+    assert chi2 < 3 * len(kept) + 20

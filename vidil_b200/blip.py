@@ -114,24 +114,33 @@ class BLIP_Decoder(nn.Module):
         raise NotImplementedError("the LM training loss (models/blip.py:104-125) is outside the inference hot path")
 
     @torch.no_grad()
-    def generate_ids(self, image, num_beams=3, max_length=30, min_length=10, repetition_penalty=1.0, return_scores=False):
-        """blip.py:127-158 up to the token ids: ViT -> beam search; returns int64 [B, L] (prompt included)."""
+    def generate_ids(self, image, num_beams=3, max_length=30, min_length=10, repetition_penalty=1.0, return_scores=False,
+                     sample=False, top_p=0.9, generator=None):
+        """blip.py:127-158 up to the token ids: ViT -> beam search (or, sample=True, nucleus sampling with the reference's
+        repetition_penalty 1.1, blip.py:139-148); returns int64 [B, L] (prompt included)."""
         image_embeds = self.visual_encoder(image)                                              # :128
         input_ids = torch.tensor([self._prompt_ids], dtype=torch.long).repeat(image.size(0), 1)  # :133-134
         input_ids[:, 0] = self.bos_token_id                                                    # :136
         input_ids = input_ids[:, :-1]                                                          # :137
+        if sample:
+            return self.text_decoder.generate(input_ids=input_ids, max_length=max_length, min_length=min_length, do_sample=True,
+                                              top_p=top_p, num_return_sequences=1, eos_token_id=self.sep_token_id,
+                                              pad_token_id=self.pad_token_id, repetition_penalty=1.1,   # :141-148
+                                              encoder_hidden_states=image_embeds, return_scores=return_scores, generator=generator)
         return self.text_decoder.generate(input_ids=input_ids, max_length=max_length, min_length=min_length, num_beams=num_beams,
                                           eos_token_id=self.sep_token_id, pad_token_id=self.pad_token_id,
                                           repetition_penalty=repetition_penalty, encoder_hidden_states=image_embeds,
                                           return_scores=return_scores)
 
     @torch.no_grad()
-    def generate(self, image, sample=False, num_beams=3, max_length=30, min_length=10, top_p=0.9, repetition_penalty=1.0):
+    def generate(self, image, sample=False, num_beams=3, max_length=30, min_length=10, top_p=0.9, repetition_penalty=1.0,
+                 generator=None):
         """Same signature and result as models/blip.py:127-167 (list of caption strings with the prompt stripped); without a
-        tokenizer the captions are lists of token ids after the prompt, special tokens removed."""
-        if sample:
-            raise NotImplementedError("nucleus sampling is not built; the shipped pipeline configs use generation_mode 'beam'")
-        outputs = self.generate_ids(image, num_beams, max_length, min_length, repetition_penalty).cpu()
+        tokenizer the captions are lists of token ids after the prompt, special tokens removed.  sample=True draws with
+        torch's global CPU generator (or `generator`): reproducible under torch.manual_seed like the reference, though not
+        draw-for-draw identical to torch.multinomial."""
+        outputs = self.generate_ids(image, num_beams, max_length, min_length, repetition_penalty, sample=sample, top_p=top_p,
+                                    generator=generator).cpu()
         captions = []
         for output in outputs:
             if self.tokenizer is not None:

@@ -242,6 +242,12 @@ int med_logits_topk_run(const float* logits, int64_t ld, int row_mul, const floa
 int med_beam_init_run(const BeamState& st, const int32_t* prompt_dev, int prompt_len, cudaStream_t s);
 int med_beam_step_run(const BeamState& st, const float* cand_score, const int32_t* cand_tok, int lists_per_frame, int nc, int V,
                       int cur_len, int parity, cudaStream_t s);
+// nucleus sampling (one beam): frame b draws its next token from logits row b after repetition penalty, MinLength (ban_token),
+// top-k and top-p, by inverse CDF with uniforms_dev[b]; finished frames emit pad
+int med_sample_step_run(const BeamState& st, const float* logits, int64_t ld, int V, int cur_len, int ban_token, int top_k, float top_p,
+                        float repetition_penalty, const float* uniforms_dev, cudaStream_t s);
+int med_sample_finalize_run(const BeamState& st, int cur_len, int max_length, int32_t* out_tokens, int32_t* out_len, float* out_score,
+                            cudaStream_t s);
 int med_beam_finalize_run(const BeamState& st, int cur_len, int parity, int max_length, int32_t* out_tokens, int32_t* out_len,
                           float* out_score, cudaStream_t s);
 int med_cls_head_run(const float* hidden, const float* W, const float* bias, float* out, int n_seq, int T, int D, int n_out,

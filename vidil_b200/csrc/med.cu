@@ -562,6 +562,204 @@ __global__ void med_beam_init_kernel(BeamState st, const int32_t* __restrict__ p
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Nucleus sampling step (BLIP_Decoder.generate(sample=True), blip.py:139-148 -> transformers v4.15 `sample()`): on the raw
+// logits of the step, RepetitionPenaltyLogitsProcessor (tokens of the sequence so far: x < 0 ? x * p : x / p), then
+// MinLengthLogitsProcessor, then the warpers — TopKLogitsWarper (config default top_k = 50: everything below the k-th largest
+// value goes, ties at it stay) and TopPLogitsWarper (descending order, a token goes once the probability mass BEFORE it
+// exceeds top_p) — softmax over what is left and one draw.  The draw is an inverse-CDF lookup in that descending order with a
+// uniform number supplied by the caller (torch.multinomial's own stream cannot be reproduced; the distribution is the same).
+// One CTA per frame; finished frames emit pad.  With one beam the ping-pong sequence buffers of the beam search hold the same
+// tokens, so both are written.
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int SP_CAP = 1024;  // tokens that can survive top-k (ties included)
+
+__device__ __forceinline__ uint32_t sp_ordered(float v) {  // monotonic float -> uint
+    const uint32_t u = __float_as_uint(v);
+    return u ^ ((u >> 31) ? 0xffffffffu : 0x80000000u);
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+    med_sample_step_kernel(BeamState st, const float* __restrict__ logits, int64_t ld, int V, int cur_len, int ban_token, int top_k,
+                           float top_p, float rep_pen, const float* __restrict__ uniforms) {
+    extern __shared__ uint32_t sp_seen[];  // one bit per token: is it in the sequence so far
+    __shared__ float c_v[SP_CAP];
+    __shared__ int c_i[SP_CAP];
+    __shared__ int s_cnt;
+    const int b = blockIdx.x, t = threadIdx.x;
+    const int Tm = st.t_max;
+    int32_t* seq0 = st.seq + static_cast<int64_t>(b) * Tm;
+    int32_t* seq1 = st.seq + (static_cast<int64_t>(st.frames) + b) * Tm;
+    if (st.done[b]) {  // block-uniform
+        if (t == 0) {
+            seq0[cur_len] = st.pad;
+            seq1[cur_len] = st.pad;
+            st.cur_tok[b] = st.pad;
+        }
+        return;
+    }
+    const int words = (V + 31) >> 5;
+    for (int i = t; i < words; i += TK_THREADS) sp_seen[i] = 0u;
+    if (t == 0) s_cnt = 0;
+    __syncthreads();
+    for (int i = t; i < cur_len; i += TK_THREADS) {
+        const int tok = seq0[i];
+        if (tok >= 0 && tok < V) atomicOr(&sp_seen[tok >> 5], 1u << (tok & 31));
+    }
+    __syncthreads();
+    const float* row = logits + static_cast<int64_t>(b) * ld;
+    auto processed = [&](int idx) {
+        float x = row[idx];
+        if ((sp_seen[idx >> 5] >> (idx & 31)) & 1u) x = x < 0.f ? x * rep_pen : x / rep_pen;
+        return idx == ban_token ? -INFINITY : x;
+    };
+    // pass 1: every thread's largest processed logit; the top_k-th largest of those 256 maxima bounds the row's top_k-th
+    // largest value from below (binary search over the ordered bit pattern, one block-wide count per bit)
+    float cm = -INFINITY;
+    for (int idx = t; idx < V; idx += TK_THREADS) cm = fmaxf(cm, processed(idx));
+    const uint32_t key = sp_ordered(cm), key_ninf = sp_ordered(-INFINITY);
+    const int finite_threads = __syncthreads_count(key > key_ninf);
+    uint32_t thr = 0u;
+    if (finite_threads >= top_k) {
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = thr | (1u << bit);
+            if (__syncthreads_count(key >= cand) >= top_k) thr = cand;
+        }
+    }
+    // pass 2: collect everything at or above it
+    for (int idx = t; idx < V; idx += TK_THREADS) {
+        const float x = processed(idx);
+        if (x != -INFINITY && sp_ordered(x) >= thr) {
+            const int pos = atomicAdd(&s_cnt, 1);
+            if (pos < SP_CAP) {
+                c_v[pos] = x;
+                c_i[pos] = idx;
+            }
+        }
+    }
+    __syncthreads();
+    int n = s_cnt;
+    if (n > SP_CAP) {
+        // more than SP_CAP values at or above the bound (a flat row): find the exact top_k-th largest value with one count of the
+        // row per bit, then keep what is at or above it — in token order, at most SP_CAP of them
+        uint32_t exact = 0u;
+        for (int bit = 31; bit >= 0; --bit) {
+            const uint32_t cand = exact | (1u << bit);
+            int mine = 0;
+            for (int idx = t; idx < V; idx += TK_THREADS) {
+                const float x = processed(idx);
+                mine += (x != -INFINITY && sp_ordered(x) >= cand) ? 1 : 0;
+            }
+            __shared__ int s_tot;
+            if (t == 0) s_tot = 0;
+            __syncthreads();
+            atomicAdd(&s_tot, mine);
+            __syncthreads();
+            if (s_tot >= top_k) exact = cand;
+            __syncthreads();
+        }
+        if (t == 0) {
+            int m = 0;
+            for (int idx = 0; idx < V && m < SP_CAP; ++idx) {
+                const float x = processed(idx);
+                if (x != -INFINITY && sp_ordered(x) >= exact) {
+                    c_v[m] = x;
+                    c_i[m] = idx;
+                    ++m;
+                }
+            }
+            s_cnt = m;
+        }
+        __syncthreads();
+        n = s_cnt;
+    }
+    // descending bitonic sort of the collected (value, token) pairs, value descending, token ascending among equals
+    int P = 1;
+    while (P < n) P <<= 1;
+    for (int i = n + t; i < P; i += TK_THREADS) {
+        c_v[i] = -INFINITY;
+        c_i[i] = 0x7fffffff;
+    }
+    __syncthreads();
+    for (int size = 2; size <= P; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int i = t; i < P; i += TK_THREADS) {
+                const int j = i ^ stride;
+                if (j > i) {
+                    const bool first_wins = cand_better(c_v[i], c_i[i], c_v[j], c_i[j]);
+                    const bool want_first = (i & size) == 0;   // this half sorted best-first
+                    if (first_wins != want_first) {
+                        const float tv = c_v[i];
+                        const int ti = c_i[i];
+                        c_v[i] = c_v[j];
+                        c_i[i] = c_i[j];
+                        c_v[j] = tv;
+                        c_i[j] = ti;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    if (t == 0) {
+        // top-k with ties, then top-p, then the draw
+        int kept = n;
+        if (n > top_k) {
+            const float vk = c_v[top_k - 1];
+            kept = top_k;
+            while (kept < n && c_v[kept] == vk) ++kept;
+        }
+        const float m = c_v[0];
+        float total = 0.f;
+        for (int j = 0; j < kept; ++j) total += expf(c_v[j] - m);
+        int nucleus = 0;
+        float cum = 0.f, mass = 0.f;
+        for (int j = 0; j < kept; ++j) {
+            if (j > 0 && cum / total > top_p) break;   // the mass before token j exceeds top_p
+            const float e = expf(c_v[j] - m);
+            cum += e;
+            mass = cum;
+            ++nucleus;
+        }
+        const float target = uniforms[b] * mass;
+        int pick = nucleus - 1;
+        float run = 0.f;
+        for (int j = 0; j < nucleus; ++j) {
+            run += expf(c_v[j] - m);
+            if (run > target) {
+                pick = j;
+                break;
+            }
+        }
+        const int tok = c_i[pick];
+        seq0[cur_len] = tok;
+        seq1[cur_len] = tok;
+        st.cur_tok[b] = tok;
+        st.beam_scores[b] += (c_v[pick] - m) - logf(mass);   // log-probability of the draw under the sampled distribution
+        if (tok == st.eos) {
+            st.done[b] = 1;
+            atomicAdd(st.n_done, 1);
+        }
+    }
+}
+
+// sequences as transformers' sample() returns them: the tokens up to and including eos (or max_length), pad behind
+__global__ void med_sample_finalize_kernel(BeamState st, int cur_len, int max_length, int32_t* __restrict__ out_tokens,
+                                           int32_t* __restrict__ out_len, float* __restrict__ out_score) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= st.frames) return;
+    const int32_t* seq = st.seq + static_cast<int64_t>(b) * st.t_max;
+    int32_t* o = out_tokens + static_cast<int64_t>(b) * max_length;
+    int len = cur_len;
+    for (int i = 0; i < cur_len; ++i) {
+        o[i] = seq[i];
+        if (seq[i] == st.eos && i + 1 < len) len = i + 1;
+    }
+    for (int i = len; i < max_length; ++i) o[i] = st.pad;
+    out_len[b] = len;
+    out_score[b] = st.beam_scores[b];
+}
+
 // out[p, j] = hidden[p * T, :] . W[j, :] + bias[j]   (itm_head on the first token, blip_itm.py:56)
 __global__ void med_cls_head_kernel(const float* __restrict__ hidden, const float* __restrict__ W, const float* __restrict__ bias,
                                     float* __restrict__ out, int n_seq, int T, int D, int n_out) {
@@ -702,6 +900,32 @@ int med_beam_step_run(const BeamState& st, const float* cand_score, const int32_
     }
     VIDIL_CUDA_OK(launch_pdl(med_beam_step_kernel, dim3((st.frames + 63) / 64), dim3(64), 0, s, st, cand_score, cand_tok, lists_per_frame, nc, V,
                              cur_len, parity));
+    count_launches(1);
+    return 0;
+}
+
+int med_sample_step_run(const BeamState& st, const float* logits, int64_t ld, int V, int cur_len, int ban_token, int top_k, float top_p,
+                        float repetition_penalty, const float* uniforms_dev, cudaStream_t s) {
+    if (st.beams != 1 || top_k < 1 || top_k > SP_CAP || !(top_p > 0.f) || !(repetition_penalty > 0.f)) {
+        set_error("sample step: one beam, top_k in [1, %d], top_p > 0 and repetition_penalty > 0 expected (beams %d, top_k %d, top_p %g, "
+                  "penalty %g)", SP_CAP, st.beams, top_k, top_p, repetition_penalty);
+        return 1;
+    }
+    const size_t smem = static_cast<size_t>((V + 31) / 32) * sizeof(uint32_t);
+    if (smem > 40 * 1024) {
+        set_error("sample step: vocabulary of %d tokens exceeds the shared-memory bit set", V);
+        return 1;
+    }
+    med_sample_step_kernel<<<st.frames, TK_THREADS, smem, s>>>(st, logits, ld, V, cur_len, ban_token, top_k, top_p, repetition_penalty, uniforms_dev);
+    VIDIL_CUDA_OK(cudaGetLastError());
+    count_launches(1);
+    return 0;
+}
+
+int med_sample_finalize_run(const BeamState& st, int cur_len, int max_length, int32_t* out_tokens, int32_t* out_len, float* out_score,
+                            cudaStream_t s) {
+    med_sample_finalize_kernel<<<(st.frames + 63) / 64, 64, 0, s>>>(st, cur_len, max_length, out_tokens, out_len, out_score);
+    VIDIL_CUDA_OK(cudaGetLastError());
     count_launches(1);
     return 0;
 }

@@ -636,10 +636,22 @@ size_t vidil_med_generate_workspace_bytes(const vidil_med* med, int32_t n_frames
     return generate_ws(med, nullptr, n_frames, n_img_tokens, num_beams, max_length, prompt_len).total;
 }
 
-int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens,
-                           const int32_t* prompt_ids_host, int32_t prompt_len, int32_t num_beams, int32_t max_length,
-                           int32_t min_length, int32_t eos_token, int32_t pad_token, float length_penalty, int32_t* out_tokens,
-                           int32_t* out_lengths, float* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+}  // extern "C"
+
+namespace {
+
+// nucleus sampling instead of beam search (blip.py:139-148): one sequence per frame, the draw of step i of frame f uses
+// uniforms[i * n_frames + f]
+struct SampleCfg {
+    int top_k;
+    float top_p, repetition_penalty;
+    const float* uniforms;
+};
+
+int generate_core(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens, const int32_t* prompt_ids_host,
+                  int32_t prompt_len, int32_t num_beams, int32_t max_length, int32_t min_length, int32_t eos_token, int32_t pad_token,
+                  float length_penalty, const SampleCfg* smp, int32_t* out_tokens, int32_t* out_lengths, float* out_scores,
+                  void* workspace, size_t workspace_bytes, void* stream) {
     if (med == nullptr || image_embeds == nullptr || out_tokens == nullptr || out_lengths == nullptr || out_scores == nullptr ||
         workspace == nullptr) {
         set_error("vidil_med_generate: null argument");
@@ -697,9 +709,15 @@ int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_
         if (run_stack(med, pl, w.b, a, s)) return 1;
         const uint8_t* last = reinterpret_cast<const uint8_t*>(w.b.xn) + static_cast<size_t>(Lp - 1) * D * 2;
         if (run_lm_head(med, last, static_cast<int64_t>(Lp) * D, F, w.head_t, w.head_ln, w.logits, s)) return 1;
-        if (med_logits_topk_run(w.logits, V, 1, nullptr, F, V, nc, Lp < min_length ? eos_token : -1, w.beam.cand_score, w.beam.cand_tok, s))
-            return 1;
-        if (med_beam_step_run(st, w.beam.cand_score, w.beam.cand_tok, 1, nc, V, Lp, 0, s)) return 1;
+        if (smp) {
+            if (med_sample_step_run(st, w.logits, V, V, Lp, Lp < min_length ? eos_token : -1, smp->top_k, smp->top_p, smp->repetition_penalty,
+                                    smp->uniforms, s))
+                return 1;
+        } else {
+            if (med_logits_topk_run(w.logits, V, 1, nullptr, F, V, nc, Lp < min_length ? eos_token : -1, w.beam.cand_score, w.beam.cand_tok, s))
+                return 1;
+            if (med_beam_step_run(st, w.beam.cand_score, w.beam.cand_tok, 1, nc, V, Lp, 0, s)) return 1;
+        }
     }
     int parity = 1, cur_len = Lp + 1;
     if (cur_len < max_length) {
@@ -718,16 +736,24 @@ int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_
             if (med_embed_run(st.cur_tok, med->word.f(), med->pos.f(), w.b.resid, R, 1, cur_len - 1, 0, D, V, c.max_positions, s)) return 1;
             if (run_stack(med, pl, w.b, a, s)) return 1;
             if (run_lm_head(med, w.b.xn, D, R, w.head_t, w.head_ln, w.logits, s)) return 1;
-            if (med_timed(med, s, VIDIL_KCLASS_OTHER, 0.0, 4.0 * R * V, [&] {
-                    return med_logits_topk_run(w.logits, V, 1, st.beam_scores, R, V, nc, cur_len < min_length ? eos_token : -1,
-                                               w.beam.cand_score, w.beam.cand_tok, s);
-                }))
-                return 1;
-            if (med_beam_step_run(st, w.beam.cand_score, w.beam.cand_tok, K, nc, V, cur_len, parity, s)) return 1;
+            if (smp) {
+                if (med_timed(med, s, VIDIL_KCLASS_OTHER, 0.0, 8.0 * R * V, [&] {
+                        return med_sample_step_run(st, w.logits, V, V, cur_len, cur_len < min_length ? eos_token : -1, smp->top_k, smp->top_p,
+                                                   smp->repetition_penalty, smp->uniforms + static_cast<size_t>(cur_len - Lp) * F, s);
+                    }))
+                    return 1;
+            } else {
+                if (med_timed(med, s, VIDIL_KCLASS_OTHER, 0.0, 4.0 * R * V, [&] {
+                        return med_logits_topk_run(w.logits, V, 1, st.beam_scores, R, V, nc, cur_len < min_length ? eos_token : -1,
+                                                   w.beam.cand_score, w.beam.cand_tok, s);
+                    }))
+                    return 1;
+                if (med_beam_step_run(st, w.beam.cand_score, w.beam.cand_tok, K, nc, V, cur_len, parity, s)) return 1;
+            }
             parity ^= 1;
-            // `if beam_scorer.is_done: break` of transformers' beam_search: every other step from min_length on (no frame can finish
-            // earlier) the host reads the count of finished frames; the remaining steps would only pad.  This synchronises the
-            // stream — once per ~8 ms of queued work.
+            // `if beam_scorer.is_done: break` of transformers' beam_search (`if unfinished_sequences.max() == 0: break` of sample()):
+            // every other step from min_length on (no frame can finish earlier) the host reads the count of finished frames; the
+            // remaining steps would only pad.  This synchronises the stream — once per ~8 ms of queued work.
             if (cur_len >= min_length && cur_len + 1 < max_length && ((cur_len - min_length) & 1) == 0) {
                 int32_t n_done = 0;
                 VIDIL_CUDA_OK(cudaMemcpyAsync(&n_done, st.n_done, sizeof(n_done), cudaMemcpyDeviceToHost, s));
@@ -739,7 +765,39 @@ int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_
             }
         }
     }
+    if (smp) return med_sample_finalize_run(st, cur_len, max_length, out_tokens, out_lengths, out_scores, s);
     return med_beam_finalize_run(st, cur_len, parity, max_length, out_tokens, out_lengths, out_scores, s);
+}
+
+}  // namespace
+
+extern "C" {
+
+int32_t vidil_med_generate(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens,
+                           const int32_t* prompt_ids_host, int32_t prompt_len, int32_t num_beams, int32_t max_length,
+                           int32_t min_length, int32_t eos_token, int32_t pad_token, float length_penalty, int32_t* out_tokens,
+                           int32_t* out_lengths, float* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+    return generate_core(med, image_embeds, n_frames, n_img_tokens, prompt_ids_host, prompt_len, num_beams, max_length, min_length,
+                         eos_token, pad_token, length_penalty, nullptr, out_tokens, out_lengths, out_scores, workspace, workspace_bytes,
+                         stream);
+}
+
+int32_t vidil_med_sample(vidil_med* med, const float* image_embeds, int32_t n_frames, int32_t n_img_tokens,
+                         const int32_t* prompt_ids_host, int32_t prompt_len, int32_t max_length, int32_t min_length, int32_t eos_token,
+                         int32_t pad_token, int32_t top_k, float top_p, float repetition_penalty, const float* uniforms,
+                         int32_t* out_tokens, int32_t* out_lengths, float* out_scores, void* workspace, size_t workspace_bytes,
+                         void* stream) {
+    if (uniforms == nullptr) {
+        set_error("vidil_med_sample: null argument");
+        return 1;
+    }
+    if (top_k < 1 || top_k > 1024 || !(top_p > 0.f) || !(repetition_penalty > 0.f)) {
+        set_error("vidil_med_sample: top_k=%d (1..1024), top_p=%g (> 0), repetition_penalty=%g (> 0)", top_k, top_p, repetition_penalty);
+        return 1;
+    }
+    const SampleCfg smp{top_k, top_p, repetition_penalty, uniforms};
+    return generate_core(med, image_embeds, n_frames, n_img_tokens, prompt_ids_host, prompt_len, 1, max_length, min_length, eos_token,
+                         pad_token, 1.0f, &smp, out_tokens, out_lengths, out_scores, workspace, workspace_bytes, stream);
 }
 
 size_t vidil_op_beam_search_workspace_bytes(int32_t n_frames, int32_t num_beams, int32_t max_length) {
@@ -793,6 +851,44 @@ int32_t vidil_op_beam_search(const float* step_logits, int32_t n_steps, int32_t 
         parity ^= 1;
     }
     return med_beam_finalize_run(st, cur_len, parity, max_length, out_tokens, out_lengths, out_scores, s);
+}
+
+int32_t vidil_op_sample(const float* step_logits, int32_t n_steps, int32_t n_frames, int32_t V, const int32_t* prompt_ids_host,
+                        int32_t prompt_len, int32_t max_length, int32_t min_length, int32_t eos_token, int32_t pad_token, int32_t top_k,
+                        float top_p, float repetition_penalty, const float* uniforms, int32_t* out_tokens, int32_t* out_lengths,
+                        float* out_scores, void* workspace, size_t workspace_bytes, void* stream) {
+    if (step_logits == nullptr || uniforms == nullptr || out_tokens == nullptr || out_lengths == nullptr || out_scores == nullptr ||
+        workspace == nullptr) {
+        set_error("vidil_op_sample: null argument");
+        return 1;
+    }
+    const int F = n_frames, Lp = prompt_len;
+    if (check_beam_args(F, 1, V, Lp, max_length, min_length, prompt_ids_host)) return 1;
+    if (n_steps != max_length - Lp) {
+        set_error("vidil_op_sample: %d steps given, max_length - prompt_len = %d needed", n_steps, max_length - Lp);
+        return 1;
+    }
+    Carver cv(workspace);
+    BeamWs w;
+    carve_beam(cv, F, 1, max_length, w);
+    if (workspace_bytes < cv.off || (reinterpret_cast<uintptr_t>(workspace) & (ALIGN - 1))) {
+        set_error("vidil_op_sample: workspace too small (%zu < %zu) or not %zu-byte aligned", workspace_bytes, cv.off, ALIGN);
+        return 1;
+    }
+    cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+    BeamState& st = w.st;
+    st.eos = eos_token;
+    st.pad = pad_token;
+    st.length_penalty = 1.0f;
+    VIDIL_CUDA_OK(cudaMemcpyAsync(w.prompt, prompt_ids_host, static_cast<size_t>(Lp) * 4, cudaMemcpyHostToDevice, s));
+    if (med_beam_init_run(st, w.prompt, Lp, s)) return 1;
+    int cur_len = Lp;
+    for (int step = 0; step < n_steps; ++step, ++cur_len) {
+        if (med_sample_step_run(st, step_logits + static_cast<size_t>(step) * F * V, V, V, cur_len, cur_len < min_length ? eos_token : -1, top_k,
+                                top_p, repetition_penalty, uniforms + static_cast<size_t>(step) * F, s))
+            return 1;
+    }
+    return med_sample_finalize_run(st, cur_len, max_length, out_tokens, out_lengths, out_scores, s);
 }
 
 }  // extern "C"

@@ -351,16 +351,20 @@ class BertLMHeadModel(nn.Module):
 
     @torch.no_grad()
     def generate(self, input_ids=None, max_length=20, min_length=0, num_beams=1, eos_token_id=None, pad_token_id=0,
-                 repetition_penalty=1.0, length_penalty=1.0, do_sample=False, encoder_hidden_states=None,
-                 encoder_attention_mask=None, return_scores=False, **unsupported):
-        """transformers v4.15 `generate(...)` as blip.py:150-158 calls it (beam search).  `encoder_hidden_states` may be the
-        per-frame tokens [B, N, E] or, as the reference passes them, already repeat_interleaved over the beams
-        [B*num_beams, N, E] (blip.py:130) — then every num_beams-th row is used.  Returns int64 [B, L] padded with
-        pad_token_id, L = min(longest hypothesis + 1, max_length), like BeamSearchScorer.finalize."""
+                 repetition_penalty=1.0, length_penalty=1.0, do_sample=False, top_p=1.0, top_k=50, num_return_sequences=1,
+                 encoder_hidden_states=None, encoder_attention_mask=None, return_scores=False, generator=None, uniforms=None,
+                 **unsupported):
+        """transformers v4.15 `generate(...)` as blip.py:139-158 calls it: beam search (do_sample False) or nucleus sampling
+        (do_sample True: repetition penalty, MinLength, top-k — the PretrainedConfig default 50 BLIP inherits — and top-p, then
+        one draw per step; `uniforms` [max_length - prompt_len, B] in [0, 1) or, if None, torch.rand from `generator` / the
+        global CPU generator).  `encoder_hidden_states` may be the per-frame tokens [B, N, E] or, as the reference passes them
+        for beam search, already repeat_interleaved over the beams [B*num_beams, N, E] (blip.py:130) — then every num_beams-th
+        row is used.  Returns int64 [B, L] padded with pad_token_id, L = min(longest hypothesis + 1, max_length), like
+        BeamSearchScorer.finalize (sampling: the longest sequence, eos included)."""
         if do_sample:
-            raise NotImplementedError("nucleus sampling (generation_mode 'sample') is not built; the shipped pipeline configs "
-                                      "use beam search")
-        if repetition_penalty != 1.0:
+            if num_beams != 1 or num_return_sequences != 1:
+                raise NotImplementedError("sampling is built as blip.py:141-148 calls it: one beam, one returned sequence")
+        elif repetition_penalty != 1.0:
             raise NotImplementedError("repetition_penalty != 1.0 is not on the beam-search path of run_video_CapFilt.py:102")
         if eos_token_id is None:
             raise ValueError("eos_token_id is required")
@@ -378,6 +382,12 @@ class BertLMHeadModel(nn.Module):
             n = self.bert._ensure_packed()
             enc = enc.contiguous().float()
             Nv, Lp = enc.shape[1], prompt.numel()
+            if do_sample:
+                if uniforms is None:
+                    uniforms = torch.rand(max_length - Lp, B, generator=generator)
+                uni = uniforms.to(dev, torch.float32)
+                if tuple(uni.shape) != (max_length - Lp, B):
+                    raise ValueError(f"uniforms must be [max_length - prompt_len, B] = [{max_length - Lp}, {B}]")
             toks = torch.empty(B, max_length, dtype=torch.int32, device=dev)
             lens = torch.empty(B, dtype=torch.int32, device=dev)
             scores = torch.empty(B, dtype=torch.float32, device=dev)
@@ -391,6 +401,15 @@ class BertLMHeadModel(nn.Module):
                 nb = min(chunk, B - b0)
                 need = n.lib.vidil_med_generate_workspace_bytes(n.handle, nb, Nv, num_beams, max_length, Lp)
                 ws = n.workspace(need, dev)
+                if do_sample:
+                    u = uni[:, b0:b0 + nb].contiguous()
+                    st = n.lib.vidil_med_sample(n.handle, enc[b0:b0 + nb].data_ptr(), nb, Nv, prompt.data_ptr(), Lp, max_length, min_length,
+                                                eos_token_id, pad_token_id, int(top_k), float(top_p), float(repetition_penalty),
+                                                u.data_ptr(), toks[b0:b0 + nb].data_ptr(), lens[b0:b0 + nb].data_ptr(),
+                                                scores[b0:b0 + nb].data_ptr(), ws.data_ptr(), ws.numel(),
+                                                torch.cuda.current_stream().cuda_stream)
+                    _lib.check(st, "vidil_med_sample")
+                    continue
                 st = n.lib.vidil_med_generate(n.handle, enc[b0:b0 + nb].data_ptr(), nb, Nv, prompt.data_ptr(), Lp, num_beams, max_length,
                                               min_length, eos_token_id, pad_token_id, float(length_penalty), toks[b0:b0 + nb].data_ptr(),
                                               lens[b0:b0 + nb].data_ptr(), scores[b0:b0 + nb].data_ptr(), ws.data_ptr(), ws.numel(),
