@@ -20,6 +20,7 @@ import numpy as np
 import torch
 
 from . import distributed as vdist
+from . import jsonio
 from .preprocess import process_frame, process_frames  # noqa: F401  (process_frame re-exported, :128-137)
 
 
@@ -240,7 +241,7 @@ def run(data, config, device, output_dir=None, **capfilt_kwargs):
     if output_dir is not None:
         os.makedirs(output_dir, exist_ok=True)
         with open(os.path.join(output_dir, 'video_text_CapFilt.json'), 'w') as out:
-            json.dump(merged_f, out, indent=4)
+            jsonio.dump_indent4(merged_f, out)    # == json.dump(..., indent=4), run_video_CapFilt.py:283-291
         with open(os.path.join(output_dir, 'video_text_Cap.json'), 'w') as out:
-            json.dump(merged_u, out, indent=4)
+            jsonio.dump_indent4(merged_u, out)
     return merged_f, merged_u

@@ -17,6 +17,8 @@ import os
 import torch
 import torch.distributed as dist
 
+from . import jsonio
+
 
 def is_dist_avail_and_initialized() -> bool:
     return dist.is_available() and dist.is_initialized()
@@ -129,5 +131,5 @@ def gather_and_write(result: dict, path: str | None, device=None) -> dict | None
     if path is not None:
         os.makedirs(os.path.dirname(os.path.abspath(path)), exist_ok=True)
         with open(path, "w") as out:
-            json.dump(merged, out, indent=4)
+            jsonio.dump_indent4(merged, out)          # == json.dump(merged, out, indent=4), run_visual_tokenization.py:52
     return merged

@@ -21,6 +21,7 @@ from collections import defaultdict
 import torch
 
 from . import distributed as vdist
+from . import jsonio
 from . import ops
 
 EMBBDING_BATCH_LIMIT_TEXT = 512  # :470 (spelling is the reference's)
@@ -49,7 +50,7 @@ def load_json(json_path):
 
 def save_json(filepath, json_object):
     with open(filepath, 'w') as f:
-        json.dump(json_object, f, indent=4)
+        jsonio.dump_indent4(json_object, f)       # == json.dump(json_object, f, indent=4), the reference's line :52
 
 
 def get_prefix_prompt_functions(version):
