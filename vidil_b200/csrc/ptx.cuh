@@ -185,14 +185,6 @@ __device__ __forceinline__ void cp_async_wait() {
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 
-// 1-D bulk copy global -> this CTA's shared memory (no tensor map): `bytes` a multiple of 16, both addresses 16-byte aligned;
-// completion bytes land on `bar`.  One instruction moves a whole contiguous row without holding a register.
-__device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-                 "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 // 2-D tiled load into this CTA's shared memory; completion bytes land on `bar` (this CTA).
 __device__ __forceinline__ void tma_load_2d(const CUtensorMap* m, uint64_t* bar, void* dst, int32_t c0,
                                             int32_t c1) {
