@@ -2,7 +2,9 @@
 // ViT-L/16 @224 shape (N = 197) and the CLIP text tower (N = 77, causal).  Reference: models/vit.py:72-83
 // (Attention.forward); the reference materialises [B,H,N,N] scores in HBM, here S and P never leave tensor memory.
 //
-// One persistent CTA per SM walks (frame, head) items.  Per item the queries form up to two 128-row tiles:
+// One persistent CTA per SM walks (frame, head) items, last frame first: the qkv GEMM wrote its rows in ascending order, so the
+// end of the 310 MB qkv matrix is what the 126 MB L2 still holds when this kernel starts, and the projection GEMM that follows
+// starts at the rows written last here.  Per item the queries form up to two 128-row tiles:
 //   S = Q_t K^T          tcgen05.mma M=128, N=ceil16(keys), K=64;  fp32 S in TMEM columns [0, 208) of the lane's 256
 //   P = exp2(c S - c max)   ONE thread per query row: pass 1 reads the row from TMEM and takes its maximum (3-input
 //                           max), pass 2 reads it again, exponentiates, accumulates the row sum and writes the 16-bit
@@ -243,7 +245,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int st = it & 1;
                 const uint32_t ph = (it >> 1) & 1;
-                const int b = item / H, h = item - b * H;
+                const int ritem = (flags & 64) ? item : n_items - 1 - item;  // last frames first: see the header (L2 residency of the freshly written qkv rows)
+                const int b = ritem / H, h = ritem - b * H;
                 const int row0 = b * N;
                 uint8_t* sq = smem + OFF_Q + st * 2 * Q_BYTES;
                 ATC_TRACE(0, 0);
@@ -340,7 +343,8 @@ __global__ void __launch_bounds__(ATC_THREADS, 1)
             if (t >= n_tiles) continue;
             const uint32_t par = n & 1;
             ++n;
-            const int b = item / H, h = item - b * H;
+            const int ritem = (flags & 64) ? item : n_items - 1 - item;
+            const int b = ritem / H, h = ritem - b * H;
             const bool warp_valid = (t * QT + quarter * 32) < N;
             // keys this query row may see: all N, or 0..row under a causal mask (padding rows see nothing that is kept)
             const int NV = causal ? min(N, t * QT + row_in_tile + 1) : N;
@@ -487,7 +491,8 @@ EncodeTiledFn encode_fn() {
 }
 
 long long* g_trace = nullptr;  // developer hook, see attention_set_trace
-// developer A/B switches (VIDIL_ATC_FLAGS): 1 = no token between the lanes, 16 = generic kernel for N = 197, 32 = all-MUFU exponentials
+// developer A/B switches (VIDIL_ATC_FLAGS): 1 = no token between the lanes, 16 = generic kernel for N = 197, 32 = all-MUFU exponentials,
+// 64 = items in ascending order
 const int g_flags = [] { const char* e = getenv("VIDIL_ATC_FLAGS"); return e ? atoi(e) : 0; }();
 
 template <typename T, int NCT, int POLY>

@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(T257_THREADS, 1)
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
                 const int st = it & 1;
                 const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
-                const int b = item / H, h = item - b * H;
+                const int ritem = n_items - 1 - item;   // last frames first, as in attention_tc.cu: the end of the qkv matrix is what L2 still holds
+                const int b = ritem / H, h = ritem - b * H;
                 const int row0 = b * NTOK;
                 uint8_t* sq = smem + OFF_Q + st * 2 * Q_BYTES;
                 uint8_t* skk = smem + OFF_K + st * KV_BYTES;
@@ -219,7 +220,8 @@ __global__ void __launch_bounds__(T257_THREADS, 1)
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int t = (L + it) & 1, st = it & 1;
             const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
-            const int b = item / H, h = item - b * H;
+            const int ritem = n_items - 1 - item;
+            const int b = ritem / H, h = ritem - b * H;
             float sum[4] = {0.f, 0.f, 0.f, 0.f};
 
             // ---- key 256: this row's score from the Q and K tiles in shared memory, under the S MMA ----
@@ -360,7 +362,8 @@ __global__ void __launch_bounds__(T257_THREADS, 1)
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const int st = it & 1;
             const uint32_t ph = it & 1, ph2 = (it >> 1) & 1;
-            const int b = item / H, h = item - b * H;
+            const int ritem = n_items - 1 - item;
+            const int b = ritem / H, h = ritem - b * H;
             if (threadIdx.x - 12 * 32 < HD)
                 tq[threadIdx.x - 12 * 32] =
                     static_cast<float>(qkv[(static_cast<int64_t>(b) * NTOK + NKM) * (3 * D) + h * HD + (threadIdx.x - 12 * 32)]) * scale_log2e;

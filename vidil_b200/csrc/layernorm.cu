@@ -4,6 +4,8 @@
 //
 // HBM-bound: one warp owns one row, reads it once with 128-bit coalesced loads, keeps it in registers,
 // reduces mean and centred variance with warp shuffles (two-pass in registers, fp32), and writes once.
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -39,13 +41,17 @@ __device__ __forceinline__ void store4<__half>(__half* p, float a, float b, floa
 template <typename OutT, int VPL>
 __global__ void __launch_bounds__(LN_WARPS * 32)
     layernorm_kernel(const float* __restrict__ in, int64_t in_row_stride, const float* __restrict__ gamma,
-                     const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps) {
+                     const float* __restrict__ beta, OutT* __restrict__ out, int rows, float eps, int ascending) {
     constexpr int D = VPL * 128;
     ptx::griddep_launch();
     ptx::griddep_wait();
-    const int row = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    // Rows are walked from the LAST to the first: the producer of `in` (the residual-add GEMM, tiles in ascending row order) wrote
+    // the last rows most recently, so that is where the 126 MB L2 still holds part of a 206 MB activation; and the GEMM that
+    // consumes `out` starts at row 0, which this kernel writes last.
+    const int walk = blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+    const int row = ascending ? walk : rows - 1 - walk;   // ascending: developer A/B switch VIDIL_ROWS_ASC=1
     const int lane = threadIdx.x & 31;
-    if (row >= rows) return;
+    if (walk >= rows) return;
     const float4* src = reinterpret_cast<const float4*>(in + static_cast<int64_t>(row) * in_row_stride);
     float4 x[VPL];
 #pragma unroll
@@ -157,14 +163,15 @@ template <typename OutT>
 int launch_ln(const float* in, int64_t stride, const float* g, const float* b, void* out, int rows, int D, float eps,
               cudaStream_t s) {
     const int grid = (rows + LN_WARPS - 1) / LN_WARPS;
+    static const int asc = [] { const char* e = getenv("VIDIL_ROWS_ASC"); return e ? atoi(e) : 0; }();
     OutT* o = reinterpret_cast<OutT*>(out);
     switch (D) {
-        case 768: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 6>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
-        case 1024: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 8>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
-        case 1280: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 10>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
-        case 512: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 4>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
-        case 256: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
-        case 128: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 1>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps)); break;
+        case 768: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 6>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps, asc)); break;
+        case 1024: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 8>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps, asc)); break;
+        case 1280: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 10>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps, asc)); break;
+        case 512: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 4>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps, asc)); break;
+        case 256: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 2>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps, asc)); break;
+        case 128: VIDIL_CUDA_OK(launch_pdl(layernorm_kernel<OutT, 1>, dim3(grid), dim3(LN_WARPS * 32), 0, s, in, stride, g, b, o, rows, eps, asc)); break;
         default: set_error("layernorm: unsupported width %d (supported: 128, 256, 512, 768, 1024, 1280)", D); return 1;
     }
     VIDIL_CUDA_OK(cudaGetLastError());
