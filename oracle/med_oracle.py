@@ -365,9 +365,11 @@ def beam_search_from_logits(step_logits, batch: int, prompt: list, num_beams: in
 # top_p=..., repetition_penalty=1.1, min_length=...)` builds (blip.py:141-148): RepetitionPenaltyLogitsProcessor,
 # MinLengthLogitsProcessor, then TopKLogitsWarper (the PretrainedConfig default top_k = 50 BLIP inherits) and
 # TopPLogitsWarper.  The four processors are pinned against the installed transformers' own classes
-# (tests/test_beam_search_pin.py::test_sampling_processors_equal_installed_transformers); the draw itself is an inverse-CDF
-# lookup with caller-supplied uniform numbers, because torch.multinomial's stream cannot be reproduced by another
-# implementation — what is compared with the native path is the same lookup on the same numbers.
+# (tests/test_beam_search_pin.py::test_sampling_processors_equal_installed_transformers) and the whole loop against the
+# installed `generate(do_sample=True, ...)` (::test_sampling_loop_equals_installed_transformers_generate, 64/64 sequences); the
+# draw itself is an inverse-CDF lookup with caller-supplied uniform numbers, because torch.multinomial's stream cannot be
+# reproduced by another implementation — that test swaps torch.multinomial for the same lookup, and what is compared with the
+# native path is the same lookup on the same numbers.
 # ----------------------------------------------------------------------------------------------------------------------
 def process_sampling_scores(logits: np.ndarray, seq: np.ndarray, cur_len: int, min_length: int, eos: int, top_k: int = 50,
                             top_p: float = 0.9, repetition_penalty: float = 1.1):
