@@ -167,7 +167,8 @@ __global__ void __launch_bounds__(ATL_THREADS, 1)
             // ===================== TMA producer =====================
             int it = 0, kc = 0, vc = 0;
             for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-                const int r = item % rounds, bh = item / rounds;
+                const int ritem = n_items - 1 - item;   // last frames first (L2 residency of the freshly written qkv rows, see attention_tc.cu)
+                const int r = ritem % rounds, bh = ritem / rounds;
                 const int b = bh / H, h = bh - b * H;
                 const int row0 = b * N;
                 ptx::mbar_wait(q_empty, (it & 1) ^ 1);
@@ -260,7 +261,8 @@ __global__ void __launch_bounds__(ATL_THREADS, 1)
         const uint32_t prow = sbase + lay.p + L * lay.pbytes + row_in_tile * 16;
         int it = 0, sc = 0, pc = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int r = item % rounds, bh = item / rounds;
+            const int ritem = n_items - 1 - item;
+            const int r = ritem % rounds, bh = ritem / rounds;
             const int b = bh / H, h = bh - b * H;
             const int slot = (L + it) & 1;
             const int t_raw = 2 * r + slot;
@@ -377,7 +379,8 @@ __global__ void __launch_bounds__(ATL_THREADS, 1)
         const int row_first = n_qt * QT;
         int it = 0, kc = 0, vc = 0;
         for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-            const int r = item % rounds, bh = item / rounds;
+            const int ritem = n_items - 1 - item;
+            const int r = ritem % rounds, bh = ritem / rounds;
             const int b = bh / H, h = bh - b * H;
             const bool work = (n_tail > 0) && (r == 0);
             float m_run[MAX_TAIL], l_run[MAX_TAIL], acc0[MAX_TAIL], acc1[MAX_TAIL];
