@@ -60,12 +60,19 @@ def test_result_file_shapes_and_subclasses():
 def test_dump_matches_on_a_result_file_and_is_not_slower(tmp_path):
     tokens = {f"video{i}": {t: [f"a photo of thing number {j}" for j in range(15)] for t in ("objects", "attributes", "scenes", "verbs")}
               for i in range(3000)}
-    t0 = time.perf_counter()
     ref = json.dumps(tokens, indent=4)
-    t1 = time.perf_counter()
     with open(tmp_path / "x.json", "w") as f:
         jsonio.dump_indent4(tokens, f)
-    t2 = time.perf_counter()
     assert open(tmp_path / "x.json").read() == ref
-    print(f"{len(ref) / 1e6:.1f} MB: json {t1 - t0:.3f} s, jsonio {t2 - t1:.3f} s")
-    assert (t2 - t1) < 1.5 * (t1 - t0)      # typically 0.55x; the bound only catches a regression to something pathological
+
+    def best_of(fn, n=3):
+        best = float("inf")
+        for _ in range(n):
+            t = time.perf_counter()
+            fn()
+            best = min(best, time.perf_counter() - t)
+        return best
+
+    t_json, t_fast = best_of(lambda: json.dumps(tokens, indent=4)), best_of(lambda: jsonio.dumps_indent4(tokens))
+    print(f"{len(ref) / 1e6:.1f} MB: json {t_json:.3f} s, jsonio {t_fast:.3f} s")
+    assert t_fast < 1.5 * t_json      # typically 0.55x; the bound only catches a regression to something pathological
