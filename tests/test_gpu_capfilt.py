@@ -101,3 +101,25 @@ def test_capfilt_end_to_end_and_video_batching(cuda):
     assert ref_kept == item["text"]
     # and the captions themselves are what the captioner gives for this video alone
     assert capfilt.dedup_exact(cap.generate(frames, sample=False, num_beams=3, max_length=20, min_length=5)) == item["unfiltered_text"]
+
+
+def test_capfilt_generation_mode_sample(cuda):
+    """generation_mode "sample" (run_video_CapFilt.py:103-104 -> blip.py:139-148): captions are strings after the prompt, the
+    run is reproducible under torch.manual_seed like the reference's torch.multinomial draws, and a different seed gives
+    different captions."""
+    cap, itm = _models(cuda)
+    frames = capfilt.process_frames(torch.as_tensor(_loader("/v/video1.mp4", "uniform", 4)).to(cuda), 224)
+    torch.manual_seed(5)
+    a = cap.generate(frames, sample=True, top_p=0.9, max_length=20, min_length=5)
+    torch.manual_seed(5)
+    b = cap.generate(frames, sample=True, top_p=0.9, max_length=20, min_length=5)
+    torch.manual_seed(6)
+    c = cap.generate(frames, sample=True, top_p=0.9, max_length=20, min_length=5)
+    assert a == b and a != c
+    assert len(a) == 4 and all(isinstance(s, str) and s and not s.startswith("a picture of") for s in a)
+    assert all(1 <= len(s.split()) <= 16 for s in a)              # max_length 20 minus the 4 prompt tokens
+    assert capfilt.caption_frames(cap, frames, mode="sample") is not None
+    data = _data(3)                                               # video 2 cannot be decoded and is skipped
+    torch.manual_seed(7)
+    capfilt.CapFilt(data, dict(CONFIG, generation_mode="sample"), cuda, captioner=cap, filterer=itm, frame_loader=_loader, video_batch=2)
+    assert all(1 <= len(d["unfiltered_text"]) <= 4 for d in data[:2]) and "unfiltered_text" not in data[2]
